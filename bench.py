@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-steps/s of the fused env-step kernel (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N=1 runs in-process; for N>1 launch with torch.distributed.run (one rank per GPU, NCCL only for
+the barrier / max-over-ranks reduction -- the env path has no data-path collective: envs shard).
+Workload (config.workload): the C5 slice of BASELINE.json -- 131072 envs per GPU (1 Mi envs at 8
+GPUs) x 1 LB agent x 64 servers, 128-slot reservoirs, synthetic Poisson flows (128 flows/s per
+agent, rho=0.8), random policy.  A "step" is one launch of step_kernel over all envs of the rank.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (envs/GPU, agents, servers/agent, flows/s per agent, K)
+    "c5": dict(envs=131072, agents=1, servers=64, rate=128.0, K=128),
+    "c2": dict(envs=4096, agents=1, servers=16, rate=32.0, K=128),
+    "c3env": dict(envs=16384, agents=2, servers=32, rate=128.0, K=128),
+}
+RHO = 0.8
+DT = 0.25
+TS_BYTES = 4  # float32 timestamps (src/vpp/lb/shm.h:23-25)
+
+
+def algorithmic_bytes_per_agent_step(S, K, F, T=TS_BYTES, log=False, replay=False):
+    """S*(2K(4+T)+92) + F*(8+2(4+T)+4[log]+8[replay]) + S*4 + 5."""
+    return S * (2 * K * (4 + T) + 92) + F * (8 + 2 * (4 + T) + 4 * log + 8 * replay) + S * 4 + 5
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(wl, n_envs, burnin, budget_s, threads, arrivals=None, seed=77):
+    """Time the CPU restatement of the same env step (oracle/flow_oracle.c, pthreads) on a bounded
+    sample of envs of the same workload.  Returns (agent_steps_per_s, steps_timed, threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import flow_oracle as fo
+    S, A = wl["servers"], wl["agents"]
+    threads = threads or fo.max_threads()
+    speeds = np.where(np.arange(S * A) % 2 == 0, 1.0, 2.0).astype(np.float32)
+    mean_work = RHO * speeds[:S].sum() / wl["rate"]
+    rng = np.random.RandomState(seed)
+    horizon = (burnin + 400) * DT
+    envs = []
+    for e in range(n_envs):
+        if arrivals is not None:
+            streams = arrivals[e]
+        else:
+            streams = []
+            for _ in range(A):
+                n = int(wl["rate"] * horizon * 1.2) + 64
+                t = np.cumsum(rng.exponential(1.0 / wl["rate"], n))
+                t = t[t < horizon].astype(np.float32)
+                streams.append({"time": t, "work": rng.exponential(mean_work, len(t)).astype(np.float32)})
+        envs.append(fo.FlowEnv(A, S, speeds, streams, reservoir_k=wl["K"], max_steps=10 ** 9))
+    acts = rng.randint(0, 3, (8, n_envs, S * A)).astype(np.int32)
+    for k in range(burnin):
+        fo.step_batch(envs, acts[k % 8], threads)
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < 400 - 1:
+        fo.step_batch(envs, acts[steps % 8], threads)
+        steps += 1
+        if time.perf_counter() - t0 > budget_s and steps >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return n_envs * A * steps / dt, steps, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference path's CPU implementation (oracle port; the reference has no
+    flow-level step of its own) on all host threads, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import flow_oracle as fo
+    threads = fo.max_threads()
+    n_envs = max(threads * 4, 32)
+    # K timed steps + W warm-up on the sample, after the same burn-in as the GPU arm
+    S, A = wl["servers"], wl["agents"]
+    speeds = np.where(np.arange(S * A) % 2 == 0, 1.0, 2.0).astype(np.float32)
+    mean_work = RHO * speeds[:S].sum() / wl["rate"]
+    rng = np.random.RandomState(77)
+    total = args.burnin + args.warmup + args.steps
+    horizon = (total + 2) * DT
+    envs = []
+    for e in range(n_envs):
+        streams = []
+        for _ in range(A):
+            n = int(wl["rate"] * horizon * 1.2) + 64
+            t = np.cumsum(rng.exponential(1.0 / wl["rate"], n))
+            t = t[t < horizon].astype(np.float32)
+            streams.append({"time": t, "work": rng.exponential(mean_work, len(t)).astype(np.float32)})
+        envs.append(fo.FlowEnv(A, S, speeds, streams, reservoir_k=wl["K"], max_steps=10 ** 9))
+    acts = rng.randint(0, 3, (8, n_envs, S * A)).astype(np.int32)
+    for k in range(args.burnin + args.warmup):
+        fo.step_batch(envs, acts[k % 8], threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        fo.step_batch(envs, acts[k % 8], threads)
+    dt = time.perf_counter() - t0
+    value = n_envs * A * args.steps / dt
+    sample = f"{n_envs} envs x {A} agent x {S} servers, {args.steps} steps after {args.burnin}+{args.warmup} untimed"
+    print(json.dumps({
+        "impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, wl),
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, wl):
+    return {"workload": f"{args.workload}: {wl['envs']} envs/GPU x {wl['agents']} LB agent x {wl['servers']} servers, "
+                        f"K={wl['K']}-slot reservoirs, Poisson {wl['rate']:.0f} flows/s/agent, rho={RHO}, random policy, SED",
+            "envs_per_gpu": wl["envs"], "agents": wl["agents"], "servers_per_agent": wl["servers"],
+            "reservoir_k": wl["K"], "flows_per_s_per_agent": wl["rate"], "dt_s": DT,
+            "burnin_steps": args.burnin,
+            "l2_policy": "per-step working set (>17 GB of reservoirs per GPU) far exceeds the 126 MB L2",
+            "parallelism": f"env-sharded x{args.gpus} (no data-path collective)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from marllb_b200 import VecLoadBalanceEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs:
+        wl["envs"] = args.envs
+    E, A, S, K = wl["envs"], wl["agents"], wl["servers"], wl["K"]
+    e2e_steps = min(args.steps, args.e2e_steps)
+    total_steps = args.burnin + args.warmup + args.steps + 3 + e2e_steps
+    env = VecLoadBalanceEnv(E, num_servers=S, num_agents=A, reservoir_capacity=K, max_steps=10 ** 9,
+                            action_dtype="uint8", env_id_base=rank * E, device=local,
+                            feature_cache=not args.no_feature_cache)
+    speeds = np.where(np.arange(S * A) % 2 == 0, 1.0, 2.0).astype(np.float32)
+    env.set_speeds(speeds)
+    mean_work = RHO * float(speeds[:S].sum()) / wl["rate"]
+    env.gen_poisson(wl["rate"], mean_work, (total_steps + 1) * DT, seed=1234)
+    env.reset()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99 + rank)
+    pool = [torch.randint(0, 3, (E, S * A), generator=g, device="cuda", dtype=torch.uint8) for _ in range(8)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.burnin + args.warmup):
+        env.step(pool[k % 8])
+    env.check_status()
+    cur0 = env.get_state("arr_cursor").astype(np.int64).sum()
+    l0 = env.launch_count
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        env.step(pool[k % 8])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = env.launch_count - l0
+    flows = env.get_state("arr_cursor").astype(np.int64).sum() - cur0
+    env.check_status()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    fl = torch.tensor([float(flows)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    value = world * E * A * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned H2D actions, D2H obs/reward/done)
+    h_act = [p.cpu().numpy() for p in pool[:2]]
+    env.step_host(h_act[0])  # allocates pinned buffers, untimed
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        env.step_host(h_act[k % 2])
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * A * e2e_steps / float(te.item())
+    h2d, d2h = env.e2e_bytes
+
+    if rank == 0:
+        F = float(fl.item()) / (world * E * A * args.steps)
+        bytes_as = algorithmic_bytes_per_agent_step(S, K, F)
+        peak, which = measured_peaks()
+        # dominant kernel = step_kernel, the only launch in the timed region: avg launch = ms/steps (rank-local)
+        achieved = bytes_as * E * A / (ms * 1e-3 / args.steps) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload)
+        out = {
+            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, wl),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                         "kernel": "mlb::step_kernel<SED>", "algorithmic_bytes_per_agent_step": bytes_as,
+                         "flows_per_agent_step": F},
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            del env
+            torch.cuda.empty_cache()
+            v, steps, cores = cpu_oracle_rate(wl, n_envs=0 or max(4 * (os.cpu_count() or 1), 32),
+                                              burnin=args.burnin, budget_s=args.cpu_budget, threads=0)
+            out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                                   "sample": f"{max(4 * (os.cpu_count() or 1), 32)} envs of the same workload, "
+                                             f"{steps} steps after {args.burnin} burn-in steps, oracle/flow_oracle.c on {cores} threads"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--burnin", type=int, default=256, help="untimed steps that bring reservoirs to steady state")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-feature-cache", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,601 @@
+// C ABI of the env path (include/marllb_b200.h): handle, device state, launches.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mlb_mt19937.h"
+#include "mlb_step_kernel.cuh"
+
+using namespace mlb;
+
+struct mlb_env {
+    mlb_config cfg;
+    DevState d;
+    int device = 0;
+    std::string err;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+    // arrival storage (owned)
+    float *arr_time = nullptr, *arr_work = nullptr, *arr_u = nullptr;
+    int32_t* arr_bucket = nullptr;
+    int64_t* arr_off = nullptr;
+    int32_t* arr_n = nullptr;
+    int64_t arr_total = 0;
+    std::vector<int64_t> h_off;
+    std::vector<int32_t> h_n;
+    bool have_arrivals = false;
+    void* d_action = nullptr;
+    size_t action_bytes = 0;
+    uint8_t* d_mask = nullptr;
+    size_t smem_bytes = 0;
+    int epb = 1, threads = 32;
+    size_t state_bytes[MLB_F_COUNT_] = {0};
+    void* state_ptr[MLB_F_COUNT_] = {nullptr};
+};
+
+static std::string g_create_err;
+
+static int fail(mlb_env* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CK(h, call)                                                                            \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(h, MLB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(mlb_env* h, T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+    if (e == cudaSuccess) {
+        h->allocs.push_back(q);
+        *p = reinterpret_cast<T*>(q);
+    }
+    return e;
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void fill_f32_kernel(float* p, size_t n, float v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// reset(): zero every per-env slice of the selected envs (env.py:186-213;
+// reservoir.py:220-225 zero-fills the sample arrays).  One block per env.
+__global__ void reset_kernel(const DevState d, const uint8_t* __restrict__ mask) {
+    const int e = blockIdx.x;
+    if (mask && !mask[e]) return;
+    const int S = d.S, tid = threadIdx.x, nt = blockDim.x;
+    const size_t sb = (size_t)e * S;
+    for (int i = tid; i < S; i += nt) {
+        d.n_on[sb + i] = 0;
+        d.last_fin[sb + i] = 0.f;
+        d.head[sb + i] = 0;
+        d.dropped[sb + i] = 0;
+    }
+    for (int i = tid; i < 2 * S; i += nt) {
+        d.res_count[(size_t)e * 2 * S + i] = 0;
+        d.res_cursor[(size_t)e * 2 * S + i] = 0;
+    }
+    const size_t rn = (size_t)S * 2 * d.KP;
+    float4* v4 = reinterpret_cast<float4*>(d.res_val + sb * 2 * d.KP);
+    float4* t4 = reinterpret_cast<float4*>(d.res_ts + sb * 2 * d.KP);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = tid; i < rn / 4; i += nt) {
+        v4[i] = z;
+        t4[i] = z;
+    }
+    for (int i = tid; i < S * MLB_OBS_COLS; i += nt) d.obs[sb * MLB_OBS_COLS + i] = 0.f;
+    for (int i = tid; i < d.A; i += nt) d.arr_cur[(size_t)e * d.A + i] = 0;
+    if (tid == 0) {
+        d.reward[e] = 0.0;
+        d.done[e] = 0;
+        d.step[e] = 0;
+    }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// One warp per (env, agent) stream: exponential inter-arrivals (rate/s) kept
+// while < horizon, exponential work (training_pipeline.py:141-155 semantics).
+__global__ void gen_poisson_kernel(float* __restrict__ time, float* __restrict__ work,
+                                   int32_t* __restrict__ bucket, float* __restrict__ uu,
+                                   int32_t* __restrict__ count, int n_streams, int cap, int Sa,
+                                   uint32_t stream_base, double rate, double mean_work,
+                                   double horizon, uint64_t seed) {
+    const int lane = threadIdx.x & 31;
+    const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sidx >= n_streams) return;
+    const size_t base = (size_t)sidx * cap;
+    double t0 = 0.0;
+    int n = 0;
+    for (int chunk = 0; n < cap && t0 < horizon; chunk++) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)(chunk * 32 + lane), stream_base + (uint32_t)sidx, 0x4d4c4221u, 0u,
+                      (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const double u1 = ((double)r[0] + 0.5) * (1.0 / 4294967296.0);
+        const double u2 = ((double)r[1] + 0.5) * (1.0 / 4294967296.0);
+        double dtv = -log(u1) / rate;
+        // inclusive warp scan of inter-arrival gaps
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(MLB_FULL, dtv, o);
+            if (lane >= o) dtv += y;
+        }
+        const double t = t0 + dtv;
+        const bool keep = (t < horizon) && (n + lane < cap);
+        if (keep) {
+            time[base + n + lane] = (float)t;
+            work[base + n + lane] = (float)(-log(u2) * mean_work);
+            if (bucket) {
+                bucket[base + n + lane] = (int32_t)(r[2] % (uint32_t)Sa);
+                uu[base + n + lane] = (float)(r[3] >> 8) * (1.0f / 16777216.0f);
+            }
+        }
+        n += __popc(__ballot_sync(MLB_FULL, keep));
+        t0 = __shfl_sync(MLB_FULL, t, 31);
+    }
+    if (lane == 0) count[sidx] = n;
+}
+
+// ------------------------------------------------------------------ helpers
+static int launch_cfg(mlb_env* h) {
+    const mlb_config& c = h->cfg;
+    const int A = c.num_agents;
+    h->epb = A >= 4 ? 1 : 4 / A;
+    h->threads = 32 * A * h->epb;
+    const int SP = (c.servers_per_agent + 31) & ~31;
+    const bool alias = c.policy == MLB_POLICY_ALIAS;
+    h->smem_bytes = (size_t)(h->threads / 32) * warp_smem_bytes(SP, alias) +
+                    (size_t)h->epb * 2 * h->d.S * 4;
+    if (h->smem_bytes > 227 * 1024) return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)", h->smem_bytes);
+    if (h->threads > 1024) return fail(h, MLB_EINVAL, "num_agents > 32 not supported");
+    cudaError_t e;
+    switch (c.policy) {
+    case MLB_POLICY_SED:
+        e = cudaFuncSetAttribute(step_kernel<MLB_POLICY_SED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        break;
+    case MLB_POLICY_LSQ:
+        e = cudaFuncSetAttribute(step_kernel<MLB_POLICY_LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        break;
+    default:
+        e = cudaFuncSetAttribute(step_kernel<MLB_POLICY_ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        break;
+    }
+    if (e != cudaSuccess) return fail(h, MLB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return MLB_OK;
+}
+
+static size_t action_elem(int kind) { return kind == MLB_ACTION_DISCRETE_U8 ? 1 : 4; }
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int mlb_abi_version(void) { return MLB_ABI_VERSION; }
+
+int mlb_config_default(mlb_config* c) {
+    if (!c) return MLB_EINVAL;
+    memset(c, 0, sizeof *c);
+    c->abi_version = MLB_ABI_VERSION;
+    c->device = 0;
+    c->num_envs = 1;
+    c->num_agents = 1;
+    c->servers_per_agent = 4;             // env.py:73
+    c->reservoir_k = 128;                 // reservoir.py:31
+    c->queue_cap = 160;                   // paper 4.2: 32 workers + 128 backlog
+    c->policy = MLB_POLICY_SED;
+    c->action_kind = MLB_ACTION_DISCRETE_I32;
+    c->n_discrete = 3;                    // env.py:69
+    c->discrete_weights[0] = 1.0f;
+    c->discrete_weights[1] = 1.5f;
+    c->discrete_weights[2] = 2.0f;
+    c->min_weight = 0.1f;                 // env.py:77
+    c->max_weight = 10.0f;                // env.py:76
+    c->dt = 0.25f;                        // env.py:80
+    c->decay = 0.9;                       // reservoir.py:106
+    c->reward_metric = MLB_REWARD_JAIN;   // env.py:78
+    c->reward_field = 10;                 // 'flow_duration_avg_decay', env.py:79,380
+    c->max_steps = 10000;                 // env.py:81
+    c->rng_seed_base = 0;
+    c->rng_table_len = 0;
+    c->feature_cache = 1;
+    c->record_assign = 0;
+    return MLB_OK;
+}
+
+const char* mlb_last_error(const mlb_env* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int64_t mlb_launch_count(const mlb_env* h) { return h ? h->launches : 0; }
+
+int mlb_destroy(mlb_env* h) {
+    if (!h) return MLB_OK;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return MLB_OK;
+}
+
+int mlb_create(const mlb_config* cfg, mlb_env** out) {
+    if (!cfg || !out) return fail(nullptr, MLB_EINVAL, "null argument");
+    *out = nullptr;
+    const mlb_config& c = *cfg;
+    if (c.abi_version != MLB_ABI_VERSION) return fail(nullptr, MLB_EINVAL, "abi_version %d != %d", c.abi_version, MLB_ABI_VERSION);
+    if (c.num_envs < 1 || c.num_agents < 1 || c.num_agents > 32) return fail(nullptr, MLB_EINVAL, "num_envs >= 1 and 1 <= num_agents <= 32 required");
+    if (c.servers_per_agent < 1 || c.servers_per_agent > 256) return fail(nullptr, MLB_EINVAL, "1 <= servers_per_agent <= 256 required");
+    if (c.reservoir_k < 1 || c.reservoir_k > 128) return fail(nullptr, MLB_EINVAL, "1 <= reservoir_k <= 128 required");
+    if (c.queue_cap < 1 || c.queue_cap > 65535) return fail(nullptr, MLB_EINVAL, "1 <= queue_cap <= 65535 required");
+    if (c.policy < 0 || c.policy > MLB_POLICY_ALIAS) return fail(nullptr, MLB_EINVAL, "unknown policy %d", c.policy);
+    if (c.action_kind < 0 || c.action_kind > MLB_ACTION_DISCRETE_U8) return fail(nullptr, MLB_EINVAL, "Unknown action_type: %d", c.action_kind);  // env.py:184
+    if (c.action_kind != MLB_ACTION_CONTINUOUS_F32 && (c.n_discrete < 1 || c.n_discrete > 8)) return fail(nullptr, MLB_EINVAL, "1 <= n_discrete <= 8 required");
+    if (c.reward_metric < 0 || c.reward_metric >= MLB_REWARD_COUNT_) return fail(nullptr, MLB_EINVAL, "Unsupported metric: %d", c.reward_metric);  // rewards.py:321-323
+    if (c.reward_field < 0 || c.reward_field > 10) return fail(nullptr, MLB_EINVAL, "reward_field must be an obs column 0..10");
+    if (!(c.dt > 0.f) || !(c.decay > 0.0)) return fail(nullptr, MLB_EINVAL, "dt and decay must be positive");
+
+    mlb_env* h = new (std::nothrow) mlb_env();
+    if (!h) return fail(nullptr, MLB_ENOMEM, "host allocation failed");
+    h->cfg = c;
+    h->device = c.device;
+    auto bail = [&](int code) {
+        g_create_err = h->err;
+        mlb_destroy(h);
+        return code;
+    };
+#define CKC(call)                                                                   \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            fail(h, e__ == cudaErrorMemoryAllocation ? MLB_ENOMEM : MLB_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+            return bail(e__ == cudaErrorMemoryAllocation ? MLB_ENOMEM : MLB_ECUDA); \
+        }                                                                           \
+    } while (0)
+
+    CKC(cudaSetDevice(c.device));
+    DevState& d = h->d;
+    memset(&d, 0, sizeof d);
+    d.E = c.num_envs; d.A = c.num_agents; d.Sa = c.servers_per_agent; d.S = d.A * d.Sa;
+    d.K = c.reservoir_k; d.KP = (c.reservoir_k + 31) & ~31; d.Q = c.queue_cap;
+    d.policy = c.policy; d.action_kind = c.action_kind; d.n_discrete = c.n_discrete;
+    d.reward_metric = c.reward_metric; d.reward_field = c.reward_field; d.max_steps = c.max_steps;
+    d.L = c.rng_table_len > 0 ? c.rng_table_len : 65536;
+    d.feature_cache = c.feature_cache; d.record_assign = c.record_assign;
+    for (int i = 0; i < 8; i++) d.dw[i] = c.discrete_weights[i];
+    d.min_w = c.min_weight; d.max_w = c.max_weight; d.dt = c.dt;
+    d.decay = c.decay; d.log2_decay = (float)std::log2(c.decay);
+
+    const size_t ES = (size_t)d.E * d.S;
+    CKC(dalloc(h, &d.n_on, ES));
+    CKC(dalloc(h, &d.last_fin, ES));
+    CKC(dalloc(h, &d.head, ES));
+    CKC(dalloc(h, &d.dropped, ES));
+    CKC(dalloc(h, &d.speed, ES));
+    CKC(dalloc(h, &d.res_val, ES * 2 * d.KP));
+    CKC(dalloc(h, &d.res_ts, ES * 2 * d.KP));
+    CKC(dalloc(h, &d.res_count, ES * 2));
+    CKC(dalloc(h, &d.res_cursor, ES * 2));
+    CKC(dalloc(h, &d.ring_arr, ES * d.Q));
+    CKC(dalloc(h, &d.ring_fin, ES * d.Q));
+    CKC(dalloc(h, &d.obs, ES * MLB_OBS_COLS));
+    CKC(dalloc(h, &d.reward, (size_t)d.E));
+    CKC(dalloc(h, &d.done, (size_t)d.E));
+    CKC(dalloc(h, &d.step, (size_t)d.E));
+    CKC(dalloc(h, &d.arr_cur, (size_t)d.E * d.A));
+    CKC(dalloc(h, &d.status, (size_t)1));
+    CKC(dalloc(h, &h->d_mask, (size_t)d.E));
+    h->action_bytes = ES * action_elem(c.action_kind);
+    CKC(dalloc(h, reinterpret_cast<uint8_t**>(&h->d_action), h->action_bytes));
+    CKC(cudaMemset(d.status, 0, sizeof(int)));
+
+    // RNG replay table: row j = raw MT19937 words of RandomState(seed_base + j)
+    {
+        std::vector<uint32_t> tab((size_t)d.S * d.L);
+        for (int j = 0; j < d.S; j++) {
+            MT19937 g(c.rng_seed_base + (uint32_t)j);
+            uint32_t* row = tab.data() + (size_t)j * d.L;
+            for (int i = 0; i < d.L; i++) row[i] = g.next();
+        }
+        uint32_t* t = nullptr;
+        CKC(dalloc(h, &t, tab.size()));
+        CKC(cudaMemcpy(t, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        d.mt_table = t;
+    }
+    // speeds default 1.0
+    fill_f32_kernel<<<256, 256>>>(d.speed, ES, 1.0f);
+    h->launches++;
+    CKC(cudaGetLastError());
+
+    h->state_ptr[MLB_F_N_FLOW_ON] = d.n_on;        h->state_bytes[MLB_F_N_FLOW_ON] = ES * 4;
+    h->state_ptr[MLB_F_RES_VALUES] = d.res_val;    h->state_bytes[MLB_F_RES_VALUES] = ES * 2 * d.KP * 4;
+    h->state_ptr[MLB_F_RES_TS] = d.res_ts;         h->state_bytes[MLB_F_RES_TS] = ES * 2 * d.KP * 4;
+    h->state_ptr[MLB_F_RES_COUNT] = d.res_count;   h->state_bytes[MLB_F_RES_COUNT] = ES * 2 * 4;
+    h->state_ptr[MLB_F_RES_CURSOR] = d.res_cursor; h->state_bytes[MLB_F_RES_CURSOR] = ES * 2 * 4;
+    h->state_ptr[MLB_F_DROPPED] = d.dropped;       h->state_bytes[MLB_F_DROPPED] = ES * 4;
+    h->state_ptr[MLB_F_LAST_FIN] = d.last_fin;     h->state_bytes[MLB_F_LAST_FIN] = ES * 4;
+    h->state_ptr[MLB_F_HEAD] = d.head;             h->state_bytes[MLB_F_HEAD] = ES * 4;
+    h->state_ptr[MLB_F_STEP] = d.step;             h->state_bytes[MLB_F_STEP] = (size_t)d.E * 4;
+    h->state_ptr[MLB_F_OBS] = d.obs;               h->state_bytes[MLB_F_OBS] = ES * MLB_OBS_COLS * 4;
+    h->state_ptr[MLB_F_ARR_CURSOR] = d.arr_cur;    h->state_bytes[MLB_F_ARR_CURSOR] = (size_t)d.E * d.A * 4;
+
+    int rc = launch_cfg(h);
+    if (rc != MLB_OK) return bail(rc);
+    rc = mlb_reset(h, nullptr, nullptr);
+    if (rc != MLB_OK) return bail(rc);
+    CKC(cudaDeviceSynchronize());
+    *out = h;
+    return MLB_OK;
+#undef CKC
+}
+
+int mlb_set_speeds(mlb_env* h, const float* speeds, int64_t n, int loc, void* stream) {
+    if (!h || !speeds) return fail(h, MLB_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    const DevState& d = h->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    const cudaMemcpyKind kind = loc == MLB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (n == (int64_t)d.E * d.S) {
+        CK(h, cudaMemcpyAsync(d.speed, speeds, (size_t)n * 4, kind, st));
+    } else if (n == d.S) {
+        std::vector<float> rep;
+        if (loc == MLB_HOST) {
+            rep.resize((size_t)d.E * d.S);
+            for (int e = 0; e < d.E; e++) memcpy(rep.data() + (size_t)e * d.S, speeds, (size_t)d.S * 4);
+            CK(h, cudaMemcpyAsync(d.speed, rep.data(), rep.size() * 4, cudaMemcpyHostToDevice, st));
+            CK(h, cudaStreamSynchronize(st));
+        } else {
+            for (int e = 0; e < d.E; e++)
+                CK(h, cudaMemcpyAsync(d.speed + (size_t)e * d.S, speeds, (size_t)d.S * 4, kind, st));
+        }
+    } else {
+        return fail(h, MLB_EINVAL, "speeds: n must be S=%d or E*S=%lld", d.S, (long long)d.E * d.S);
+    }
+    return MLB_OK;
+}
+
+static int alloc_arrivals(mlb_env* h, int64_t total, bool alias) {
+    DevState& d = h->d;
+    if (total > h->arr_total || (alias && !h->arr_bucket)) {
+        // grow-only; old buffers stay in the handle's free list
+        CK(h, dalloc(h, &h->arr_time, (size_t)total));
+        CK(h, dalloc(h, &h->arr_work, (size_t)total));
+        if (alias) {
+            CK(h, dalloc(h, &h->arr_bucket, (size_t)total));
+            CK(h, dalloc(h, &h->arr_u, (size_t)total));
+        }
+        if (h->cfg.record_assign) {
+            int32_t* a = nullptr;
+            CK(h, dalloc(h, &a, (size_t)total));
+            d.assign = a;
+        }
+        h->arr_total = total;
+    }
+    if (!h->arr_off) {
+        CK(h, dalloc(h, &h->arr_off, (size_t)d.E * d.A));
+        CK(h, dalloc(h, &h->arr_n, (size_t)d.E * d.A));
+    }
+    d.arr_time = h->arr_time; d.arr_work = h->arr_work;
+    d.arr_bucket = h->arr_bucket; d.arr_u = h->arr_u;
+    d.arr_off = h->arr_off; d.arr_n = h->arr_n;
+    return MLB_OK;
+}
+
+int mlb_load_arrivals(mlb_env* h, const float* time, const float* work, const int32_t* bucket,
+                      const float* u, const int64_t* offsets, int loc, void* stream) {
+    if (!h || !time || !work || !offsets) return fail(h, MLB_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    DevState& d = h->d;
+    const bool alias = h->cfg.policy == MLB_POLICY_ALIAS;
+    if (alias && (!bucket || !u)) return fail(h, MLB_EINVAL, "alias policy needs pre-drawn bucket/u arrays");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int EA = d.E * d.A;
+    std::vector<int64_t> off(EA + 1);
+    if (loc == MLB_DEVICE) {
+        CK(h, cudaMemcpy(off.data(), offsets, (size_t)(EA + 1) * 8, cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(off.data(), offsets, (size_t)(EA + 1) * 8);
+    }
+    const int64_t total = off[EA];
+    h->h_off.assign(off.begin(), off.begin() + EA);
+    h->h_n.resize(EA);
+    for (int i = 0; i < EA; i++) {
+        const int64_t n = off[i + 1] - off[i];
+        if (n < 0 || n > 0x7fffffff) return fail(h, MLB_EINVAL, "offsets must be non-decreasing (stream %d)", i);
+        h->h_n[i] = (int32_t)n;
+    }
+    int rc = alloc_arrivals(h, total > 0 ? total : 1, alias);
+    if (rc != MLB_OK) return rc;
+    const cudaMemcpyKind kind = loc == MLB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (total > 0) {
+        CK(h, cudaMemcpyAsync(h->arr_time, time, (size_t)total * 4, kind, st));
+        CK(h, cudaMemcpyAsync(h->arr_work, work, (size_t)total * 4, kind, st));
+        if (alias) {
+            CK(h, cudaMemcpyAsync(h->arr_bucket, bucket, (size_t)total * 4, kind, st));
+            CK(h, cudaMemcpyAsync(h->arr_u, u, (size_t)total * 4, kind, st));
+        }
+    }
+    CK(h, cudaMemcpyAsync(h->arr_off, h->h_off.data(), (size_t)EA * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->arr_n, h->h_n.data(), (size_t)EA * 4, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemsetAsync(d.arr_cur, 0, (size_t)EA * 4, st));
+    CK(h, cudaStreamSynchronize(st));  // host staging vectors must outlive the copies
+    h->have_arrivals = true;
+    return MLB_OK;
+}
+
+int mlb_gen_poisson(mlb_env* h, double rate, double mean_work, double horizon, uint64_t seed, void* stream) {
+    if (!h) return MLB_EINVAL;
+    if (!(rate > 0) || !(mean_work > 0) || !(horizon > 0)) return fail(h, MLB_EINVAL, "rate, mean_work, horizon must be positive");
+    CK(h, cudaSetDevice(h->device));
+    DevState& d = h->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int EA = d.E * d.A;
+    const double mu = rate * horizon;
+    const int cap = (int)(mu + 8.0 * std::sqrt(mu) + 64.0);
+    const bool alias = h->cfg.policy == MLB_POLICY_ALIAS;
+    int rc = alloc_arrivals(h, (int64_t)EA * cap, alias);
+    if (rc != MLB_OK) return rc;
+    h->h_off.resize(EA);
+    for (int i = 0; i < EA; i++) h->h_off[i] = (int64_t)i * cap;
+    CK(h, cudaMemcpyAsync(h->arr_off, h->h_off.data(), (size_t)EA * 8, cudaMemcpyHostToDevice, st));
+    const int threads = 128;
+    const int blocks = (int)(((int64_t)EA * 32 + threads - 1) / threads);
+    gen_poisson_kernel<<<blocks, threads, 0, st>>>(h->arr_time, h->arr_work, alias ? h->arr_bucket : nullptr,
+                                                   alias ? h->arr_u : nullptr, h->arr_n, EA, cap, d.Sa,
+                                                   (uint32_t)h->cfg.env_id_base * (uint32_t)d.A,
+                                                   rate, mean_work, horizon, seed);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemsetAsync(d.arr_cur, 0, (size_t)EA * 4, st));
+    h->h_n.resize(EA);
+    CK(h, cudaMemcpyAsync(h->h_n.data(), h->arr_n, (size_t)EA * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    h->have_arrivals = true;
+    return MLB_OK;
+}
+
+int mlb_get_arrivals(mlb_env* h, int32_t env, int32_t agent, float* time, float* work,
+                     int32_t* bucket, float* u, int64_t cap, int64_t* n) {
+    if (!h || !n) return MLB_EINVAL;
+    if (!h->have_arrivals) return fail(h, MLB_ESTATE, "no arrivals loaded");
+    const DevState& d = h->d;
+    if (env < 0 || env >= d.E || agent < 0 || agent >= d.A) return fail(h, MLB_EINVAL, "env/agent out of range");
+    CK(h, cudaSetDevice(h->device));
+    const int ea = env * d.A + agent;
+    const int64_t cnt = h->h_n[ea], off = h->h_off[ea];
+    *n = cnt;
+    const int64_t m = cnt < cap ? cnt : cap;
+    if (m > 0) {
+        if (time) CK(h, cudaMemcpy(time, h->arr_time + off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        if (work) CK(h, cudaMemcpy(work, h->arr_work + off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        if (bucket && h->arr_bucket) CK(h, cudaMemcpy(bucket, h->arr_bucket + off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        if (u && h->arr_u) CK(h, cudaMemcpy(u, h->arr_u + off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    }
+    return MLB_OK;
+}
+
+int mlb_reset(mlb_env* h, const uint8_t* env_mask, void* stream) {
+    if (!h) return MLB_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* dm = nullptr;
+    if (env_mask) {
+        CK(h, cudaMemcpyAsync(h->d_mask, env_mask, (size_t)h->d.E, cudaMemcpyHostToDevice, st));
+        dm = h->d_mask;
+    }
+    reset_kernel<<<h->d.E, 256, 0, st>>>(h->d, dm);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return MLB_OK;
+}
+
+int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, double* out_reward,
+             uint8_t* out_done, int out_loc, void* stream) {
+    if (!h || !action) return fail(h, MLB_EINVAL, "null argument");
+    if (!h->have_arrivals) return fail(h, MLB_ESTATE, "mlb_step before mlb_load_arrivals / mlb_gen_poisson");
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevState& d = h->d;
+    const void* dact = action;
+    if (action_loc == MLB_HOST) {
+        CK(h, cudaMemcpyAsync(h->d_action, action, h->action_bytes, cudaMemcpyHostToDevice, st));
+        dact = h->d_action;
+    }
+    const int blocks = (d.E + h->epb - 1) / h->epb;
+    switch (d.policy) {
+    case MLB_POLICY_SED: step_kernel<MLB_POLICY_SED><<<blocks, h->threads, h->smem_bytes, st>>>(d, dact); break;
+    case MLB_POLICY_LSQ: step_kernel<MLB_POLICY_LSQ><<<blocks, h->threads, h->smem_bytes, st>>>(d, dact); break;
+    default: step_kernel<MLB_POLICY_ALIAS><<<blocks, h->threads, h->smem_bytes, st>>>(d, dact); break;
+    }
+    h->launches++;
+    CK(h, cudaGetLastError());
+    const cudaMemcpyKind kind = out_loc == MLB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t ES = (size_t)d.E * d.S;
+    if (out_obs) CK(h, cudaMemcpyAsync(out_obs, d.obs, ES * MLB_OBS_COLS * 4, kind, st));
+    if (out_reward) CK(h, cudaMemcpyAsync(out_reward, d.reward, (size_t)d.E * 8, kind, st));
+    if (out_done) CK(h, cudaMemcpyAsync(out_done, d.done, (size_t)d.E, kind, st));
+    return MLB_OK;
+}
+
+int mlb_get_assignments(mlb_env* h, int32_t* dst, int64_t n, int loc, void* stream) {
+    if (!h || !dst) return MLB_EINVAL;
+    if (!h->d.assign) return fail(h, MLB_ESTATE, "record_assign was not enabled");
+    if (n > h->arr_total) return fail(h, MLB_EINVAL, "n exceeds the number of loaded flows");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaMemcpyAsync(dst, h->d.assign, (size_t)n * 4,
+                          loc == MLB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                          (cudaStream_t)stream));
+    if (loc == MLB_HOST) CK(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return MLB_OK;
+}
+
+int mlb_device_ptr(mlb_env* h, int what, void** ptr, size_t* bytes) {
+    if (!h || !ptr) return MLB_EINVAL;
+    const DevState& d = h->d;
+    size_t b = 0;
+    void* p = nullptr;
+    if (what >= 0 && what < MLB_F_COUNT_) { p = h->state_ptr[what]; b = h->state_bytes[what]; }
+    else if (what == MLB_PTR_OBS) { p = d.obs; b = (size_t)d.E * d.S * MLB_OBS_COLS * 4; }
+    else if (what == MLB_PTR_REWARD) { p = d.reward; b = (size_t)d.E * 8; }
+    else if (what == MLB_PTR_DONE) { p = d.done; b = (size_t)d.E; }
+    else if (what == MLB_PTR_ASSIGN) { p = d.assign; b = (size_t)h->arr_total * 4; }
+    else return fail(h, MLB_EINVAL, "unknown pointer id %d", what);
+    *ptr = p;
+    if (bytes) *bytes = b;
+    return MLB_OK;
+}
+
+int mlb_get_state(mlb_env* h, int field, void* dst, size_t bytes, int loc) {
+    if (!h || !dst) return MLB_EINVAL;
+    if (field < 0 || field >= MLB_F_COUNT_) return fail(h, MLB_EINVAL, "unknown field %d", field);
+    if (bytes != h->state_bytes[field]) return fail(h, MLB_EINVAL, "field %d is %zu bytes, caller passed %zu", field, h->state_bytes[field], bytes);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(dst, h->state_ptr[field], bytes, loc == MLB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+    return MLB_OK;
+}
+
+int mlb_status(mlb_env* h, void* stream) {
+    if (!h) return MLB_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    int st = 0;
+    CK(h, cudaMemcpyAsync(&st, h->d.status, sizeof st, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(h, cudaStreamSynchronize((cudaStream_t)stream));
+    if (st & ST_ERR_RNG) return fail(h, MLB_ERNG, "replayed MT19937 stream exhausted: raise rng_table_len (now %d words per seed)", h->d.L);
+    if (st & ST_ERR_ACTION) return fail(h, MLB_EACTION, "discrete action outside [0, %d)", h->d.n_discrete);
+    return MLB_OK;
+}
+
+int mlb_mt19937_fill(uint32_t seed, uint32_t* out, int64_t n) {
+    if (!out || n < 0) return MLB_EINVAL;
+    MT19937 g(seed);
+    for (int64_t i = 0; i < n; i++) out[i] = g.next();
+    return MLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Common device helpers for the marllb_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MLB_FULL 0xffffffffu
+#define MLB_OBS_COLS 11
+#define MLB_INF __int_as_float(0x7f800000)
+
+namespace mlb {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// total order on floats as unsigned ints (for REDUX-based argmin)
+__device__ __forceinline__ uint32_t f32_orderable(float f) {
+    uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MLB_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MLB_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(MLB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(MLB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(MLB_FULL, v, o));
+    return v;
+}
+
+// inclusive warp scan (Kogge-Stone)
+__device__ __forceinline__ float warp_scan_incl(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(MLB_FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// streaming (evict-first) global accesses for data touched once per step
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    return __ldcs(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+    return __ldcs(reinterpret_cast<const float2*>(p));
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) { return __ldcs(p); }
+
+}  // namespace mlb

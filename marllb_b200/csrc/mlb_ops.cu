@@ -1,0 +1,198 @@
+// Stand-alone batched pieces of the hot path behind the C ABI:
+//   ReservoirSampler.add / get_features (problem-01-reservoir-sampling/src/reservoir.py)
+//   fairness metrics (problem-03-rl-environment/src/rewards.py)
+//   legacy random observation (problem-03-rl-environment/src/env.py:425-448)
+#include <cuda_runtime.h>
+
+#include "mlb_step_kernel.cuh"
+
+using namespace mlb;
+
+// One thread per reservoir: adds are sequential within a reservoir by definition.
+__global__ void reservoir_add_kernel(float* __restrict__ values, float* __restrict__ ts,
+                                     uint32_t* __restrict__ count, uint32_t* __restrict__ cursor,
+                                     const uint32_t* __restrict__ mt_table,
+                                     const int32_t* __restrict__ seed_row, int L, int R, int K, int KP,
+                                     const float* __restrict__ add_v, const float* __restrict__ add_t,
+                                     const int32_t* __restrict__ n_add, int max_add,
+                                     uint8_t* __restrict__ accepted, int* status) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    uint32_t cnt = count[r], cur = cursor[r];
+    const uint32_t* row = mt_table + (size_t)seed_row[r] * L;
+    const int n = n_add[r];
+    for (int i = 0; i < n; i++) {
+        const int slot = res_draw_slot(cnt, cur, row, L, K, status);
+        cnt++;
+        if (slot >= 0) {
+            values[(size_t)r * KP + slot] = add_v[(size_t)r * max_add + i];
+            ts[(size_t)r * KP + slot] = add_t[(size_t)r * max_add + i];
+        }
+        if (accepted) accepted[(size_t)r * max_add + i] = slot >= 0;
+    }
+    count[r] = cnt;
+    cursor[r] = cur;
+}
+
+// One warp per reservoir.
+__global__ void reservoir_features_kernel(const float* __restrict__ values, const float* __restrict__ ts,
+                                          const uint32_t* __restrict__ count, int R, int K, int KP,
+                                          double decay, float log2_decay, const float* __restrict__ now,
+                                          float* __restrict__ out) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const uint32_t c = count[r];
+    const int n = c < (uint32_t)K ? (int)c : K;
+    float f[5];
+    warp_features(values + (size_t)r * KP, ts + (size_t)r * KP, n, now[r], decay, log2_decay, f);
+    float mine = f[0];
+#pragma unroll
+    for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
+    if (lane < 5) out[(size_t)r * 5 + lane] = mine;
+}
+
+// One warp per row of values.
+__global__ void reward_metric_kernel(int metric, const double* __restrict__ values,
+                                     const int32_t* __restrict__ n, int B, int stride,
+                                     double* __restrict__ out) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    double r;
+    if (n[b] == 0) {
+        // empty-list conventions of the bare metric functions (rewards.py:49-50,91-92,...)
+        r = metric == MLB_REWARD_JAIN ? 1.0 : 0.0;
+    } else {
+        r = reward_staged<double>(metric, values + (size_t)b * stride, nullptr, n[b]);
+    }
+    if ((threadIdx.x & 31) == 0) out[b] = r;
+}
+
+// ---- device MT19937, state [E][625] (624 words + position) -------------------
+__device__ __forceinline__ uint32_t mt_next(uint32_t* st) {
+    uint32_t pos = st[624];
+    if (pos >= 624) {
+        for (int k = 0; k < 624; k++) {
+            const uint32_t y = (st[k] & 0x80000000u) | (st[(k + 1) % 624] & 0x7fffffffu);
+            st[k] = st[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        pos = 0;
+    }
+    uint32_t y = st[pos];
+    st[624] = pos + 1;
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+__device__ __forceinline__ double mt_double(uint32_t* st) {  // random_sample
+    const uint32_t a = mt_next(st) >> 5, b = mt_next(st) >> 6;
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+
+__global__ void legacy_seed_kernel(uint32_t* __restrict__ state, const uint32_t* __restrict__ seeds, int E) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    uint32_t* st = state + (size_t)e * 625;
+    uint32_t x = seeds[e];
+    st[0] = x;
+    for (int i = 1; i < 624; i++) {
+        x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+        st[i] = x;
+    }
+    st[624] = 624;
+}
+
+// env.py:425-448: per server randint(5,20) then six uniform() draws; the derived
+// columns are float32 products (numpy >= 2 semantics, see oracle/flow_oracle.c).
+__global__ void legacy_obs_kernel(uint32_t* __restrict__ state, int E, int S, float* __restrict__ obs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    uint32_t* st = state + (size_t)e * 625;
+    for (int s = 0; s < S; s++) {
+        float* o = obs + ((size_t)e * S + s) * MLB_OBS_COLS;
+        uint32_t v;
+        do { v = mt_next(st) & 15u; } while (v > 14u);          // randint(5, 20)
+        const float c0 = (float)(5 + (int)v);
+        // uniform(lo, hi) = lo + (hi - lo) * random_sample(), no FMA contraction
+        const float c1 = (float)__dadd_rn(5.0, __dmul_rn(15.0 - 5.0, mt_double(st)));
+        const float c2 = (float)__dadd_rn(10.0, __dmul_rn(25.0 - 10.0, mt_double(st)));
+        const float c3 = (float)__dadd_rn(1.0, __dmul_rn(5.0 - 1.0, mt_double(st)));
+        const float c6 = (float)__dadd_rn(8.0, __dmul_rn(18.0 - 8.0, mt_double(st)));
+        const float c7 = (float)__dadd_rn(15.0, __dmul_rn(30.0 - 15.0, mt_double(st)));
+        const float c8 = (float)__dadd_rn(2.0, __dmul_rn(8.0 - 2.0, mt_double(st)));
+        o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+        o[4] = __fmul_rn(c1, 0.9f);
+        o[5] = __fmul_rn(c2, 0.9f);
+        o[6] = c6; o[7] = c7; o[8] = c8;
+        o[9] = __fmul_rn(c6, 0.85f);
+        o[10] = __fmul_rn(c6, 0.9f);
+    }
+}
+
+#define CKL()                                          \
+    do {                                               \
+        if (cudaGetLastError() != cudaSuccess) return MLB_ECUDA; \
+    } while (0)
+
+extern "C" {
+
+int mlb_reservoir_add(float* values, float* ts, uint32_t* count, uint32_t* cursor,
+                      const uint32_t* mt_table, const int32_t* seed_row, int32_t table_len,
+                      int32_t R, int32_t K, const float* add_v, const float* add_t,
+                      const int32_t* n_add, int32_t max_add, uint8_t* accepted, int32_t* status,
+                      void* stream) {
+    if (!values || !ts || !count || !cursor || !mt_table || !seed_row || !add_v || !add_t || !n_add || !status)
+        return MLB_EINVAL;
+    if (K < 1 || K > 128 || R < 0) return MLB_EINVAL;
+    if (R == 0) return MLB_OK;
+    const int KP = (K + 31) & ~31;
+    reservoir_add_kernel<<<(R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        values, ts, count, cursor, mt_table, seed_row, table_len, R, K, KP, add_v, add_t, n_add,
+        max_add, accepted, status);
+    CKL();
+    return MLB_OK;
+}
+
+int mlb_reservoir_features(const float* values, const float* ts, const uint32_t* count, int32_t R,
+                           int32_t K, double decay, const float* now, float* out, void* stream) {
+    if (!values || !ts || !count || !now || !out) return MLB_EINVAL;
+    if (K < 1 || K > 128 || R < 0 || !(decay > 0)) return MLB_EINVAL;
+    if (R == 0) return MLB_OK;
+    const int KP = (K + 31) & ~31;
+    const int wpb = 4;
+    reservoir_features_kernel<<<(R + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+        values, ts, count, R, K, KP, decay, (float)log2(decay), now, out);
+    CKL();
+    return MLB_OK;
+}
+
+int mlb_reward_metric(int metric, const double* values, const int32_t* n, int32_t B, int32_t stride,
+                      double* out, void* stream) {
+    if (!values || !n || !out) return MLB_EINVAL;
+    if (metric < 0 || metric >= MLB_REWARD_COUNT_) return MLB_EINVAL;
+    if (B == 0) return MLB_OK;
+    const int wpb = 4;
+    reward_metric_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(metric, values, n, B, stride, out);
+    CKL();
+    return MLB_OK;
+}
+
+int mlb_legacy_seed(uint32_t* mt_state, const uint32_t* seeds, int32_t E, void* stream) {
+    if (!mt_state || !seeds || E < 0) return MLB_EINVAL;
+    if (E == 0) return MLB_OK;
+    legacy_seed_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(mt_state, seeds, E);
+    CKL();
+    return MLB_OK;
+}
+
+int mlb_legacy_obs(uint32_t* mt_state, int32_t E, int32_t S, float* obs, void* stream) {
+    if (!mt_state || !obs || E < 0 || S < 1) return MLB_EINVAL;
+    if (E == 0) return MLB_OK;
+    legacy_obs_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(mt_state, E, S, obs);
+    CKL();
+    return MLB_OK;
+}
+
+}  // extern "C"

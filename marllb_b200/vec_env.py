@@ -1,0 +1,272 @@
+"""Batched flow-level load-balancer environment on one B200.
+
+`VecLoadBalanceEnv` is the batched counterpart of the reference's
+`LoadBalanceEnv` (simulation-mode/problem-03-rl-environment/src/env.py:41-470)
+and `MultiAgentLoadBalanceEnv` (problem-05-qmix/src/multi_agent_env.py:22-290):
+the same constructor vocabulary, `reset()` / `step(action)`, but for E
+independent env instances stepped by one fused CUDA kernel through the C ABI
+(include/marllb_b200.h).  Observations, rewards and done flags are returned as
+torch CUDA tensors that alias extension-owned buffers (valid until the next
+step); `step_host` is the end-to-end variant with pinned host buffers.
+
+PyTorch is used only for device/pinned memory and stream handles.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, check
+
+_TORCH_TYPESTR = {torch.float32: "<f4", torch.float64: "<f8", torch.uint8: "|u1",
+                  torch.int32: "<i4", torch.int64: "<i8"}
+
+
+class _DevView:
+    """Expose a raw device pointer through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, shape, dtype, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": _TORCH_TYPESTR[dtype],
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+        self._owner = owner  # keep the handle alive while views exist
+
+
+def _dptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _nptr(a) -> C.c_void_p:
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class VecLoadBalanceEnv:
+    """E independent LB envs (A agents x Sa servers each) stepped on one GPU.
+
+    Args mirror env.py:71-87 (`num_servers` = servers per agent, `action_type`,
+    `discrete_weights`, `max_weight`, `min_weight`, `reward_metric`,
+    `reward_field`, `step_interval`, `max_steps`) plus `num_envs`, `num_agents`
+    (multi_agent_env.py:44-53) and the flow-level knobs of SURVEY App. B.
+    """
+
+    def __init__(self, num_envs: int, num_servers: int = 4, num_agents: int = 1,
+                 action_type: str = "discrete", discrete_weights: Optional[Sequence[float]] = None,
+                 max_weight: float = 10.0, min_weight: float = 0.1, reward_metric: str = "jain",
+                 reward_field="flow_duration_avg_decay", step_interval: float = 0.25,
+                 max_steps: int = 10000, policy: str = "sed", reservoir_capacity: int = 128,
+                 queue_capacity: int = 160, decay: float = 0.9, seed_base: int = 0,
+                 rng_table_len: int = 65536, feature_cache: bool = True,
+                 record_assign: bool = False, action_dtype: str = "int32", env_id_base: int = 0,
+                 device: int = 0):
+        if action_type not in ("discrete", "continuous"):
+            raise ValueError(f"Unknown action_type: {action_type}")          # env.py:184
+        if reward_metric not in _lib.METRICS:
+            raise ValueError(f"Unsupported metric: {reward_metric}. "
+                             f"Supported: {list(_lib.METRICS.keys())}")      # rewards.py:321-323
+        if policy not in _lib.POLICIES:
+            raise ValueError(f"Unknown policy: {policy}")
+        if isinstance(reward_field, str):
+            if reward_field not in _lib.FEATURE_NAMES:
+                raise ValueError(f"Unknown reward_field: {reward_field}")
+            reward_field = _lib.FEATURE_NAMES.index(reward_field)
+        self._L = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("marllb_b200 needs a CUDA device (there is no CPU fallback)")
+        cfg = Config()
+        check(self._L.mlb_config_default(C.byref(cfg)))
+        cfg.device = device
+        cfg.num_envs, cfg.num_agents, cfg.servers_per_agent = num_envs, num_agents, num_servers
+        cfg.reservoir_k, cfg.queue_cap = reservoir_capacity, queue_capacity
+        cfg.policy = _lib.POLICIES[policy]
+        if action_type == "continuous":
+            cfg.action_kind = _lib.ACTION_CONTINUOUS_F32
+        else:
+            cfg.action_kind = _lib.ACTION_DISCRETE_U8 if action_dtype == "uint8" else _lib.ACTION_DISCRETE_I32
+        dw = list(discrete_weights) if discrete_weights else [1.0, 1.5, 2.0]   # env.py:69
+        if len(dw) > 8:
+            raise ValueError("at most 8 discrete weight levels")
+        cfg.n_discrete = len(dw)
+        for i, w in enumerate(dw):
+            cfg.discrete_weights[i] = w
+        cfg.min_weight, cfg.max_weight = min_weight, max_weight
+        cfg.dt, cfg.decay = step_interval, decay
+        cfg.reward_metric, cfg.reward_field = _lib.METRICS[reward_metric], int(reward_field)
+        cfg.max_steps = max_steps
+        cfg.rng_seed_base, cfg.rng_table_len = seed_base, rng_table_len
+        cfg.feature_cache, cfg.record_assign = int(feature_cache), int(record_assign)
+        cfg.env_id_base = env_id_base
+        self.cfg = cfg
+        self.num_envs, self.num_agents, self.servers_per_agent = num_envs, num_agents, num_servers
+        self.total_servers = num_agents * num_servers
+        self.action_type, self.policy = action_type, policy
+        self.discrete_weights = dw
+        self.max_steps = max_steps
+        self.reservoir_capacity = reservoir_capacity
+        self.device = torch.device("cuda", device)
+        self._h = C.c_void_p()
+        check(self._L.mlb_create(C.byref(cfg), C.byref(self._h)))
+        E, S = num_envs, self.total_servers
+        self.obs = self._view(_lib.PTR_OBS, (E, S, 11), torch.float32)
+        self.reward = self._view(_lib.PTR_REWARD, (E,), torch.float64)
+        self.done = self._view(_lib.PTR_DONE, (E,), torch.uint8)
+        self._adtype = {_lib.ACTION_DISCRETE_I32: torch.int32, _lib.ACTION_CONTINUOUS_F32: torch.float32,
+                        _lib.ACTION_DISCRETE_U8: torch.uint8}[cfg.action_kind]
+        self._np_adtype = {torch.int32: np.int32, torch.float32: np.float32, torch.uint8: np.uint8}[self._adtype]
+        # pinned host buffers for the end-to-end path
+        self._h_action = self._h_obs = self._h_reward = self._h_done = None
+
+    # ------------------------------------------------------------------ utils
+    def _view(self, what, shape, dtype):
+        p, n = C.c_void_p(), C.c_size_t()
+        check(self._L.mlb_device_ptr(self._h, what, C.byref(p), C.byref(n)), self._h)
+        return torch.as_tensor(_DevView(p.value, shape, dtype, self), device=self.device)
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.mlb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ----------------------------------------------------------------- inputs
+    def set_speeds(self, speeds):
+        """Per-server processing speeds: shape (S,) broadcast to all envs or (E, S)."""
+        a = np.ascontiguousarray(speeds, np.float32).reshape(-1)
+        check(self._L.mlb_set_speeds(self._h, _nptr(a), a.size, _lib.HOST, self._stream()), self._h)
+
+    def load_arrivals(self, streams):
+        """streams: list over (env, agent) -- env-major -- of dicts with float32 arrays
+        'time', 'work' and, for the alias policy, 'bucket' (int32) and 'u' (float32)."""
+        EA = self.num_envs * self.num_agents
+        if len(streams) != EA:
+            raise ValueError(f"expected {EA} arrival streams (num_envs*num_agents), got {len(streams)}")
+        off = np.zeros(EA + 1, np.int64)
+        off[1:] = np.cumsum([len(s["time"]) for s in streams])
+        cat = lambda key, dt: np.ascontiguousarray(np.concatenate([np.asarray(s[key], dt) for s in streams])
+                                                   if off[-1] else np.zeros(0, dt))
+        time, work = cat("time", np.float32), cat("work", np.float32)
+        bucket = u = None
+        if self.policy == "alias":
+            bucket, u = cat("bucket", np.int32), cat("u", np.float32)
+        self.load_arrivals_csr(time, work, off, bucket, u)
+
+    def load_arrivals_csr(self, time, work, offsets, bucket=None, u=None):
+        time = np.ascontiguousarray(time, np.float32)
+        work = np.ascontiguousarray(work, np.float32)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        if bucket is not None:
+            bucket, u = np.ascontiguousarray(bucket, np.int32), np.ascontiguousarray(u, np.float32)
+        check(self._L.mlb_load_arrivals(self._h, _nptr(time), _nptr(work), _nptr(bucket), _nptr(u),
+                                        _nptr(offsets), _lib.HOST, self._stream()), self._h)
+
+    def gen_poisson(self, rate: float, mean_work: float, horizon: float, seed: int = 0):
+        """Synthetic Poisson arrivals generated on the device (training_pipeline.py:141-155)."""
+        check(self._L.mlb_gen_poisson(self._h, rate, mean_work, horizon, seed, self._stream()), self._h)
+
+    def get_arrivals(self, env: int, agent: int = 0):
+        n = C.c_int64()
+        check(self._L.mlb_get_arrivals(self._h, env, agent, None, None, None, None, 0, C.byref(n)), self._h)
+        t, w = np.empty(n.value, np.float32), np.empty(n.value, np.float32)
+        b = np.empty(n.value, np.int32) if self.policy == "alias" else None
+        u = np.empty(n.value, np.float32) if self.policy == "alias" else None
+        check(self._L.mlb_get_arrivals(self._h, env, agent, _nptr(t), _nptr(w), _nptr(b), _nptr(u),
+                                       n.value, C.byref(n)), self._h)
+        out = {"time": t, "work": w}
+        if b is not None:
+            out.update(bucket=b, u=u)
+        return out
+
+    # ------------------------------------------------------------- reset/step
+    def reset(self, mask=None):
+        """env.py:186-213 for all (or the masked) envs; returns the (E,S,11) obs view (zeros)."""
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
+            if m.shape != (self.num_envs,):
+                raise ValueError("mask must have shape (num_envs,)")
+        check(self._L.mlb_reset(self._h, _nptr(m), self._stream()), self._h)
+        if m is not None:
+            torch.cuda.current_stream().synchronize()  # pageable mask must outlive the async copy
+        return self.obs
+
+    def step(self, action):
+        """One env step for every env.  `action`: (E, S) CUDA tensor (or numpy array) of
+        int32/uint8 indices (discrete) or float32 weights (continuous).
+        Returns (obs (E,S,11) f32, reward (E,) f64, done (E,) u8) device tensors."""
+        E, S = self.num_envs, self.total_servers
+        if isinstance(action, torch.Tensor):
+            a = action.to(device=self.device, dtype=self._adtype).contiguous()
+        else:
+            a = torch.as_tensor(np.ascontiguousarray(action, self._np_adtype)).to(self.device)
+        if a.numel() != E * S:
+            raise ValueError(f"action must have {E}x{S} entries, got shape {tuple(a.shape)}")
+        check(self._L.mlb_step(self._h, _dptr(a), _lib.DEVICE, None, None, None, _lib.DEVICE,
+                               self._stream()), self._h)
+        self._last_action = a  # keep alive until the kernel has consumed it
+        return self.obs, self.reward, self.done
+
+    def step_host(self, action: np.ndarray):
+        """End-to-end step with HOST buffers: pinned H2D of the actions, kernel, pinned D2H of
+        obs / reward / done, then a stream synchronise.  Returns numpy views of the pinned buffers."""
+        E, S = self.num_envs, self.total_servers
+        if self._h_action is None:
+            self._h_action = torch.empty((E, S), dtype=self._adtype, pin_memory=True)
+            self._h_obs = torch.empty((E, S, 11), dtype=torch.float32, pin_memory=True)
+            self._h_reward = torch.empty((E,), dtype=torch.float64, pin_memory=True)
+            self._h_done = torch.empty((E,), dtype=torch.uint8, pin_memory=True)
+        self._h_action.numpy()[...] = np.asarray(action).reshape(E, S)
+        check(self._L.mlb_step(self._h, _dptr(self._h_action), _lib.HOST, _dptr(self._h_obs),
+                               _dptr(self._h_reward), _dptr(self._h_done), _lib.HOST, self._stream()), self._h)
+        torch.cuda.current_stream().synchronize()
+        return self._h_obs.numpy(), self._h_reward.numpy(), self._h_done.numpy()
+
+    @property
+    def e2e_bytes(self):
+        """(h2d, d2h) bytes moved per step_host call."""
+        E, S = self.num_envs, self.total_servers
+        return E * S * torch.empty(0, dtype=self._adtype).element_size(), E * S * 11 * 4 + E * 8 + E
+
+    def check_status(self):
+        """Raise if a kernel reported a sticky error (RNG table exhausted, bad action index)."""
+        check(self._L.mlb_status(self._h, self._stream()), self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.mlb_launch_count(self._h))
+
+    # ------------------------------------------------------------ state dumps
+    def get_state(self, field: str) -> np.ndarray:
+        E, S, K = self.num_envs, self.total_servers, self.reservoir_capacity
+        KP = (K + 31) // 32 * 32
+        spec = {"n_flow_on": (_lib.F_N_FLOW_ON, np.int32, (E, S)),
+                "res_values": (_lib.F_RES_VALUES, np.float32, (E, S, 2, KP)),
+                "res_ts": (_lib.F_RES_TS, np.float32, (E, S, 2, KP)),
+                "res_count": (_lib.F_RES_COUNT, np.uint32, (E, 2, S)),
+                "res_cursor": (_lib.F_RES_CURSOR, np.uint32, (E, 2, S)),
+                "dropped": (_lib.F_DROPPED, np.uint32, (E, S)),
+                "last_fin": (_lib.F_LAST_FIN, np.float32, (E, S)),
+                "head": (_lib.F_HEAD, np.uint32, (E, S)),
+                "step": (_lib.F_STEP, np.int32, (E,)),
+                "obs": (_lib.F_OBS, np.float32, (E, S, 11)),
+                "arr_cursor": (_lib.F_ARR_CURSOR, np.int32, (E, self.num_agents))}[field]
+        out = np.empty(spec[2], spec[1])
+        check(self._L.mlb_get_state(self._h, spec[0], _nptr(out), out.nbytes, _lib.HOST), self._h)
+        if field in ("res_values", "res_ts"):
+            out = out[..., :K]
+        return out
+
+    def get_assignments(self, n: int) -> np.ndarray:
+        out = np.empty(n, np.int32)
+        check(self._L.mlb_get_assignments(self._h, _nptr(out), n, _lib.HOST, self._stream()), self._h)
+        return out

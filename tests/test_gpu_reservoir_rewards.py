@@ -1,0 +1,111 @@
+"""GPU: stand-alone reservoir / reward kernels against the reference-generated fixtures
+(SURVEY App. D goldens, reference tests' known answers)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import OBS_RTOL, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reservoir_appendix_d_golden():
+    from marllb_b200 import ReservoirSampler
+    g = load_golden("reservoir_seed42")
+    r = ReservoirSampler(capacity=128, seed=42)
+    # timestamps i*1e-3 are stored as float32 on the device; slots/accept flags must still match
+    acc = r.add_many(np.arange(1128, dtype=np.float32), np.arange(1128) * 1e-3)
+    assert np.array_equal(acc.astype(np.uint8), g["accepted"]) and int(acc[128:].sum()) == 297
+    assert r.count == 1128 and r.get_size() == 128 and r.is_full()
+    v = r.values
+    assert np.array_equal(v, g["values"])
+    assert v[:16].tolist() == [1087, 378, 1017, 1067, 1117, 1064, 1016, 993, 679, 1096, 10, 768, 1100, 195, 261, 588]
+    assert hashlib.sha256(v.tobytes()).hexdigest()[:16] == "4ef41e7995d7e99e"
+    f = r.get_feature_vector(0.9, current_time=1.128)
+    np.testing.assert_allclose(f, g["feature_vector"], rtol=OBS_RTOL)
+    assert f[4] == 1041.0 and abs(f[1] - 1040.30005) < 1e-3
+
+
+def test_single_adds_follow_reference_semantics():
+    from marllb_b200 import ReservoirSampler
+    r = ReservoirSampler(capacity=128, seed=42)
+    for i in range(128):                       # test_reservoir.py:40-47: fill phase always accepts
+        assert r.add(float(i), timestamp=float(i))
+    assert r.is_full() and len(r) == 128
+    g = load_golden("reservoir_seed42")
+    for i in range(128, 160):
+        assert r.add(float(i), timestamp=float(i)) == bool(g["accepted"][i])
+    r.reset()                                  # test_reservoir.py:133-146
+    assert r.count == 0 and len(r) == 0 and not r.values.any()
+    assert r.get_features() == {k: 0.0 for k in ("mean", "p90", "std", "mean_decay", "p90_decay")}
+
+
+def test_reservoir_streams():
+    from marllb_b200.reservoir import BatchedReservoirs
+    g = load_golden("reservoir_streams")
+    keys = sorted({k.rsplit("_in_v", 1)[0] for k in g if k.endswith("_in_v")})
+    for key in keys:
+        cap, seed = int(key.split("_")[0][1:]), int(key.split("_")[1][1:])
+        b = BatchedReservoirs(1, cap, seeds=[seed])
+        acc = b.add(g[key + "_in_v"][None], g[key + "_in_t"][None])
+        b.check_status()
+        assert np.array_equal(acc[0].cpu().numpy(), g[key + "_acc"])
+        assert np.array_equal(b.values[0, :cap].cpu().numpy(), g[key + "_values"])
+        assert np.array_equal(b.timestamps[0, :cap].cpu().numpy().astype(np.float64), g[key + "_ts"])
+        f = b.features(0.9, float(g[key + "_now"]))[0].cpu().numpy()
+        np.testing.assert_allclose(f, g[key + "_fv"], rtol=OBS_RTOL)
+
+
+def test_features_cases_batched():
+    import torch
+    from marllb_b200.reservoir import BatchedReservoirs
+    g = load_golden("features_cases")
+    N = len(g["n"])
+    b = BatchedReservoirs(N, 128)
+    b.values.copy_(torch.as_tensor(g["values"]))
+    b.timestamps.copy_(torch.as_tensor(g["ts"]))
+    b.count.copy_(torch.as_tensor(g["n"]))
+    f = b.features(0.9, torch.as_tensor(g["now"])).cpu().numpy()
+    np.testing.assert_allclose(f[:, [0, 2, 3]], g["fv"][:, [0, 2, 3]], rtol=OBS_RTOL)   # mean, std, mean_decay
+    assert np.array_equal(f[:, 1], g["fv"][:, 1])       # p90: exact order statistics + same f32 lerp
+    assert np.array_equal(f[:, 4], g["fv"][:, 4])       # p90_decay: an element of the reservoir
+
+
+def test_multi_metric_and_per_server_state():
+    from marllb_b200 import MultiMetricReservoir, PerServerFeatures
+    m = MultiMetricReservoir(metrics=["fct", "flow_duration"], capacity=128, seed=3)
+    rng = np.random.RandomState(0)
+    for i in range(40):
+        m.add("fct", float(rng.exponential(0.1)), timestamp=i * 0.01)
+        m.add("flow_duration", float(rng.uniform(0.01, 1.0)), timestamp=i * 0.01)
+    with pytest.raises(ValueError):
+        m.add("nope", 1.0)                              # test_reservoir.py:195-198
+    v = m.get_feature_vector(0.9, current_time=0.5)
+    assert v.shape == (10,) and v.dtype == np.float32   # test_reservoir.py:217-226
+    p = PerServerFeatures(2)
+    p.update_flow_count(0, 7)
+    st = p.get_state_vector([v, v], active_servers=[0])
+    assert st.shape == (2, 11) and st[0, 0] == 7 and not st[1].any()
+
+
+def test_rewards_cases_and_reference_literals():
+    import torch
+    from marllb_b200 import _lib, rewards
+    g = load_golden("rewards_cases")
+    vals = torch.as_tensor(g["values"]).cuda()
+    n = torch.as_tensor(g["n"]).cuda()
+    for m, name in enumerate(_lib.METRICS):
+        out = rewards.reward_metric_batch(name, vals, n).cpu().numpy()
+        np.testing.assert_allclose(out, g["out"][:, m], rtol=1e-12, atol=1e-300, err_msg=name)
+    # tests/test_rewards.py:31-48,83-119
+    assert rewards.jain_fairness([10, 10, 10, 10]) == pytest.approx(1.0)
+    assert rewards.jain_fairness([40, 0, 0, 0]) == pytest.approx(0.25)
+    assert rewards.jain_fairness([15, 10, 10, 5]) == pytest.approx(0.888888, abs=1e-5)
+    assert rewards.variance_fairness([40, 0, 0, 0]) == pytest.approx(-300.0)
+    assert rewards.max_min_fairness([40, 0, 0, 0]) == pytest.approx(-40.0)
+    assert rewards.range_fairness([40, 5, 5, 0]) == pytest.approx(-40.0)
+    assert rewards.jain_fairness([]) == 1.0 and rewards.variance_fairness([]) == 0.0
+    rf = rewards.RewardFunction("jain", "fct_mean")      # tests/test_rewards.py:159-182
+    obs = {"active_servers": [0, 1, 2, 3], "server_stats": {i: {"fct_mean": v} for i, v in enumerate([10, 12, 11, 10])}}
+    assert 0.99 < rf.compute(obs) <= 1.0 and rf(obs) == rf.compute(obs)
