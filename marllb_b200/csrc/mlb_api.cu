@@ -168,10 +168,18 @@ __global__ void gen_poisson_kernel(float* __restrict__ time, float* __restrict__
 }
 
 // ------------------------------------------------------------------ helpers
+static const void* step_fn(int policy, bool single) {
+    switch (policy) {
+    case MLB_POLICY_SED: return single ? (const void*)step_kernel<MLB_POLICY_SED, true> : (const void*)step_kernel<MLB_POLICY_SED, false>;
+    case MLB_POLICY_LSQ: return single ? (const void*)step_kernel<MLB_POLICY_LSQ, true> : (const void*)step_kernel<MLB_POLICY_LSQ, false>;
+    default: return single ? (const void*)step_kernel<MLB_POLICY_ALIAS, true> : (const void*)step_kernel<MLB_POLICY_ALIAS, false>;
+    }
+}
+
 static int launch_cfg(mlb_env* h) {
     const mlb_config& c = h->cfg;
     const int A = c.num_agents;
-    h->epb = A >= 4 ? 1 : 4 / A;
+    h->epb = A == 1 ? 4 : (A == 2 ? 2 : 1);
     h->threads = 32 * A * h->epb;
     const int SP = (c.servers_per_agent + 31) & ~31;
     const bool alias = c.policy == MLB_POLICY_ALIAS;
@@ -179,17 +187,14 @@ static int launch_cfg(mlb_env* h) {
                     (size_t)h->epb * 2 * h->d.S * 4;
     if (h->smem_bytes > 227 * 1024) return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)", h->smem_bytes);
     if (h->threads > 1024) return fail(h, MLB_EINVAL, "num_agents > 32 not supported");
-    cudaError_t e;
-    switch (c.policy) {
-    case MLB_POLICY_SED:
-        e = cudaFuncSetAttribute(step_kernel<MLB_POLICY_SED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-        break;
-    case MLB_POLICY_LSQ:
-        e = cudaFuncSetAttribute(step_kernel<MLB_POLICY_LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-        break;
-    default:
-        e = cudaFuncSetAttribute(step_kernel<MLB_POLICY_ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-        break;
+    const void* fn = step_fn(c.policy, A == 1);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (e == cudaSuccess) {
+        // shared-memory carve-out sized for 8 resident blocks (the rest stays L1)
+        size_t want = 8 * (h->smem_bytes + 1024);
+        int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
+        pct = pct > 100 ? 100 : pct;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
     if (e != cudaSuccess) return fail(h, MLB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return MLB_OK;
@@ -527,10 +532,11 @@ int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, dou
         dact = h->d_action;
     }
     const int blocks = (d.E + h->epb - 1) / h->epb;
-    switch (d.policy) {
-    case MLB_POLICY_SED: step_kernel<MLB_POLICY_SED><<<blocks, h->threads, h->smem_bytes, st>>>(d, dact); break;
-    case MLB_POLICY_LSQ: step_kernel<MLB_POLICY_LSQ><<<blocks, h->threads, h->smem_bytes, st>>>(d, dact); break;
-    default: step_kernel<MLB_POLICY_ALIAS><<<blocks, h->threads, h->smem_bytes, st>>>(d, dact); break;
+    {
+        DevState dv = d;
+        const void* act = dact;
+        void* args[] = {&dv, &act};
+        CK(h, cudaLaunchKernel(step_fn(d.policy, d.A == 1), dim3(blocks), dim3(h->threads), args, h->smem_bytes, st));
     }
     h->launches++;
     CK(h, cudaGetLastError());

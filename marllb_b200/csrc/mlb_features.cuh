@@ -28,53 +28,71 @@ namespace mlb {
 // not trusted (error bound of the fast path is < 1e-5 * W)
 #define MLB_WP_MARGIN 5e-5f
 
-template <int EPL>
-__device__ __forceinline__ void bitonic_sort_kv(float (&k)[EPL], float (&p)[EPL], int lane) {
-    // element index i = lane*EPL + r, ascending overall
+// One compare-exchange stage of the bitonic network; SIZE / STRIDE are template
+// constants so every register index is static (no local-memory arrays).
+template <int EPL, int SIZE, int STRIDE>
+__device__ __forceinline__ void bitonic_stage(float (&k)[EPL], float (&p)[EPL], int lane) {
+    // Branch-free compare-exchange: the new key is min or max (FMNMX + FSEL); the payload
+    // follows iff the key changed, so equal keys keep their own payload on both sides.
+    if constexpr (STRIDE >= EPL) {
+        constexpr int LSTRIDE = STRIDE / EPL;
+        const bool keep_min = (((lane * EPL) & SIZE) == 0) == ((lane & LSTRIDE) == 0);
 #pragma unroll
-    for (int size = 2; size <= 32 * EPL; size <<= 1) {
+        for (int r = 0; r < EPL; r++) {
+            const float ok = __shfl_xor_sync(MLB_FULL, k[r], LSTRIDE);
+            const float op = __shfl_xor_sync(MLB_FULL, p[r], LSTRIDE);
+            const float nk = keep_min ? fminf(k[r], ok) : fmaxf(k[r], ok);
+            p[r] = (nk != k[r]) ? op : p[r];
+            k[r] = nk;
+        }
+    } else {
 #pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= EPL) {
-                const int lstride = stride / EPL;
-                const bool up = ((lane * EPL) & size) == 0;
-                const bool lower = (lane & lstride) == 0;
-                const bool keep_min = (up == lower);
-#pragma unroll
-                for (int r = 0; r < EPL; r++) {
-                    const float ok = __shfl_xor_sync(MLB_FULL, k[r], lstride);
-                    const float op = __shfl_xor_sync(MLB_FULL, p[r], lstride);
-                    // strict compares on both sides: equal keys keep their own payload
-                    const bool take = keep_min ? (ok < k[r]) : (ok > k[r]);
-                    k[r] = take ? ok : k[r];
-                    p[r] = take ? op : p[r];
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < EPL; r++) {
-                    if ((r & stride) == 0) {
-                        const int r2 = r | stride;
-                        const bool up = (((lane * EPL + r) & size) == 0);
-                        const bool sw = up ? (k[r2] < k[r]) : (k[r2] > k[r]);
-                        const float k0 = k[r], p0 = p[r];
-                        k[r] = sw ? k[r2] : k0;
-                        p[r] = sw ? p[r2] : p0;
-                        k[r2] = sw ? k0 : k[r2];
-                        p[r2] = sw ? p0 : p[r2];
-                    }
-                }
+        for (int r = 0; r < EPL; r++) {
+            if ((r & STRIDE) == 0) {
+                const int r2 = r | STRIDE;
+                const bool up = (((lane * EPL + r) & SIZE) == 0);
+                const float a = k[r], b = k[r2], pa = p[r], pb = p[r2];
+                const float lo = fminf(a, b), hi = fmaxf(a, b);
+                const float na = up ? lo : hi;
+                const bool sw = na != a;
+                k[r] = na;
+                k[r2] = up ? hi : lo;
+                p[r] = sw ? pb : pa;
+                p[r2] = sw ? pa : pb;
             }
         }
     }
+    if constexpr (STRIDE > 1) bitonic_stage<EPL, SIZE, STRIDE / 2>(k, p, lane);
 }
 
-// value at sorted position `pos` (warp-uniform)
+template <int EPL, int SIZE>
+__device__ __forceinline__ void bitonic_merge_levels(float (&k)[EPL], float (&p)[EPL], int lane) {
+    bitonic_stage<EPL, SIZE, SIZE / 2>(k, p, lane);
+    if constexpr (SIZE < 32 * EPL) bitonic_merge_levels<EPL, SIZE * 2>(k, p, lane);
+}
+
+// ascending sort of the 32*EPL (key, payload) pairs, element index = lane*EPL + r
+template <int EPL>
+__device__ __forceinline__ void bitonic_sort_kv(float (&k)[EPL], float (&p)[EPL], int lane) {
+    bitonic_merge_levels<EPL, 2>(k, p, lane);
+}
+
+// value at sorted position `pos` (warp-uniform).  Written as a select tree on
+// the sub-index bits: a sequential `if (sub == r) c = k[r]` chain makes nvcc
+// materialise k[] as a dynamically indexed local-memory array.
 template <int EPL>
 __device__ __forceinline__ float sorted_at(const float (&k)[EPL], int pos) {
-    float c = k[0];
-#pragma unroll
-    for (int r = 1; r < EPL; r++)
-        if ((pos % EPL) == r) c = k[r];
+    float c;
+    if constexpr (EPL == 4) {
+        const int sub = pos & 3;
+        const float lo = (sub & 1) ? k[1] : k[0];
+        const float hi = (sub & 1) ? k[3] : k[2];
+        c = (sub & 2) ? hi : lo;
+    } else if constexpr (EPL == 2) {
+        c = (pos & 1) ? k[1] : k[0];
+    } else {
+        c = k[0];
+    }
     return __shfl_sync(MLB_FULL, c, pos / EPL);
 }
 

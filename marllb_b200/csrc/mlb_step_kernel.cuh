@@ -256,12 +256,15 @@ __device__ inline double reward_staged(int metric, const T* rv, const uint32_t* 
     return -(sqrt(var) / (mean + eps));
 }
 
-template <int POLICY>
-__global__ void step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action) {
+// SINGLE = one agent per env (A == 1): blocks are exactly 4 warps = 4 envs and no
+// inter-warp barrier is needed, so the kernel can be register-capped for occupancy.
+template <int POLICY, bool SINGLE>
+__global__ void __launch_bounds__(SINGLE ? 128 : 1024, SINGLE ? 8 : 1)
+step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int A = d.A, Sa = d.Sa, S = d.S;
+    const int A = SINGLE ? 1 : d.A, Sa = d.Sa, S = d.S;
     const int nwarps = blockDim.x >> 5;
     const int epb = nwarps / A;
     const int env_in_blk = warp / A;
@@ -455,10 +458,12 @@ __global__ void step_kernel(const __grid_constant__ DevState d, const void* __re
         rv[seed0 + j] = x;
         ra[seed0 + j] = active ? 1u : 0u;
     }
-    if (A == 1) {
+    if (SINGLE) {
         __syncwarp();
+    } else if (env_in_blk == 0) {  // at most 2 envs per block when A > 1: static barrier ids
+        asm volatile("bar.sync 1, %0;" ::"r"(A * 32) : "memory");
     } else {
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + env_in_blk), "r"(A * 32) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"r"(A * 32) : "memory");
     }
     if (agent == 0) {
         const double r = reward_staged(d.reward_metric, rv, ra, S);
