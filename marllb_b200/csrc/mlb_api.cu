@@ -96,10 +96,12 @@ __global__ void reset_kernel(const DevState d, const uint8_t* __restrict__ mask)
     const size_t rn = (size_t)S * 2 * d.KP;
     float4* v4 = reinterpret_cast<float4*>(d.res_val + sb * 2 * d.KP);
     float4* t4 = reinterpret_cast<float4*>(d.res_ts + sb * 2 * d.KP);
+    uint32_t* r4 = reinterpret_cast<uint32_t*>(d.res_rank + sb * 2 * d.KP);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (size_t i = tid; i < rn / 4; i += nt) {
         v4[i] = z;
         t4[i] = z;
+        r4[i] = 0u;
     }
     for (int i = tid; i < S * MLB_OBS_COLS; i += nt) d.obs[sb * MLB_OBS_COLS + i] = 0.f;
     for (int i = tid; i < d.A; i += nt) d.arr_cur[(size_t)e * d.A + i] = 0;
@@ -183,7 +185,7 @@ static int launch_cfg(mlb_env* h) {
     h->threads = 32 * A * h->epb;
     const int SP = (c.servers_per_agent + 31) & ~31;
     const bool alias = c.policy == MLB_POLICY_ALIAS;
-    h->smem_bytes = (size_t)(h->threads / 32) * warp_smem_bytes(SP, alias) +
+    h->smem_bytes = (size_t)(h->threads / 32) * (warp_smem_bytes(SP, alias) + MLB_SCRATCH_BYTES) +
                     (size_t)h->epb * 2 * h->d.S * 4;
     if (h->smem_bytes > 227 * 1024) return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)", h->smem_bytes);
     if (h->threads > 1024) return fail(h, MLB_EINVAL, "num_agents > 32 not supported");
@@ -191,7 +193,7 @@ static int launch_cfg(mlb_env* h) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess) {
         // shared-memory carve-out sized for 8 resident blocks (the rest stays L1)
-        size_t want = 8 * (h->smem_bytes + 1024);
+        size_t want = 7 * (h->smem_bytes + 1024);
         int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
         pct = pct > 100 ? 100 : pct;
         e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -306,6 +308,7 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     CKC(dalloc(h, &d.res_ts, ES * 2 * d.KP));
     CKC(dalloc(h, &d.res_count, ES * 2));
     CKC(dalloc(h, &d.res_cursor, ES * 2));
+    CKC(dalloc(h, &d.res_rank, ES * 2 * d.KP));
     CKC(dalloc(h, &d.ring_arr, ES * d.Q));
     CKC(dalloc(h, &d.ring_fin, ES * d.Q));
     CKC(dalloc(h, &d.obs, ES * MLB_OBS_COLS));

@@ -30,6 +30,7 @@ struct DevState {
     float* res_ts;
     uint32_t* res_count;
     uint32_t* res_cursor;
+    uint8_t* res_rank;     // [E][S][2][KP] rank of each slot's value (order statistics cache)
     // ---- FIFO rings [E][S][Q]
     float* ring_arr;
     float* ring_fin;

@@ -8,8 +8,17 @@
 //
 // Layout: the K<=128 slots of one reservoir are spread over the 32 lanes,
 // EPL = 1, 2 or 4 consecutive slots per lane (one 32/64/128-bit load each).
-// Sorting is an in-register bitonic network over (value, timestamp) pairs:
-// intra-lane stages are compare-exchanges, inter-lane stages use shuffles.
+//
+// Order statistics come from a per-slot RANK (position of the slot's value in
+// ascending order).  Ranks are either computed from scratch -- an in-register
+// bitonic network over (value, slot) pairs, intra-lane stages as compare-
+// exchanges and inter-lane stages as shuffles -- or, when the caller keeps the
+// ranks of the previous step, updated incrementally for the few slots that
+// Algorithm R replaced (remove the old rank, count-and-insert the new value:
+// ~50 instructions per replaced slot instead of a ~600-instruction sort).
+// Values and weights are then scattered by rank into a 1 KB per-warp shared-
+// memory scratch, which makes "value at rank r" a broadcast read and the
+// weighted percentile a blocked read + warp scan.
 //
 // The decay weights only matter up to a common factor (both weighted outputs
 // are ratios / order decisions), so the fast path evaluates them in float32
@@ -77,23 +86,37 @@ __device__ __forceinline__ void bitonic_sort_kv(float (&k)[EPL], float (&p)[EPL]
     bitonic_merge_levels<EPL, 2>(k, p, lane);
 }
 
-// value at sorted position `pos` (warp-uniform).  Written as a select tree on
-// the sub-index bits: a sequential `if (sub == r) c = k[r]` chain makes nvcc
-// materialise k[] as a dynamically indexed local-memory array.
+// blocked read of EPL consecutive floats per lane from shared memory
 template <int EPL>
-__device__ __forceinline__ float sorted_at(const float (&k)[EPL], int pos) {
-    float c;
+__device__ __forceinline__ void load_smem_block(const float* base, int lane, float (&x)[EPL]) {
     if constexpr (EPL == 4) {
-        const int sub = pos & 3;
-        const float lo = (sub & 1) ? k[1] : k[0];
-        const float hi = (sub & 1) ? k[3] : k[2];
+        const float4 q = *reinterpret_cast<const float4*>(base + lane * 4);
+        x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+    } else if constexpr (EPL == 2) {
+        const float2 q = *reinterpret_cast<const float2*>(base + lane * 2);
+        x[0] = q.x; x[1] = q.y;
+    } else {
+        x[0] = base[lane];
+    }
+}
+
+// element `slot` (warp-uniform) of an array spread EPL-per-lane.  Written as a select tree
+// on the sub-index bits: a sequential `if (sub == r) c = x[r]` chain makes nvcc materialise
+// x[] as a dynamically indexed local-memory array.
+template <int EPL, typename T>
+__device__ __forceinline__ T slot_fetch(const T (&x)[EPL], int slot) {
+    T c;
+    if constexpr (EPL == 4) {
+        const int sub = slot & 3;
+        const T lo = (sub & 1) ? x[1] : x[0];
+        const T hi = (sub & 1) ? x[3] : x[2];
         c = (sub & 2) ? hi : lo;
     } else if constexpr (EPL == 2) {
-        c = (pos & 1) ? k[1] : k[0];
+        c = (slot & 1) ? x[1] : x[0];
     } else {
-        c = k[0];
+        c = x[0];
     }
-    return __shfl_sync(MLB_FULL, c, pos / EPL);
+    return __shfl_sync(MLB_FULL, c, slot / EPL);
 }
 
 template <int EPL>
@@ -109,70 +132,183 @@ __device__ __forceinline__ void load_slots(const float* __restrict__ base, int l
     }
 }
 
-// Features of one reservoir held in registers: v/t are this lane's EPL slots
-// (slot index lane*EPL + r), n = number of valid slots (>= 1).
+// ranks are one byte per slot in global memory
 template <int EPL>
-__device__ __forceinline__ void warp_features_regs(float (&v)[EPL], float (&t)[EPL], int n, float now,
-                                                   double decay, float log2_decay, float (&out)[5]) {
+__device__ __forceinline__ void load_ranks(const uint8_t* __restrict__ base, int lane, int (&rk)[EPL]) {
+    if constexpr (EPL == 4) {
+        const uint32_t q = *reinterpret_cast<const uint32_t*>(base + lane * 4);
+        rk[0] = q & 255; rk[1] = (q >> 8) & 255; rk[2] = (q >> 16) & 255; rk[3] = q >> 24;
+    } else if constexpr (EPL == 2) {
+        const uint32_t q = *reinterpret_cast<const uint16_t*>(base + lane * 2);
+        rk[0] = q & 255; rk[1] = q >> 8;
+    } else {
+        rk[0] = base[lane];
+    }
+}
+template <int EPL>
+__device__ __forceinline__ void store_ranks(uint8_t* __restrict__ base, int lane, const int (&rk)[EPL]) {
+    if constexpr (EPL == 4) {
+        *reinterpret_cast<uint32_t*>(base + lane * 4) =
+            (uint32_t)(rk[0] & 255) | ((uint32_t)(rk[1] & 255) << 8) | ((uint32_t)(rk[2] & 255) << 16) | ((uint32_t)rk[3] << 24);
+    } else if constexpr (EPL == 2) {
+        *reinterpret_cast<uint16_t*>(base + lane * 2) = (uint16_t)((rk[0] & 255) | ((rk[1] & 255) << 8));
+    } else {
+        base[lane] = (uint8_t)rk[0];
+    }
+}
+
+// per-warp shared-memory scratch: sv[128] (values by rank), sw[128] (weights by rank)
+struct WarpScratch {
+    float* sv;
+    float* sw;
+};
+#define MLB_SCRATCH_BYTES 1024
+
+// Ranks from scratch: bitonic sort of (value, slot) pairs, then transpose position->slot
+// into slot->position through shared-memory bytes.  Slots >= n get rank 255.
+template <int EPL>
+__device__ __forceinline__ void ranks_full_sort(const float (&v)[EPL], int n, int (&rk)[EPL],
+                                                const WarpScratch& sc, int lane) {
+    float k[EPL], p[EPL];
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const int slot = lane * EPL + r;
+        k[r] = slot < n ? v[r] : MLB_INF;  // padding sorts to the end
+        p[r] = __int_as_float(slot);
+    }
+    bitonic_sort_kv<EPL>(k, p, lane);
+    uint8_t* sb = reinterpret_cast<uint8_t*>(sc.sw);
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const int pos = lane * EPL + r;
+        sb[__float_as_int(p[r])] = (uint8_t)(pos < n ? pos : 255);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < EPL; r++) rk[r] = sb[lane * EPL + r];
+    __syncwarp();
+}
+
+// Incremental rank maintenance.  `mw` = bit mask (warp-uniform) of the slots Algorithm R
+// wrote this step; slots < n_old existed before (their stored rank is removed), every
+// changed slot < n_new is (re-)inserted by counting the present elements below it.
+// Ties are ordered by slot index; any order of equal values is a valid sorted order.
+template <int EPL>
+__device__ __forceinline__ void ranks_update(const float (&v)[EPL], int (&rk)[EPL], int n_new, int n_old,
+                                             const uint32_t (&mw)[4], int lane) {
+    constexpr int NW = EPL == 4 ? 4 : EPL;  // mask words that can hold slots < 32*EPL
+    const int s0 = lane * EPL;
+    uint32_t word = mw[0];
+    if constexpr (EPL >= 2) word = (s0 >> 5) == 1 ? mw[1] : word;
+    if constexpr (EPL == 4) {
+        word = (s0 >> 5) == 2 ? mw[2] : word;
+        word = (s0 >> 5) == 3 ? mw[3] : word;
+    }
+    const uint32_t chg = (word >> (s0 & 31)) & ((1u << EPL) - 1u);
+    uint32_t pres = 0;
+    int dec[EPL];
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        dec[r] = 0;
+        if (s0 + r < n_new && !((chg >> r) & 1u)) pres |= 1u << r;
+    }
+    // pass 1: remove the old ranks of replaced slots (compare against ORIGINAL ranks)
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        uint32_t bits = mw[w];
+        while (bits) {
+            const int c = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (c < n_old) {
+                const int rc = slot_fetch<EPL, int>(rk, c);
+#pragma unroll
+                for (int r = 0; r < EPL; r++) dec[r] += rk[r] > rc ? 1 : 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < EPL; r++) rk[r] -= dec[r];
+    // pass 2: insert the new values one at a time
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        uint32_t bits = mw[w];
+        while (bits) {
+            const int c = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (c >= n_new) continue;
+            const float x = slot_fetch<EPL, float>(v, c);
+            int less = 0;
+#pragma unroll
+            for (int r = 0; r < EPL; r++) {
+                const bool lt = v[r] < x || (v[r] == x && s0 + r < c);
+                less += (((pres >> r) & 1u) && lt) ? 1 : 0;
+            }
+            const int rnew = __reduce_add_sync(MLB_FULL, less);
+#pragma unroll
+            for (int r = 0; r < EPL; r++) {
+                if (((pres >> r) & 1u) && rk[r] >= rnew) rk[r] += 1;
+                if (s0 + r == c) {
+                    rk[r] = rnew;
+                    pres |= 1u << r;
+                }
+            }
+        }
+    }
+}
+
+// The five features given slot-ordered values/timestamps and valid ranks.
+template <int EPL>
+__device__ __forceinline__ void features_ranked(const float (&v)[EPL], const float (&t)[EPL],
+                                                const int (&rk)[EPL], int n, float now, double decay,
+                                                float log2_decay, const WarpScratch& sc, float (&out)[5]) {
     const int lane = lane_id();
+    const int s0 = lane * EPL;
     // ---- mean / std (np.mean, np.std on float32: reservoir.py:143,145)
     float s = 0.f, tmax = -MLB_INF;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const bool valid = lane * EPL + r < n;
+        const bool valid = s0 + r < n;
         s += valid ? v[r] : 0.f;
         tmax = valid ? fmaxf(tmax, t[r]) : tmax;
     }
     const float nf = (float)n;
     const float mean = warp_sum(s) / nf;
     tmax = warp_max(tmax);
-    float s2 = 0.f;
+    // ---- decay weights relative to the newest sample (float32 fast path), scatter by rank
+    float s2 = 0.f, svw = 0.f;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const bool valid = lane * EPL + r < n;
+        const bool valid = s0 + r < n;
         const float d = v[r] - mean;
         s2 += valid ? d * d : 0.f;
-        if (!valid) v[r] = MLB_INF;  // padding sorts to the end
+        const float w = valid ? exp2f(log2_decay * (tmax - t[r])) : 0.f;
+        svw += valid ? v[r] * w : 0.f;
+        const int pos = valid ? rk[r] : s0 + r;  // ranks cover [0,n); slots >= n pad positions >= n
+        sc.sv[pos] = v[r];
+        sc.sw[pos] = w;
     }
     const float sd = sqrtf(warp_sum(s2) / nf);
-
-    // ---- sort by value, timestamp rides along
-    bitonic_sort_kv<EPL>(v, t, lane);
-
-    // ---- p90 = np.percentile(values, 90): float32 'linear' rule of numpy >= 2
-    const float vidx = (float)(n - 1) * (90.0f / 100.0f);
-    const float fl = floorf(vidx);
-    int lo = (int)fl, hi = lo + 1;
-    if (vidx >= (float)(n - 1)) { lo = n - 1; hi = n - 1; }
-    hi = hi > n - 1 ? n - 1 : hi;
-    const float gamma = vidx - fl;
-    const float a = sorted_at<EPL>(v, lo), b = sorted_at<EPL>(v, hi);
-    const float diff = __fsub_rn(b, a);
-    float p90 = __fadd_rn(a, __fmul_rn(diff, gamma));
-    if (gamma >= 0.5f) p90 = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
-
-    // ---- decay weights relative to the newest sample (float32 fast path)
-    float w[EPL], cum[EPL];
-    float sw = 0.f, svw = 0.f;
+    svw = warp_sum(svw);
+    __syncwarp();
+    // ---- weighted percentile: blocked read of weights in rank order + warp scan
+    float wq[EPL], cum[EPL];
+    load_smem_block<EPL>(sc.sw, lane, wq);
+    float sw = 0.f;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const bool valid = lane * EPL + r < n;
-        const float x = log2_decay * (tmax - t[r]);
-        w[r] = valid ? exp2f(x) : 0.f;
-        sw += w[r];
-        svw += valid ? v[r] * w[r] : 0.f;
+        sw += wq[r];
         cum[r] = sw;
     }
     const float incl = warp_scan_incl(sw, lane);
     const float W = __shfl_sync(MLB_FULL, incl, 31);
     const float excl = incl - sw;
-    const float mean_decay = warp_sum(svw) / W;
+    const float mean_decay = svw / W;
     const float cutoff = 0.9f * W;
     int below = 0;
     float dmin = MLB_INF;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const bool valid = lane * EPL + r < n;
+        const bool valid = s0 + r < n;  // here s0+r is a POSITION in rank order
         const float c = excl + cum[r];
         below += (valid && c < cutoff) ? 1 : 0;
         dmin = valid ? fminf(dmin, fabsf(c - cutoff)) : dmin;
@@ -180,12 +316,19 @@ __device__ __forceinline__ void warp_features_regs(float (&v)[EPL], float (&t)[E
     int idx = __reduce_add_sync(MLB_FULL, below);
     const uint32_t dmin_bits = __reduce_min_sync(MLB_FULL, __float_as_uint(dmin));
     if (__uint_as_float(dmin_bits) < MLB_WP_MARGIN * W) {
-        // ---- faithful float64 decision (reservoir.py:148-149,181-196)
+        // ---- faithful float64 decision (reservoir.py:148-149,181-196): pow(decay, now - t)
+        // and a strictly sequential cumsum in value order
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < EPL; r++)
+            if (s0 + r < n) sc.sw[rk[r]] = t[r];
+        __syncwarp();
+        float tq[EPL];
+        load_smem_block<EPL>(sc.sw, lane, tq);
         double wd[EPL], cd[EPL];
 #pragma unroll
         for (int r = 0; r < EPL; r++) {
-            const bool valid = lane * EPL + r < n;
-            wd[r] = valid ? pow(decay, (double)now - (double)t[r]) : 0.0;
+            wd[r] = s0 + r < n ? pow(decay, (double)now - (double)tq[r]) : 0.0;
             cd[r] = 0.0;
         }
         double c = 0.0;
@@ -199,14 +342,23 @@ __device__ __forceinline__ void warp_features_regs(float (&v)[EPL], float (&t)[E
         const double cut = 0.9 * c;  // percentile * cumsum[-1]
         below = 0;
 #pragma unroll
-        for (int r = 0; r < EPL; r++) {
-            const bool valid = lane * EPL + r < n;
-            below += (valid && cd[r] < cut) ? 1 : 0;
-        }
+        for (int r = 0; r < EPL; r++) below += (s0 + r < n && cd[r] < cut) ? 1 : 0;
         idx = __reduce_add_sync(MLB_FULL, below);
     }
     idx = idx > n - 1 ? n - 1 : idx;  // reservoir.py:193-194
-    const float p90_decay = sorted_at<EPL>(v, idx);
+    // ---- p90 = np.percentile(values, 90): float32 'linear' rule of numpy >= 2
+    const float vidx = (float)(n - 1) * (90.0f / 100.0f);
+    const float fl = floorf(vidx);
+    int lo = (int)fl, hi = lo + 1;
+    if (vidx >= (float)(n - 1)) { lo = n - 1; hi = n - 1; }
+    hi = hi > n - 1 ? n - 1 : hi;
+    const float gamma = vidx - fl;
+    const float a = sc.sv[lo], b = sc.sv[hi];
+    const float p90_decay = sc.sv[idx];
+    const float diff = __fsub_rn(b, a);
+    float p90 = __fadd_rn(a, __fmul_rn(diff, gamma));
+    if (gamma >= 0.5f) p90 = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+    __syncwarp();  // scratch is reused by the next reservoir
     out[0] = mean;
     out[1] = p90;
     out[2] = sd;
@@ -214,29 +366,82 @@ __device__ __forceinline__ void warp_features_regs(float (&v)[EPL], float (&t)[E
     out[4] = p90_decay;
 }
 
-// Load + compute for one reservoir in global memory.  n = min(count, K), may be 0.
+// Stateless form: ranks from scratch every time.  n = min(count, K), may be 0.
 __device__ __forceinline__ void warp_features(const float* __restrict__ vals,
                                               const float* __restrict__ tss, int n, float now,
-                                              double decay, float log2_decay, float (&out)[5]) {
+                                              double decay, float log2_decay, const WarpScratch& sc,
+                                              float (&out)[5]) {
     const int lane = lane_id();
     if (n <= 0) {  // reservoir.py:127-134
 #pragma unroll
         for (int q = 0; q < 5; q++) out[q] = 0.f;
     } else if (n <= 32) {
         float v[1], t[1];
+        int rk[1];
         load_slots<1>(vals, lane, v);
         load_slots<1>(tss, lane, t);
-        warp_features_regs<1>(v, t, n, now, decay, log2_decay, out);
+        ranks_full_sort<1>(v, n, rk, sc, lane);
+        features_ranked<1>(v, t, rk, n, now, decay, log2_decay, sc, out);
     } else if (n <= 64) {
         float v[2], t[2];
+        int rk[2];
         load_slots<2>(vals, lane, v);
         load_slots<2>(tss, lane, t);
-        warp_features_regs<2>(v, t, n, now, decay, log2_decay, out);
+        ranks_full_sort<2>(v, n, rk, sc, lane);
+        features_ranked<2>(v, t, rk, n, now, decay, log2_decay, sc, out);
     } else {
         float v[4], t[4];
+        int rk[4];
         load_slots<4>(vals, lane, v);
         load_slots<4>(tss, lane, t);
-        warp_features_regs<4>(v, t, n, now, decay, log2_decay, out);
+        ranks_full_sort<4>(v, n, rk, sc, lane);
+        features_ranked<4>(v, t, rk, n, now, decay, log2_decay, sc, out);
+    }
+}
+
+// Stateful form used by the env step: ranks live in global memory next to the reservoir
+// and are updated incrementally when only a few slots changed.
+//   n_old  valid slots when the stored ranks were computed (0: no ranks yet)
+//   mw     mask of slots written since then;  nchg = popcount(mw)
+//   force_full: ignore stored ranks (feature_cache modes 0 / 2)
+template <int EPL>
+__device__ __forceinline__ void features_cached_epl(const float* __restrict__ vals, const float* __restrict__ tss,
+                                                    uint8_t* __restrict__ ranks, int n, int n_old,
+                                                    const uint32_t (&mw)[4], int nchg, bool force_full,
+                                                    float now, double decay, float log2_decay,
+                                                    const WarpScratch& sc, float (&out)[5]) {
+    const int lane = lane_id();
+    float v[EPL], t[EPL];
+    int rk[EPL];
+    load_slots<EPL>(vals, lane, v);
+    load_slots<EPL>(tss, lane, t);
+    // stored ranks are only meaningful if they were laid out for a population that this
+    // EPL variant also covers (n_old <= 32*EPL always holds since n_old <= n)
+    constexpr int kMaxIncremental = EPL == 1 ? 2 : (EPL == 2 ? 5 : 10);  // ~50 instr per slot vs the sort
+    if (force_full || n_old == 0 || nchg > kMaxIncremental) {
+        ranks_full_sort<EPL>(v, n, rk, sc, lane);
+    } else {
+        load_ranks<EPL>(ranks, lane, rk);
+        ranks_update<EPL>(v, rk, n, n_old, mw, lane);
+    }
+    store_ranks<EPL>(ranks, lane, rk);
+    features_ranked<EPL>(v, t, rk, n, now, decay, log2_decay, sc, out);
+}
+
+__device__ __forceinline__ void warp_features_cached(const float* __restrict__ vals, const float* __restrict__ tss,
+                                                     uint8_t* __restrict__ ranks, int n, int n_old,
+                                                     const uint32_t (&mw)[4], int nchg, bool force_full,
+                                                     float now, double decay, float log2_decay,
+                                                     const WarpScratch& sc, float (&out)[5]) {
+    if (n <= 0) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) out[q] = 0.f;
+    } else if (n <= 32) {
+        features_cached_epl<1>(vals, tss, ranks, n, n_old, mw, nchg, force_full, now, decay, log2_decay, sc, out);
+    } else if (n <= 64) {
+        features_cached_epl<2>(vals, tss, ranks, n, n_old, mw, nchg, force_full, now, decay, log2_decay, sc, out);
+    } else {
+        features_cached_epl<4>(vals, tss, ranks, n, n_old, mw, nchg, force_full, now, decay, log2_decay, sc, out);
     }
 }
 

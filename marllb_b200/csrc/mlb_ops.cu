@@ -39,13 +39,16 @@ __global__ void reservoir_features_kernel(const float* __restrict__ values, cons
                                           const uint32_t* __restrict__ count, int R, int K, int KP,
                                           double decay, float log2_decay, const float* __restrict__ now,
                                           float* __restrict__ out) {
+    __shared__ __align__(16) float scratch[4][256];
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= R) return;
     const uint32_t c = count[r];
     const int n = c < (uint32_t)K ? (int)c : K;
+    float* scr = scratch[threadIdx.x >> 5];
+    const WarpScratch sc{scr, scr + 128};
     float f[5];
-    warp_features(values + (size_t)r * KP, ts + (size_t)r * KP, n, now[r], decay, log2_decay, f);
+    warp_features(values + (size_t)r * KP, ts + (size_t)r * KP, n, now[r], decay, log2_decay, sc, f);
     float mine = f[0];
 #pragma unroll
     for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;

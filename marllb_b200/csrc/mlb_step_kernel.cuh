@@ -24,7 +24,7 @@
 
 namespace mlb {
 
-constexpr int NF = 13;  // per-server shared-memory fields
+constexpr int NF = 23;  // per-server shared-memory fields (4 bytes each)
 
 struct WarpSmem {
     int32_t* n_on;
@@ -38,6 +38,9 @@ struct WarpSmem {
     uint32_t* cur[2];
     uint32_t* dropped;
     uint32_t* flags;
+    uint32_t* nold[2];    // valid slots at step start (what the stored ranks describe)
+    uint32_t* chg;        // [2][4][SP] bit mask of reservoir slots written this step
+    int sp;
     // alias policy only
     double* prob;
     int32_t* alias;
@@ -71,6 +74,10 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, int SP, bool alia
     w.cur[1] = q + 10 * SP;
     w.dropped = q + 11 * SP;
     w.flags = q + 12 * SP;
+    w.nold[0] = q + 13 * SP;
+    w.nold[1] = q + 14 * SP;
+    w.chg = q + 15 * SP;
+    w.sp = SP;
     w.alias = alias ? reinterpret_cast<int32_t*>(q + NF * SP) : nullptr;
     w.stack = alias ? reinterpret_cast<int32_t*>(q + (NF + 1) * SP) : nullptr;
     return w;
@@ -123,6 +130,7 @@ __device__ __forceinline__ void res_add(const DevState& d, const WarpSmem& s, in
         d.res_val[at] = value;
         d.res_ts[at] = ts;
         s.flags[j] |= (1u << m);
+        s.chg[(m * 4 + (slot >> 5)) * s.sp + j] |= 1u << (slot & 31);
     }
 }
 
@@ -279,6 +287,9 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
     // per-env reward staging after all warp areas
     float* rv = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * wbytes) + (size_t)env_in_blk * 2 * S;
     uint32_t* ra = reinterpret_cast<uint32_t*>(rv + S);
+    // per-warp 1 KB scratch for the rank-ordered statistics, after the reward staging
+    float* scr = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * wbytes) + (size_t)epb * 2 * S + (size_t)warp * 256;
+    const WarpScratch scratch{scr, scr + 128};
 
     const int step = d.step[e] + 1;                       // env.py:230
     const float t1 = __fmul_rn((float)step, d.dt);        // window end
@@ -316,8 +327,12 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
 #pragma unroll
         for (int m = 0; m < 2; m++) {
             const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
-            s.cnt[m][j] = d.res_count[c];
+            const uint32_t cnt = d.res_count[c];
+            s.cnt[m][j] = cnt;
             s.cur[m][j] = d.res_cursor[c];
+            s.nold[m][j] = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s.chg[(m * 4 + k) * s.sp + j] = 0;
         }
     }
     __syncwarp();
@@ -423,7 +438,7 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
     for (int jb = 0; jb < SP; jb += 32) {
         const int j = jb + lane;
         uint32_t fl = 0;
-        if (j < Sa) fl = d.feature_cache ? s.flags[j] : 3u;
+        if (j < Sa) fl = d.feature_cache ? s.flags[j] : 3u;  // mode 0: recompute every reservoir
 #pragma unroll
         for (int m = 0; m < 2; m++) {
             unsigned todo = __ballot_sync(MLB_FULL, (fl >> m) & 1u);
@@ -433,8 +448,13 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
                 const uint32_t cnt = s.cnt[m][jj];
                 const int n = cnt < (uint32_t)d.K ? (int)cnt : d.K;
                 const size_t rid = ((sbase + jj) * 2 + m) * d.KP;
+                uint32_t mw[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) mw[k] = s.chg[(m * 4 + k) * s.sp + jj];
+                const int nchg = __popc(mw[0]) + __popc(mw[1]) + __popc(mw[2]) + __popc(mw[3]);
                 float f[5];
-                warp_features(d.res_val + rid, d.res_ts + rid, n, t1, d.decay, d.log2_decay, f);
+                warp_features_cached(d.res_val + rid, d.res_ts + rid, d.res_rank + rid, n, (int)s.nold[m][jj],
+                                     mw, nchg, d.feature_cache != 1, t1, d.decay, d.log2_decay, scratch, f);
                 float mine = f[0];
 #pragma unroll
                 for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
