@@ -170,11 +170,22 @@ __global__ void gen_poisson_kernel(float* __restrict__ time, float* __restrict__
 }
 
 // ------------------------------------------------------------------ helpers
-static const void* step_fn(int policy, bool single) {
+template <int POLICY>
+static const void* step_fn_r(int R) {
+    switch (R) {
+    case 1: return (const void*)step_kernel<POLICY, 1>;
+    case 2: return (const void*)step_kernel<POLICY, 2>;
+    case 4: return (const void*)step_kernel<POLICY, 4>;
+    default: return (const void*)step_kernel<POLICY, 8>;
+    }
+}
+static int lanes_r(int Sa) { return Sa <= 32 ? 1 : (Sa <= 64 ? 2 : (Sa <= 128 ? 4 : 8)); }
+static const void* step_fn(int policy, int Sa) {
+    const int R = lanes_r(Sa);
     switch (policy) {
-    case MLB_POLICY_SED: return single ? (const void*)step_kernel<MLB_POLICY_SED, true> : (const void*)step_kernel<MLB_POLICY_SED, false>;
-    case MLB_POLICY_LSQ: return single ? (const void*)step_kernel<MLB_POLICY_LSQ, true> : (const void*)step_kernel<MLB_POLICY_LSQ, false>;
-    default: return single ? (const void*)step_kernel<MLB_POLICY_ALIAS, true> : (const void*)step_kernel<MLB_POLICY_ALIAS, false>;
+    case MLB_POLICY_SED: return step_fn_r<MLB_POLICY_SED>(R);
+    case MLB_POLICY_LSQ: return step_fn_r<MLB_POLICY_LSQ>(R);
+    default: return step_fn_r<MLB_POLICY_ALIAS>(R);
     }
 }
 
@@ -183,17 +194,17 @@ static int launch_cfg(mlb_env* h) {
     const int A = c.num_agents;
     h->epb = A == 1 ? 4 : (A == 2 ? 2 : 1);
     h->threads = 32 * A * h->epb;
-    const int SP = (c.servers_per_agent + 31) & ~31;
+    const int SP = 32 * lanes_r(c.servers_per_agent);
     const bool alias = c.policy == MLB_POLICY_ALIAS;
-    h->smem_bytes = (size_t)(h->threads / 32) * (warp_smem_bytes(SP, alias) + MLB_SCRATCH_BYTES) +
+    h->smem_bytes = (size_t)(h->threads / 32) * warp_smem_bytes(SP, alias) +
                     (size_t)h->epb * 2 * h->d.S * 4;
     if (h->smem_bytes > 227 * 1024) return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)", h->smem_bytes);
     if (h->threads > 1024) return fail(h, MLB_EINVAL, "num_agents > 32 not supported");
-    const void* fn = step_fn(c.policy, A == 1);
+    const void* fn = step_fn(c.policy, c.servers_per_agent);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess) {
         // shared-memory carve-out sized for 8 resident blocks (the rest stays L1)
-        size_t want = 7 * (h->smem_bytes + 1024);
+        size_t want = 8 * (h->smem_bytes + 1024);
         int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
         pct = pct > 100 ? 100 : pct;
         e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -334,6 +345,18 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
         CKC(dalloc(h, &t, tab.size()));
         CKC(cudaMemcpy(t, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
         d.mt_table = t;
+    }
+    // SED score table, same arithmetic as the oracle: (float)((double)(n+1) / (1e-9 + (double)w))
+    {
+        const int TQ = d.Q + 2;
+        std::vector<float> tab((size_t)8 * TQ, 0.f);
+        for (int a = 0; a < c.n_discrete && a < 8; a++)
+            for (int n = 0; n < TQ; n++)
+                tab[(size_t)a * TQ + n] = (float)((double)(n + 1) / (1e-9 + (double)c.discrete_weights[a]));
+        float* t = nullptr;
+        CKC(dalloc(h, &t, tab.size()));
+        CKC(cudaMemcpy(t, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        d.sed_table = t;
     }
     // speeds default 1.0
     fill_f32_kernel<<<256, 256>>>(d.speed, ES, 1.0f);
@@ -539,7 +562,7 @@ int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, dou
         DevState dv = d;
         const void* act = dact;
         void* args[] = {&dv, &act};
-        CK(h, cudaLaunchKernel(step_fn(d.policy, d.A == 1), dim3(blocks), dim3(h->threads), args, h->smem_bytes, st));
+        CK(h, cudaLaunchKernel(step_fn(d.policy, d.Sa), dim3(blocks), dim3(h->threads), args, h->smem_bytes, st));
     }
     h->launches++;
     CK(h, cudaGetLastError());

@@ -53,6 +53,13 @@ __device__ __forceinline__ float warp_scan_incl(float v, int lane) {
     return v;
 }
 
+// 2^x, x <= 0: single MUFU.EX2 (2 ulp), denormal results flush to zero
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // streaming (evict-first) global accesses for data touched once per step
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     return __ldcs(reinterpret_cast<const float4*>(p));

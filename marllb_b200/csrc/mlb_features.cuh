@@ -166,27 +166,49 @@ struct WarpScratch {
 
 // Ranks from scratch: bitonic sort of (value, slot) pairs, then transpose position->slot
 // into slot->position through shared-memory bytes.  Slots >= n get rank 255.
+// noinline: cold once reservoirs are full and ranks are maintained incrementally; keeping
+// it out of line keeps the steady-state loop inside the instruction cache.  Values go in by
+// value and the EPL ranks come back packed in one word so that nothing lives in local memory.
 template <int EPL>
-__device__ __forceinline__ void ranks_full_sort(const float (&v)[EPL], int n, int (&rk)[EPL],
-                                                const WarpScratch& sc, int lane) {
+struct SlotVals {
+    float x[EPL];
+};
+
+template <int EPL>
+__device__ __noinline__ uint32_t ranks_full_sort_packed(SlotVals<EPL> v, int n, float* sw) {
+    const int lane = lane_id();
     float k[EPL], p[EPL];
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
         const int slot = lane * EPL + r;
-        k[r] = slot < n ? v[r] : MLB_INF;  // padding sorts to the end
+        k[r] = slot < n ? v.x[r] : MLB_INF;  // padding sorts to the end
         p[r] = __int_as_float(slot);
     }
     bitonic_sort_kv<EPL>(k, p, lane);
-    uint8_t* sb = reinterpret_cast<uint8_t*>(sc.sw);
+    uint8_t* sb = reinterpret_cast<uint8_t*>(sw);
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
         const int pos = lane * EPL + r;
         sb[__float_as_int(p[r])] = (uint8_t)(pos < n ? pos : 255);
     }
     __syncwarp();
+    uint32_t packed = 0;
 #pragma unroll
-    for (int r = 0; r < EPL; r++) rk[r] = sb[lane * EPL + r];
+    for (int r = 0; r < EPL; r++) packed |= (uint32_t)sb[lane * EPL + r] << (8 * r);
     __syncwarp();
+    return packed;
+}
+
+template <int EPL>
+__device__ __forceinline__ void ranks_full_sort(const float (&v)[EPL], int n, int (&rk)[EPL],
+                                                const WarpScratch& sc, int lane) {
+    SlotVals<EPL> sv;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) sv.x[r] = v[r];
+    const uint32_t packed = ranks_full_sort_packed<EPL>(sv, n, sc.sw);
+#pragma unroll
+    for (int r = 0; r < EPL; r++) rk[r] = (packed >> (8 * r)) & 255u;
+    (void)lane;
 }
 
 // Incremental rank maintenance.  `mw` = bit mask (warp-uniform) of the slots Algorithm R
@@ -195,15 +217,11 @@ __device__ __forceinline__ void ranks_full_sort(const float (&v)[EPL], int n, in
 // Ties are ordered by slot index; any order of equal values is a valid sorted order.
 template <int EPL>
 __device__ __forceinline__ void ranks_update(const float (&v)[EPL], int (&rk)[EPL], int n_new, int n_old,
-                                             const uint32_t (&mw)[4], int lane) {
-    constexpr int NW = EPL == 4 ? 4 : EPL;  // mask words that can hold slots < 32*EPL
+                                             const uint32_t* mws, int stride, int lane) {
+    // mws[k * stride], k = 0..3: mask words in shared memory (warp-uniform addresses)
+    constexpr int NW = EPL == 4 ? 4 : EPL;  // words that can hold slots < 32*EPL
     const int s0 = lane * EPL;
-    uint32_t word = mw[0];
-    if constexpr (EPL >= 2) word = (s0 >> 5) == 1 ? mw[1] : word;
-    if constexpr (EPL == 4) {
-        word = (s0 >> 5) == 2 ? mw[2] : word;
-        word = (s0 >> 5) == 3 ? mw[3] : word;
-    }
+    const uint32_t word = mws[(s0 >> 5) * stride];
     const uint32_t chg = (word >> (s0 & 31)) & ((1u << EPL) - 1u);
     uint32_t pres = 0;
     int dec[EPL];
@@ -213,9 +231,10 @@ __device__ __forceinline__ void ranks_update(const float (&v)[EPL], int (&rk)[EP
         if (s0 + r < n_new && !((chg >> r) & 1u)) pres |= 1u << r;
     }
     // pass 1: remove the old ranks of replaced slots (compare against ORIGINAL ranks)
-#pragma unroll
+#pragma unroll 1
     for (int w = 0; w < NW; w++) {
-        uint32_t bits = mw[w];
+        uint32_t bits = mws[w * stride];
+#pragma unroll 1
         while (bits) {
             const int c = w * 32 + __ffs(bits) - 1;
             bits &= bits - 1;
@@ -229,9 +248,10 @@ __device__ __forceinline__ void ranks_update(const float (&v)[EPL], int (&rk)[EP
 #pragma unroll
     for (int r = 0; r < EPL; r++) rk[r] -= dec[r];
     // pass 2: insert the new values one at a time
-#pragma unroll
+#pragma unroll 1
     for (int w = 0; w < NW; w++) {
-        uint32_t bits = mw[w];
+        uint32_t bits = mws[w * stride];
+#pragma unroll 1
         while (bits) {
             const int c = w * 32 + __ffs(bits) - 1;
             bits &= bits - 1;
@@ -254,6 +274,41 @@ __device__ __forceinline__ void ranks_update(const float (&v)[EPL], int (&rk)[EP
             }
         }
     }
+}
+
+// Cold path of the weighted percentile: the reference's float64 arithmetic
+// (reservoir.py:148-149,181-196): w = pow(decay, now - t) and a strictly sequential cumsum
+// in value order.  st = timestamps in rank order (shared memory), n <= 128.  Returns the
+// searchsorted-left index of 0.9 * cumsum[-1] (n if none).
+static __device__ __noinline__ int weighted_index_f64(const float* st, int n, float now, double decay) {
+    const int lane = lane_id();
+    double w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int pos = k * 32 + lane;
+        w[k] = pos < n ? pow(decay, (double)now - (double)st[pos]) : 0.0;
+    }
+    double c = 0.0;
+#pragma unroll 1
+    for (int p = 0; p < n; p++) {
+        const int k = p >> 5;
+        const double wk = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
+        c += __shfl_sync(MLB_FULL, wk, p & 31);
+    }
+    const double cut = 0.9 * c;  // percentile * cumsum[-1]
+    c = 0.0;
+    int idx = n;
+#pragma unroll 1
+    for (int p = 0; p < n; p++) {
+        const int k = p >> 5;
+        const double wk = k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]));
+        c += __shfl_sync(MLB_FULL, wk, p & 31);
+        if (c >= cut) {
+            idx = p;
+            break;
+        }
+    }
+    return idx;
 }
 
 // The five features given slot-ordered values/timestamps and valid ranks.
@@ -281,7 +336,7 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
         const bool valid = s0 + r < n;
         const float d = v[r] - mean;
         s2 += valid ? d * d : 0.f;
-        const float w = valid ? exp2f(log2_decay * (tmax - t[r])) : 0.f;
+        const float w = valid ? fast_exp2(log2_decay * (tmax - t[r])) : 0.f;
         svw += valid ? v[r] * w : 0.f;
         const int pos = valid ? rk[r] : s0 + r;  // ranks cover [0,n); slots >= n pad positions >= n
         sc.sv[pos] = v[r];
@@ -316,34 +371,13 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
     int idx = __reduce_add_sync(MLB_FULL, below);
     const uint32_t dmin_bits = __reduce_min_sync(MLB_FULL, __float_as_uint(dmin));
     if (__uint_as_float(dmin_bits) < MLB_WP_MARGIN * W) {
-        // ---- faithful float64 decision (reservoir.py:148-149,181-196): pow(decay, now - t)
-        // and a strictly sequential cumsum in value order
+        // ---- not trusted: redo the decision in the reference's float64 arithmetic
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < EPL; r++)
             if (s0 + r < n) sc.sw[rk[r]] = t[r];
         __syncwarp();
-        float tq[EPL];
-        load_smem_block<EPL>(sc.sw, lane, tq);
-        double wd[EPL], cd[EPL];
-#pragma unroll
-        for (int r = 0; r < EPL; r++) {
-            wd[r] = s0 + r < n ? pow(decay, (double)now - (double)tq[r]) : 0.0;
-            cd[r] = 0.0;
-        }
-        double c = 0.0;
-        for (int L = 0; L * EPL < n; L++) {
-#pragma unroll
-            for (int r = 0; r < EPL; r++) {
-                c += __shfl_sync(MLB_FULL, wd[r], L);  // padding adds 0.0
-                if (lane == L) cd[r] = c;
-            }
-        }
-        const double cut = 0.9 * c;  // percentile * cumsum[-1]
-        below = 0;
-#pragma unroll
-        for (int r = 0; r < EPL; r++) below += (s0 + r < n && cd[r] < cut) ? 1 : 0;
-        idx = __reduce_add_sync(MLB_FULL, below);
+        idx = weighted_index_f64(sc.sw, n, now, decay);
     }
     idx = idx > n - 1 ? n - 1 : idx;  // reservoir.py:193-194
     // ---- p90 = np.percentile(values, 90): float32 'linear' rule of numpy >= 2
@@ -402,12 +436,12 @@ __device__ __forceinline__ void warp_features(const float* __restrict__ vals,
 // Stateful form used by the env step: ranks live in global memory next to the reservoir
 // and are updated incrementally when only a few slots changed.
 //   n_old  valid slots when the stored ranks were computed (0: no ranks yet)
-//   mw     mask of slots written since then;  nchg = popcount(mw)
+//   mws    mask (4 words, shared memory, word k at mws[k*stride]) of slots written since then
 //   force_full: ignore stored ranks (feature_cache modes 0 / 2)
 template <int EPL>
 __device__ __forceinline__ void features_cached_epl(const float* __restrict__ vals, const float* __restrict__ tss,
                                                     uint8_t* __restrict__ ranks, int n, int n_old,
-                                                    const uint32_t (&mw)[4], int nchg, bool force_full,
+                                                    const uint32_t* mws, int stride, int nchg, bool force_full,
                                                     float now, double decay, float log2_decay,
                                                     const WarpScratch& sc, float (&out)[5]) {
     const int lane = lane_id();
@@ -422,7 +456,7 @@ __device__ __forceinline__ void features_cached_epl(const float* __restrict__ va
         ranks_full_sort<EPL>(v, n, rk, sc, lane);
     } else {
         load_ranks<EPL>(ranks, lane, rk);
-        ranks_update<EPL>(v, rk, n, n_old, mw, lane);
+        ranks_update<EPL>(v, rk, n, n_old, mws, stride, lane);
     }
     store_ranks<EPL>(ranks, lane, rk);
     features_ranked<EPL>(v, t, rk, n, now, decay, log2_decay, sc, out);
@@ -430,18 +464,18 @@ __device__ __forceinline__ void features_cached_epl(const float* __restrict__ va
 
 __device__ __forceinline__ void warp_features_cached(const float* __restrict__ vals, const float* __restrict__ tss,
                                                      uint8_t* __restrict__ ranks, int n, int n_old,
-                                                     const uint32_t (&mw)[4], int nchg, bool force_full,
+                                                     const uint32_t* mws, int stride, int nchg, bool force_full,
                                                      float now, double decay, float log2_decay,
                                                      const WarpScratch& sc, float (&out)[5]) {
     if (n <= 0) {
 #pragma unroll
         for (int q = 0; q < 5; q++) out[q] = 0.f;
     } else if (n <= 32) {
-        features_cached_epl<1>(vals, tss, ranks, n, n_old, mw, nchg, force_full, now, decay, log2_decay, sc, out);
+        features_cached_epl<1>(vals, tss, ranks, n, n_old, mws, stride, nchg, force_full, now, decay, log2_decay, sc, out);
     } else if (n <= 64) {
-        features_cached_epl<2>(vals, tss, ranks, n, n_old, mw, nchg, force_full, now, decay, log2_decay, sc, out);
+        features_cached_epl<2>(vals, tss, ranks, n, n_old, mws, stride, nchg, force_full, now, decay, log2_decay, sc, out);
     } else {
-        features_cached_epl<4>(vals, tss, ranks, n, n_old, mw, nchg, force_full, now, decay, log2_decay, sc, out);
+        features_cached_epl<4>(vals, tss, ranks, n, n_old, mws, stride, nchg, force_full, now, decay, log2_decay, sc, out);
     }
 }
 

@@ -7,15 +7,18 @@
 //   phase A  per arrival (time order): retire finished flows (n_flow_on--, fct
 //            sample -> Algorithm-R add, reservoir.py:50-85), choose a server
 //            (SED / LSQ / alias, src/vpp/lb/node.c:393-460) with REDUX argmin,
-//            push on that server's FIFO ring
-//   phase C  window end: retire, then one flow_duration sample per active flow
+//            push on that server's FIFO ring; the window end is one more
+//            (pseudo-)event of the same loop
+//   phase C  one flow_duration sample per still-active flow, state write-back
 //   phase B  reservoir statistics of every reservoir touched this step
 //            (reservoir.py:105-196) -> obs columns (features.py:256-286)
 //   phase R  reward over the env's active servers (rewards.py:329-381), done flag
 //
-// Every per-server scalar is owned by lane (server % 32) of the agent's warp, so
-// phases A/C need no intra-warp locking; phase B is warp-cooperative per
-// reservoir with warp-uniform control flow.
+// Lane (server % 32) of the agent's warp owns every scalar of that server, so
+// phases A/C need no intra-warp locking.  What is tested on every arrival (the
+// finish time of the oldest flow, the assignment score) lives in registers,
+// R = ceil(Sa/32) per lane; what changes only on events lives in shared memory.
+// Phase B is warp-cooperative per reservoir with warp-uniform control flow.
 #pragma once
 #include "mlb_common.cuh"
 #include "mlb_env.cuh"
@@ -24,72 +27,39 @@
 
 namespace mlb {
 
-constexpr int NF = 23;  // per-server shared-memory fields (4 bytes each)
-
-struct WarpSmem {
-    int32_t* n_on;
-    float* last_fin;
-    uint32_t* head;
-    float* head_fin;
-    uint32_t* score;
-    float* speed;
-    float* weight;
-    uint32_t* cnt[2];
-    uint32_t* cur[2];
-    uint32_t* dropped;
-    uint32_t* flags;
-    uint32_t* nold[2];    // valid slots at step start (what the stored ranks describe)
-    uint32_t* chg;        // [2][4][SP] bit mask of reservoir slots written this step
-    int sp;
-    // alias policy only
-    double* prob;
-    int32_t* alias;
-    int32_t* stack;
+// per-server shared-memory fields (4 bytes each), field f of server j at smem[f*SP + j]
+enum : int {
+    F_NON = 0,   // n_flow_on
+    F_LASTFIN,   // finish time of the newest queued flow
+    F_HEAD,      // ring position of the oldest in-system flow
+    F_ACT,       // discrete action index (or float weight bits for continuous actions)
+    F_CNT0, F_CNT1,  // reservoir counts   (fct, flow_duration)
+    F_CUR0, F_CUR1,  // MT19937 replay cursors
+    F_FLAGS,     // bit0/bit1: reservoir m touched this step
+    F_NOLD,      // valid slots at step start: fct | flow_duration << 8
+    F_CHG,       // 8 words: [metric][word] mask of reservoir slots written this step
+    NF = F_CHG + 8
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(int SP, bool alias) {
-    return (size_t)NF * SP * 4 + (alias ? (size_t)SP * (8 + 4 + 8) : 0);
+    return (size_t)NF * SP * 4 + MLB_SCRATCH_BYTES + (alias ? (size_t)SP * (8 + 4 + 8) : 0);
 }
 
-__device__ __forceinline__ WarpSmem carve(unsigned char* base, int SP, bool alias) {
-    WarpSmem w;
-    unsigned char* p = base;
-    if (alias) {  // doubles first: keep 8-byte alignment
-        w.prob = reinterpret_cast<double*>(p);
-        p += (size_t)SP * 8;
-    } else {
-        w.prob = nullptr;
-    }
-    uint32_t* q = reinterpret_cast<uint32_t*>(p);
-    w.n_on = reinterpret_cast<int32_t*>(q + 0 * SP);
-    w.last_fin = reinterpret_cast<float*>(q + 1 * SP);
-    w.head = q + 2 * SP;
-    w.head_fin = reinterpret_cast<float*>(q + 3 * SP);
-    w.score = q + 4 * SP;
-    w.speed = reinterpret_cast<float*>(q + 5 * SP);
-    w.weight = reinterpret_cast<float*>(q + 6 * SP);
-    w.cnt[0] = q + 7 * SP;
-    w.cnt[1] = q + 8 * SP;
-    w.cur[0] = q + 9 * SP;
-    w.cur[1] = q + 10 * SP;
-    w.dropped = q + 11 * SP;
-    w.flags = q + 12 * SP;
-    w.nold[0] = q + 13 * SP;
-    w.nold[1] = q + 14 * SP;
-    w.chg = q + 15 * SP;
-    w.sp = SP;
-    w.alias = alias ? reinterpret_cast<int32_t*>(q + NF * SP) : nullptr;
-    w.stack = alias ? reinterpret_cast<int32_t*>(q + (NF + 1) * SP) : nullptr;
-    return w;
-}
-
-// score of one server under SED / LSQ as an order-preserving uint
-// node.c:395-404: f32 score = (n_flow_on + 1) / (1e-9 + weight), evaluated in double
+// Assignment score of one server as an order-preserving uint.
+// node.c:395-404: f32 score = (n_flow_on + 1) / (1e-9 + weight), evaluated in double.
+// For discrete actions the quotient comes from a table built on the host with exactly
+// that arithmetic: sed_table[a * (Q + 2) + n].
 template <int POLICY>
-__device__ __forceinline__ uint32_t server_score(int n, float w) {
+__device__ __forceinline__ uint32_t server_score(const DevState& d, int n, uint32_t act) {
     if (POLICY == MLB_POLICY_SED) {
-        const double s = (double)(n + 1) / (1e-9 + (double)w);
-        return f32_orderable((float)s);
+        float sc;
+        if (d.action_kind == MLB_ACTION_CONTINUOUS_F32) {
+            const double s = (double)(n + 1) / (1e-9 + (double)__uint_as_float(act));
+            sc = (float)s;
+        } else {
+            sc = __ldg(d.sed_table + act * (d.Q + 2) + n);
+        }
+        return f32_orderable(sc);
     } else {
         return f32_orderable((float)n);  // node.c:419-431
     }
@@ -117,44 +87,37 @@ __device__ __forceinline__ int res_draw_slot(uint32_t cnt, uint32_t& cur, const 
     return v < (uint32_t)K ? (int)v : -1;  // reservoir.py:78-85
 }
 
-// ReservoirSampler.add by the owning lane of server j, metric m.
-__device__ __forceinline__ void res_add(const DevState& d, const WarpSmem& s, int m, int j,
-                                        size_t srv, int seed_row, float value, float ts) {
-    const uint32_t cnt = s.cnt[m][j];
-    uint32_t c = s.cur[m][j];
-    const int slot = res_draw_slot(cnt, c, d.mt_table + (size_t)seed_row * d.L, d.L, d.K, d.status);
-    s.cur[m][j] = c;
-    s.cnt[m][j] = cnt + 1;
-    if (slot >= 0) {
-        const size_t at = (srv * 2 + m) * d.KP + slot;
-        d.res_val[at] = value;
-        d.res_ts[at] = ts;
-        s.flags[j] |= (1u << m);
-        s.chg[(m * 4 + (slot >> 5)) * s.sp + j] |= 1u << (slot & 31);
-    }
-}
+// per-warp view of the global arrays (32-bit offsets below these bases)
+struct WarpGlobals {
+    float* res_val;     // this agent's reservoirs [Sa][2][KP]
+    float* res_ts;
+    uint8_t* res_rank;
+    float* ring_arr;    // [Sa][Q]
+    float* ring_fin;
+    float* obs;         // [Sa][11]
+    const uint32_t* mt; // replay rows of this agent's servers [Sa][L]
+};
 
-template <int POLICY>
-__device__ __forceinline__ void retire(const DevState& d, const WarpSmem& s, int j, size_t srv,
-                                       int seed_row, float now) {
-    // pop while the oldest flow finished strictly before `now`
-    while (s.head_fin[j] < now) {
-        uint32_t h = s.head[j];
-        const size_t rb = srv * d.Q;
-        const float arr = d.ring_arr[rb + h];
-        const float fin = s.head_fin[j];
-        h = (h + 1 == (uint32_t)d.Q) ? 0u : h + 1;
-        s.head[j] = h;
-        const int n = s.n_on[j] - 1;  // src/vpp/lb/lbhash.h:120
-        s.n_on[j] = n;
-        s.head_fin[j] = n > 0 ? d.ring_fin[rb + h] : MLB_INF;
-        res_add(d, s, 0, j, srv, seed_row, __fsub_rn(fin, arr), fin);  // lbhash.h:122-124
-        if (POLICY != MLB_POLICY_ALIAS) s.score[j] = server_score<POLICY>(n, s.weight[j]);
+// ReservoirSampler.add by the owning lane of server j, metric m.
+template <int SP>
+__device__ __forceinline__ void res_add(const DevState& d, uint32_t* sm, const WarpGlobals& g, int m, int j,
+                                        float value, float ts) {
+    const uint32_t cnt = sm[(F_CNT0 + m) * SP + j];
+    uint32_t c = sm[(F_CUR0 + m) * SP + j];
+    const int slot = res_draw_slot(cnt, c, g.mt + (size_t)j * d.L, d.L, d.K, d.status);
+    sm[(F_CUR0 + m) * SP + j] = c;
+    sm[(F_CNT0 + m) * SP + j] = cnt + 1;
+    if (slot >= 0) {
+        const int at = (j * 2 + m) * d.KP + slot;
+        g.res_val[at] = value;
+        g.res_ts[at] = ts;
+        sm[F_FLAGS * SP + j] |= (1u << m);
+        sm[(F_CHG + m * 4 + (slot >> 5)) * SP + j] |= 1u << (slot & 31);
     }
 }
 
 // numpy pairwise block sum (n <= 128) and its two-block extension (n <= 256)
-__device__ inline double np_block_sum(const double* a, int n) {
+static __device__ inline double np_block_sum(const double* a, int n) {
     if (n < 8) {
         double r = -0.0;
         for (int i = 0; i < n; i++) r += a[i];
@@ -169,7 +132,7 @@ __device__ inline double np_block_sum(const double* a, int n) {
     for (; i < n; i++) res += a[i];
     return res;
 }
-__device__ inline double np_sum_f64(const double* a, int n) {
+static __device__ inline double np_sum_f64(const double* a, int n) {
     if (n <= 128) return np_block_sum(a, n);
     int n2 = n / 2;
     n2 -= n2 % 8;
@@ -177,32 +140,32 @@ __device__ inline double np_sum_f64(const double* a, int n) {
 }
 
 // rl_controller.py:359-405 _build_alias_table over p = w / sum(w); one lane.
-__device__ inline void alias_build(const WarpSmem& s, int Sa) {
-    for (int k = 0; k < Sa; k++) s.prob[k] = (double)s.weight[k];
-    const double tot = np_sum_f64(s.prob, Sa);
-    int* small = s.stack;
-    int* large = s.stack + Sa;
+static __device__ __noinline__ void alias_build(double* prob, int32_t* alias, int32_t* stack, const float* weight, int Sa) {
+    for (int k = 0; k < Sa; k++) prob[k] = (double)weight[k];
+    const double tot = np_sum_f64(prob, Sa);
+    int* small = stack;
+    int* large = stack + Sa;
     int ns = 0, nl = 0;
     for (int k = 0; k < Sa; k++) {
-        const double p = (s.prob[k] / tot) * (double)Sa;
-        s.prob[k] = p;
-        s.alias[k] = k;
+        const double p = (prob[k] / tot) * (double)Sa;
+        prob[k] = p;
+        alias[k] = k;
         if (p < 1.0) small[ns++] = k; else large[nl++] = k;
     }
     while (ns > 0 && nl > 0) {
         const int l = small[--ns];
         const int g = large[--nl];
-        s.alias[l] = g;
-        const double pg = s.prob[g] + s.prob[l] - 1.0;
-        s.prob[g] = pg;
+        alias[l] = g;
+        const double pg = prob[g] + prob[l] - 1.0;
+        prob[g] = pg;
         if (pg < 1.0) small[ns++] = g; else large[nl++] = g;
     }
 }
 
-// Reward metric over the staged reward-field values of one env (leader warp).
+// Reward metric over staged reward-field values (one warp).
 // rewards.py:21-287; float64 throughout like the reference.
 template <typename T>
-__device__ inline double reward_staged(int metric, const T* rv, const uint32_t* ra, int S) {
+__device__ __noinline__ double reward_staged(int metric, const T* rv, const uint32_t* ra, int S) {
     const int lane = lane_id();
     const double eps = 1e-10;
     int na = 0;
@@ -264,15 +227,16 @@ __device__ inline double reward_staged(int metric, const T* rv, const uint32_t* 
     return -(sqrt(var) / (mean + eps));
 }
 
-// SINGLE = one agent per env (A == 1): blocks are exactly 4 warps = 4 envs and no
-// inter-warp barrier is needed, so the kernel can be register-capped for occupancy.
-template <int POLICY, bool SINGLE>
-__global__ void __launch_bounds__(SINGLE ? 128 : 1024, SINGLE ? 8 : 1)
+// R = servers per lane (Sa <= 32*R), SP = 32*R.
+template <int POLICY, int R>
+__global__ void __launch_bounds__(1024, 1)
 step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SP = 32 * R;
+    constexpr bool kAlias = (POLICY == MLB_POLICY_ALIAS);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int A = SINGLE ? 1 : d.A, Sa = d.Sa, S = d.S;
+    const int A = d.A, Sa = d.Sa, S = d.S;
     const int nwarps = blockDim.x >> 5;
     const int epb = nwarps / A;
     const int env_in_blk = warp / A;
@@ -280,79 +244,102 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
     const int e = blockIdx.x * epb + env_in_blk;
     if (e >= d.E) return;  // whole env (all its warps) leaves together
 
-    const int SP = (Sa + 31) & ~31;
-    constexpr bool kAlias = (POLICY == MLB_POLICY_ALIAS);
+    // ---- shared memory: [per warp: fields | scratch | alias] ... [per env: reward staging]
     const size_t wbytes = warp_smem_bytes(SP, kAlias);
-    const WarpSmem s = carve(smem_raw + (size_t)warp * wbytes, SP, kAlias);
-    // per-env reward staging after all warp areas
+    unsigned char* wbase = smem_raw + (size_t)warp * wbytes;
+    uint32_t* sm = reinterpret_cast<uint32_t*>(wbase);
+    float* smf = reinterpret_cast<float*>(wbase);
+    float* scr = reinterpret_cast<float*>(wbase + (size_t)NF * SP * 4);
+    const WarpScratch scratch{scr, scr + 128};
+    double* a_prob = reinterpret_cast<double*>(wbase + (size_t)NF * SP * 4 + MLB_SCRATCH_BYTES);
+    int32_t* a_alias = reinterpret_cast<int32_t*>(a_prob + SP);
     float* rv = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * wbytes) + (size_t)env_in_blk * 2 * S;
     uint32_t* ra = reinterpret_cast<uint32_t*>(rv + S);
-    // per-warp 1 KB scratch for the rank-ordered statistics, after the reward staging
-    float* scr = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * wbytes) + (size_t)epb * 2 * S + (size_t)warp * 256;
-    const WarpScratch scratch{scr, scr + 128};
 
     const int step = d.step[e] + 1;                       // env.py:230
     const float t1 = __fmul_rn((float)step, d.dt);        // window end
     const size_t sbase = (size_t)e * S + (size_t)agent * Sa;
     const int seed0 = agent * Sa;                         // replay row = server index in env
+    WarpGlobals g;
+    g.res_val = d.res_val + sbase * 2 * d.KP;
+    g.res_ts = d.res_ts + sbase * 2 * d.KP;
+    g.res_rank = d.res_rank + sbase * 2 * d.KP;
+    g.ring_arr = d.ring_arr + sbase * d.Q;
+    g.ring_fin = d.ring_fin + sbase * d.Q;
+    g.obs = d.obs + sbase * MLB_OBS_COLS;
+    g.mt = d.mt_table + (size_t)seed0 * d.L;
+    const int Q = d.Q;
 
     // ---------------- phase 0: load state, action -> weights -----------------
-    for (int j = lane; j < Sa; j += 32) {
-        const size_t g = sbase + j;
-        const int n = d.n_on[g];
-        const uint32_t h = d.head[g];
-        s.n_on[j] = n;
-        s.last_fin[j] = d.last_fin[g];
-        s.head[j] = h;
-        s.head_fin[j] = n > 0 ? d.ring_fin[g * d.Q + h] : MLB_INF;
-        s.speed[j] = d.speed[g];
-        s.dropped[j] = d.dropped[g];
-        s.flags[j] = 0;
-        float w;
-        if (d.action_kind == MLB_ACTION_CONTINUOUS_F32) {
-            const float x = reinterpret_cast<const float*>(action)[g];
-            w = fminf(fmaxf(x, d.min_w), d.max_w);        // env.py:349-351
-        } else {
-            int a = d.action_kind == MLB_ACTION_DISCRETE_U8
-                        ? (int)reinterpret_cast<const uint8_t*>(action)[g]
-                        : reinterpret_cast<const int32_t*>(action)[g];
-            if ((unsigned)a >= (unsigned)d.n_discrete) {
-                atomicOr(d.status, ST_ERR_ACTION);
-                a = 0;
+    float hf[R];       // finish time of the oldest in-system flow (INF: idle)
+    uint32_t sc[R];    // assignment score as an order-preserving uint
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = lane + 32 * r;
+        hf[r] = MLB_INF;
+        sc[r] = 0xffffffffu;
+        if (j < Sa) {
+            const size_t gi = sbase + j;
+            const int n = d.n_on[gi];
+            const uint32_t h = d.head[gi];
+            sm[F_NON * SP + j] = (uint32_t)n;
+            smf[F_LASTFIN * SP + j] = d.last_fin[gi];
+            sm[F_HEAD * SP + j] = h;
+            if (n > 0) hf[r] = g.ring_fin[j * Q + h];
+            uint32_t act;
+            if (d.action_kind == MLB_ACTION_CONTINUOUS_F32) {
+                const float x = reinterpret_cast<const float*>(action)[gi];
+                act = __float_as_uint(fminf(fmaxf(x, d.min_w), d.max_w));  // env.py:349-351
+            } else {
+                int a = d.action_kind == MLB_ACTION_DISCRETE_U8
+                            ? (int)reinterpret_cast<const uint8_t*>(action)[gi]
+                            : reinterpret_cast<const int32_t*>(action)[gi];
+                if ((unsigned)a >= (unsigned)d.n_discrete) {
+                    atomicOr(d.status, ST_ERR_ACTION);
+                    a = 0;
+                }
+                act = (uint32_t)a;                                          // env.py:346
             }
-            w = d.dw[a];                                  // env.py:346
-        }
-        s.weight[j] = w;
-        if (!kAlias) s.score[j] = server_score<POLICY>(n, w);
+            sm[F_ACT * SP + j] = act;
+            if (!kAlias) sc[r] = server_score<POLICY>(d, n, act);
+            uint32_t nold = 0;
 #pragma unroll
-        for (int m = 0; m < 2; m++) {
-            const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
-            const uint32_t cnt = d.res_count[c];
-            s.cnt[m][j] = cnt;
-            s.cur[m][j] = d.res_cursor[c];
-            s.nold[m][j] = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
+            for (int m = 0; m < 2; m++) {
+                const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
+                const uint32_t cnt = d.res_count[c];
+                sm[(F_CNT0 + m) * SP + j] = cnt;
+                sm[(F_CUR0 + m) * SP + j] = d.res_cursor[c];
+                nold |= (cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K) << (8 * m);
+            }
+            sm[F_NOLD * SP + j] = nold;
+            sm[F_FLAGS * SP + j] = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) s.chg[(m * 4 + k) * s.sp + j] = 0;
+            for (int k = 0; k < 8; k++) sm[(F_CHG + k) * SP + j] = 0;
         }
     }
     __syncwarp();
     if (kAlias) {
-        if (lane == 0) alias_build(s, Sa);
+        // weights as floats for the alias builder, staged in the scratch area
+        for (int j = lane; j < Sa; j += 32) {
+            const uint32_t act = sm[F_ACT * SP + j];
+            scr[j] = d.action_kind == MLB_ACTION_CONTINUOUS_F32 ? __uint_as_float(act) : d.dw[act];
+        }
+        __syncwarp();
+        if (lane == 0) alias_build(a_prob, a_alias, a_alias + SP, scr, Sa);
         __syncwarp();
     }
 
-    // ---------------- phase A: arrivals of this window, in time order --------
+    // ---------------- phase A: events of this window, in time order ----------
     const int ea = e * A + agent;
     const int64_t aoff = d.arr_off[ea];
     const int an = d.arr_n[ea];
     int cur = d.arr_cur[ea];
-    while (true) {
+    for (;;) {
         const int idx = cur + lane;
         const float at = idx < an ? __ldcs(d.arr_time + aoff + idx) : MLB_INF;
-        const bool inw = at < t1;
-        const unsigned bal = __ballot_sync(MLB_FULL, inw);
+        const unsigned bal = __ballot_sync(MLB_FULL, at < t1);
         const int nv = (bal == MLB_FULL) ? 32 : (__ffs(~bal) - 1);
-        if (nv == 0) break;
+        const bool last = nv < 32;
         const float awk = lane < nv ? __ldcs(d.arr_work + aoff + idx) : 0.f;
         int abk = 0;
         float au = 0.f;
@@ -360,113 +347,147 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
             abk = __ldcs(d.arr_bucket + aoff + idx);
             au = __ldcs(d.arr_u + aoff + idx);
         }
-        for (int i = 0; i < nv; i++) {
-            const float a = __shfl_sync(MLB_FULL, at, i);
-            const float wk = __shfl_sync(MLB_FULL, awk, i);
-            for (int j = lane; j < Sa; j += 32) retire<POLICY>(d, s, j, sbase + j, seed0 + j, a);
+        const int iters = nv + (last ? 1 : 0);  // the window end is the final pseudo-event
+        for (int i = 0; i < iters; i++) {
+            const bool real = i < nv;
+            const float ash = __shfl_sync(MLB_FULL, at, i & 31);
+            const float wk = __shfl_sync(MLB_FULL, awk, i & 31);
+            const float a = real ? ash : t1;
+            // --- retire every flow that finished strictly before this event
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (hf[r] < a) {
+                    const int j = lane + 32 * r;
+                    uint32_t h = sm[F_HEAD * SP + j];
+                    int n = (int)sm[F_NON * SP + j];
+                    float fin = hf[r];
+                    do {
+                        const float arr = g.ring_arr[j * Q + h];
+                        h = (h + 1 == (uint32_t)Q) ? 0u : h + 1;
+                        n -= 1;                                             // src/vpp/lb/lbhash.h:120
+                        res_add<SP>(d, sm, g, 0, j, __fsub_rn(fin, arr), fin);  // lbhash.h:122-124
+                        fin = n > 0 ? g.ring_fin[j * Q + h] : MLB_INF;
+                    } while (fin < a);
+                    hf[r] = fin;
+                    sm[F_HEAD * SP + j] = h;
+                    sm[F_NON * SP + j] = (uint32_t)n;
+                    if (!kAlias) sc[r] = server_score<POLICY>(d, n, sm[F_ACT * SP + j]);
+                }
+            }
             __syncwarp();
+            if (!real) break;
+            // --- choose a server
             int kstar;
             if (kAlias) {
                 const int b = __shfl_sync(MLB_FULL, abk, i);
                 const float u = __shfl_sync(MLB_FULL, au, i);
-                kstar = ((double)u < s.prob[b]) ? b : s.alias[b];  // test_integration.py:57-63
+                kstar = ((double)u < a_prob[b]) ? b : a_alias[b];           // test_integration.py:57-63
             } else {
-                uint32_t bkey = 0xffffffffu;
-                int bj = 0x7fffffff;
-                for (int j = lane; j < Sa; j += 32) {
-                    const uint32_t key = s.score[j];
-                    if (key < bkey) { bkey = key; bj = j; }  // strict <: first minimum wins
+                uint32_t bkey = sc[0];
+                int bj = lane;
+#pragma unroll
+                for (int r = 1; r < R; r++) {
+                    if (sc[r] < bkey) { bkey = sc[r]; bj = lane + 32 * r; }  // strict <: first minimum wins
                 }
                 const uint32_t mkey = __reduce_min_sync(MLB_FULL, bkey);
                 kstar = (int)__reduce_min_sync(MLB_FULL, (uint32_t)(bkey == mkey ? bj : 0x7fffffff));
             }
+            // --- push on that server's FIFO ring (owner lane)
             if (lane == (kstar & 31)) {
                 const int k = kstar;
-                const int n = s.n_on[k];
-                if (n >= d.Q) {
-                    s.dropped[k] += 1;  // [B] drop-and-count
+                const int n = (int)sm[F_NON * SP + k];
+                if (n >= Q) {
+                    atomicAdd(d.dropped + sbase + k, 1u);                   // [B] drop-and-count
                 } else {
-                    const float start = fmaxf(s.last_fin[k], a);
-                    const float fin = __fadd_rn(start, __fdiv_rn(wk, s.speed[k]));
-                    uint32_t pos = s.head[k] + (uint32_t)n;
-                    if (pos >= (uint32_t)d.Q) pos -= (uint32_t)d.Q;
-                    const size_t rb = (sbase + k) * d.Q;
-                    d.ring_arr[rb + pos] = a;
-                    d.ring_fin[rb + pos] = fin;
-                    if (n == 0) s.head_fin[k] = fin;
-                    s.last_fin[k] = fin;
-                    s.n_on[k] = n + 1;  // lbhash.h:142,167
-                    if (!kAlias) s.score[k] = server_score<POLICY>(n + 1, s.weight[k]);
+                    const float start = fmaxf(smf[F_LASTFIN * SP + k], a);
+                    const float fin = __fadd_rn(start, __fdiv_rn(wk, __ldg(d.speed + sbase + k)));
+                    uint32_t pos = sm[F_HEAD * SP + k] + (uint32_t)n;
+                    if (pos >= (uint32_t)Q) pos -= (uint32_t)Q;
+                    g.ring_arr[k * Q + pos] = a;
+                    g.ring_fin[k * Q + pos] = fin;
+                    smf[F_LASTFIN * SP + k] = fin;
+                    sm[F_NON * SP + k] = (uint32_t)(n + 1);                 // lbhash.h:142,167
+                    uint32_t nsc = 0;
+                    if (!kAlias) nsc = server_score<POLICY>(d, n + 1, sm[F_ACT * SP + k]);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        if ((k >> 5) == r) {
+                            if (n == 0) hf[r] = fin;
+                            sc[r] = nsc;
+                        }
+                    }
                 }
+                if (d.record_assign) d.assign[aoff + cur + i] = seed0 + k;
             }
-            if (d.record_assign && lane == 0) d.assign[aoff + cur + i] = seed0 + kstar;
             __syncwarp();
         }
         cur += nv;
-        if (nv < 32) break;
+        if (last) break;
     }
     if (lane == 0) d.arr_cur[ea] = cur;
 
-    // ---------------- phase C: window end ------------------------------------
-    for (int j = lane; j < Sa; j += 32) {
-        const size_t srv = sbase + j;
-        retire<POLICY>(d, s, j, srv, seed0 + j, t1);
-        const int n = s.n_on[j];
-        uint32_t pos = s.head[j];
-        const size_t rb = srv * d.Q;
-        for (int q = 0; q < n; q++) {  // lbhash.h:131-135, one sample per active flow per step
-            const float arr = d.ring_arr[rb + pos];
-            res_add(d, s, 1, j, srv, seed0 + j, __fsub_rn(t1, arr), t1);
-            pos = (pos + 1 == (uint32_t)d.Q) ? 0u : pos + 1;
-        }
-        // write back per-server state and the n_flow_on column (features.py:274)
-        d.n_on[srv] = n;
-        d.last_fin[srv] = s.last_fin[j];
-        d.head[srv] = s.head[j];
-        d.dropped[srv] = s.dropped[j];
-        d.obs[srv * MLB_OBS_COLS] = (float)n;
+    // ---------------- phase C: flow_duration samples, state write-back -------
 #pragma unroll
-        for (int m = 0; m < 2; m++) {
-            const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
-            d.res_count[c] = s.cnt[m][j];
-            d.res_cursor[c] = s.cur[m][j];
+    for (int r = 0; r < R; r++) {
+        const int j = lane + 32 * r;
+        if (j < Sa) {
+            const size_t gi = sbase + j;
+            const int n = (int)sm[F_NON * SP + j];
+            uint32_t pos = sm[F_HEAD * SP + j];
+            d.n_on[gi] = n;
+            d.last_fin[gi] = smf[F_LASTFIN * SP + j];
+            d.head[gi] = pos;
+            g.obs[j * MLB_OBS_COLS] = (float)n;                             // features.py:274
+            for (int q = 0; q < n; q++) {  // lbhash.h:131-135, one sample per active flow per step
+                const float arr = g.ring_arr[j * Q + pos];
+                res_add<SP>(d, sm, g, 1, j, __fsub_rn(t1, arr), t1);
+                pos = (pos + 1 == (uint32_t)Q) ? 0u : pos + 1;
+            }
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
+                d.res_count[c] = sm[(F_CNT0 + m) * SP + j];
+                d.res_cursor[c] = sm[(F_CUR0 + m) * SP + j];
+            }
         }
     }
     __syncwarp();
 
     // ---------------- phase B: statistics of touched reservoirs --------------
+    const bool all = d.feature_cache == 0;  // mode 0: recompute every reservoir
+#pragma unroll 1
     for (int jb = 0; jb < SP; jb += 32) {
         const int j = jb + lane;
-        uint32_t fl = 0;
-        if (j < Sa) fl = d.feature_cache ? s.flags[j] : 3u;  // mode 0: recompute every reservoir
-#pragma unroll
+        const uint32_t fl = j < Sa ? (all ? 3u : sm[F_FLAGS * SP + j]) : 0u;
+#pragma unroll 1
         for (int m = 0; m < 2; m++) {
             unsigned todo = __ballot_sync(MLB_FULL, (fl >> m) & 1u);
+#pragma unroll 1
             while (todo) {
                 const int jj = jb + __ffs(todo) - 1;
                 todo &= todo - 1;
-                const uint32_t cnt = s.cnt[m][jj];
+                const uint32_t cnt = sm[(F_CNT0 + m) * SP + jj];
                 const int n = cnt < (uint32_t)d.K ? (int)cnt : d.K;
-                const size_t rid = ((sbase + jj) * 2 + m) * d.KP;
-                uint32_t mw[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) mw[k] = s.chg[(m * 4 + k) * s.sp + jj];
-                const int nchg = __popc(mw[0]) + __popc(mw[1]) + __popc(mw[2]) + __popc(mw[3]);
+                const int n_old = (int)((sm[F_NOLD * SP + jj] >> (8 * m)) & 255u);
+                const uint32_t* mws = sm + (F_CHG + m * 4) * SP + jj;
+                const int nchg = __popc(mws[0]) + __popc(mws[SP]) + __popc(mws[2 * SP]) + __popc(mws[3 * SP]);
+                const int rid = (jj * 2 + m) * d.KP;
                 float f[5];
-                warp_features_cached(d.res_val + rid, d.res_ts + rid, d.res_rank + rid, n, (int)s.nold[m][jj],
-                                     mw, nchg, d.feature_cache != 1, t1, d.decay, d.log2_decay, scratch, f);
+                warp_features_cached(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, n_old, mws, SP,
+                                     nchg, d.feature_cache != 1, t1, d.decay, d.log2_decay, scratch, f);
                 float mine = f[0];
 #pragma unroll
                 for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
-                if (lane < 5) d.obs[(sbase + jj) * MLB_OBS_COLS + 1 + 5 * m + lane] = mine;
+                if (lane < 5) g.obs[jj * MLB_OBS_COLS + 1 + 5 * m + lane] = mine;
             }
         }
     }
     __syncwarp();
 
     // ---------------- phase R: reward over the env's active servers ----------
+#pragma unroll 1
     for (int j = lane; j < Sa; j += 32) {
-        const float* row = d.obs + (sbase + j) * MLB_OBS_COLS;
+        const float* row = g.obs + j * MLB_OBS_COLS;
         bool active = false;  // env.py:410-413
         float x = 0.f;
 #pragma unroll
@@ -478,7 +499,7 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
         rv[seed0 + j] = x;
         ra[seed0 + j] = active ? 1u : 0u;
     }
-    if (SINGLE) {
+    if (A == 1) {
         __syncwarp();
     } else if (env_in_blk == 0) {  // at most 2 envs per block when A > 1: static barrier ids
         asm volatile("bar.sync 1, %0;" ::"r"(A * 32) : "memory");
@@ -486,9 +507,9 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
         asm volatile("bar.sync 2, %0;" ::"r"(A * 32) : "memory");
     }
     if (agent == 0) {
-        const double r = reward_staged(d.reward_metric, rv, ra, S);
+        const double rw = reward_staged<float>(d.reward_metric, rv, ra, S);
         if (lane == 0) {
-            d.reward[e] = r;                               // multi_agent_env.py:143-145: same scalar for all agents
+            d.reward[e] = rw;                              // multi_agent_env.py:143-145: same scalar for all agents
             d.done[e] = step >= d.max_steps ? 1 : 0;       // env.py:267
             d.step[e] = step;
         }
