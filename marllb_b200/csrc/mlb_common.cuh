@@ -60,6 +60,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // streaming (evict-first) global accesses for data touched once per step
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     return __ldcs(reinterpret_cast<const float4*>(p));

@@ -217,69 +217,111 @@ __device__ __forceinline__ void ranks_full_sort(const float (&v)[EPL], int n, in
 // Ties are ordered by slot index; any order of equal values is a valid sorted order.
 template <int EPL>
 __device__ __forceinline__ void ranks_update(const float (&v)[EPL], int (&rk)[EPL], int n_new, int n_old,
-                                             const uint32_t* mws, int stride, int lane) {
-    // mws[k * stride], k = 0..3: mask words in shared memory (warp-uniform addresses)
+                                             const uint32_t* mws, int stride, int nchg,
+                                             const WarpScratch& sc, int lane) {
+    // mws[k * stride], k = 0..3: mask words in shared memory (warp-uniform addresses).
+    // Every changed slot is published as (new value, slot, old rank) in a small shared list;
+    // then each lane fixes the ranks of its own slots in ONE pass over that list:
+    //   unchanged slot i : rank - #{removed with lower old rank} + #{inserted (x,c) < (v_i,i)}
+    //   changed slot c   : #{unchanged (v_i,i) < (x_c,c)} + #{inserted (x,c') < (x_c,c)}
     constexpr int NW = EPL == 4 ? 4 : EPL;  // words that can hold slots < 32*EPL
     const int s0 = lane * EPL;
-    const uint32_t word = mws[(s0 >> 5) * stride];
+    const int wi = s0 >> 5;
+    uint32_t word = mws[0];
+    int below = 0;
+    if constexpr (NW >= 2) {
+        const uint32_t m1 = mws[stride];
+        below = wi >= 1 ? __popc(word) : 0;
+        word = wi == 1 ? m1 : word;
+        if constexpr (NW == 4) {
+            const uint32_t m2 = mws[2 * stride], m3 = mws[3 * stride];
+            below += wi >= 2 ? __popc(m1) : 0;
+            below += wi >= 3 ? __popc(m2) : 0;
+            word = wi == 2 ? m2 : (wi == 3 ? m3 : word);
+        }
+    }
     const uint32_t chg = (word >> (s0 & 31)) & ((1u << EPL) - 1u);
-    uint32_t pres = 0;
-    int dec[EPL];
+    below += __popc(word & ((1u << (s0 & 31)) - 1u));
+    float* Lx = sc.sv;
+    int* Lc = reinterpret_cast<int*>(sc.sw);
+    int* Lr = Lc + 32;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        dec[r] = 0;
-        if (s0 + r < n_new && !((chg >> r) & 1u)) pres |= 1u << r;
-    }
-    // pass 1: remove the old ranks of replaced slots (compare against ORIGINAL ranks)
-#pragma unroll 1
-    for (int w = 0; w < NW; w++) {
-        uint32_t bits = mws[w * stride];
-#pragma unroll 1
-        while (bits) {
-            const int c = w * 32 + __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (c < n_old) {
-                const int rc = slot_fetch<EPL, int>(rk, c);
-#pragma unroll
-                for (int r = 0; r < EPL; r++) dec[r] += rk[r] > rc ? 1 : 0;
-            }
+        if ((chg >> r) & 1u) {
+            Lx[below] = v[r];
+            Lc[below] = s0 + r;
+            Lr[below] = s0 + r < n_old ? rk[r] : 1000;  // 1000: did not exist, removes nothing
+            below++;
         }
     }
+    __syncwarp();
+    int adj[EPL], self[EPL];
 #pragma unroll
-    for (int r = 0; r < EPL; r++) rk[r] -= dec[r];
-    // pass 2: insert the new values one at a time
+    for (int r = 0; r < EPL; r++) { adj[r] = 0; self[r] = 0; }
 #pragma unroll 1
-    for (int w = 0; w < NW; w++) {
-        uint32_t bits = mws[w * stride];
-#pragma unroll 1
-        while (bits) {
-            const int c = w * 32 + __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (c >= n_new) continue;
-            const float x = slot_fetch<EPL, float>(v, c);
-            int less = 0;
+    for (int k = 0; k < nchg; k++) {
+        const float x = Lx[k];
+        const int c = Lc[k], rold = Lr[k];
+        int cnt = 0;
 #pragma unroll
-            for (int r = 0; r < EPL; r++) {
-                const bool lt = v[r] < x || (v[r] == x && s0 + r < c);
-                less += (((pres >> r) & 1u) && lt) ? 1 : 0;
-            }
-            const int rnew = __reduce_add_sync(MLB_FULL, less);
-#pragma unroll
-            for (int r = 0; r < EPL; r++) {
-                if (((pres >> r) & 1u) && rk[r] >= rnew) rk[r] += 1;
-                if (s0 + r == c) {
-                    rk[r] = rnew;
-                    pres |= 1u << r;
-                }
-            }
+        for (int r = 0; r < EPL; r++) {
+            const int slot = s0 + r;
+            const bool lt = x < v[r] || (x == v[r] && c < slot);  // (x_k, c_k) < (v_i, i)
+            const bool unchanged = slot < n_new && !((chg >> r) & 1u);
+            adj[r] += lt ? 1 : 0;
+            adj[r] -= (unchanged && rk[r] > rold) ? 1 : 0;
+            cnt += (unchanged && !lt) ? 1 : 0;  // strict total order: !lt <=> (v_i, i) < (x_k, c_k)
         }
+        const int tot = __reduce_add_sync(MLB_FULL, cnt);
+#pragma unroll
+        for (int r = 0; r < EPL; r++) self[r] = (s0 + r == c) ? tot : self[r];
     }
+#pragma unroll
+    for (int r = 0; r < EPL; r++) rk[r] = (((chg >> r) & 1u) ? self[r] : rk[r]) + adj[r];
+    __syncwarp();  // the list lives in the scratch that features_ranked overwrites next
 }
 
-// Cold path of the weighted percentile: the reference's float64 arithmetic
-// (reservoir.py:148-149,181-196): w = pow(decay, now - t) and a strictly sequential cumsum
-// in value order.  st = timestamps in rank order (shared memory), n <= 128.  Returns the
-// searchsorted-left index of 0.9 * cumsum[-1] (n if none).
+// Cold paths of the weighted percentile, taken when the float32 cumulative weights come
+// within MLB_WP_MARGIN of the cutoff.  st = timestamps in rank order (shared memory), n <= 128.
+//
+// Tier 2: float64 weights 2^(log2(decay) * (tmax - t)) and a float64 warp scan; decides unless
+// a cumulative weight is within 1e-9 (relative) of the cutoff, i.e. a genuine tie.
+static __device__ __noinline__ int weighted_index_scan_f64(const float* st, int n, float tmax, double decay,
+                                                           bool* ambiguous) {
+    const int lane = lane_id();
+    const double l2d = log2(decay);
+    double w[4], c[4];
+    double carry = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {  // position p = k*32 + lane
+        const int pos = k * 32 + lane;
+        w[k] = pos < n ? exp2(l2d * ((double)tmax - (double)st[pos])) : 0.0;
+        double sc = w[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(MLB_FULL, sc, o);
+            if (lane >= o) sc += y;
+        }
+        c[k] = carry + sc;
+        carry = __shfl_sync(MLB_FULL, c[k], 31);
+    }
+    const double cut = 0.9 * carry;
+    int below = 0;
+    double dmin = 1.0e308;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool valid = k * 32 + lane < n;
+        below += (valid && c[k] < cut) ? 1 : 0;
+        dmin = valid ? fmin(dmin, fabs(c[k] - cut)) : dmin;
+    }
+    dmin = warp_min(dmin);
+    *ambiguous = dmin < 1e-9 * carry;
+    return __reduce_add_sync(MLB_FULL, below);
+}
+
+// Tier 3: the reference's own arithmetic (reservoir.py:148-149,181-196): w = pow(decay, now - t)
+// and a strictly sequential cumsum in value order.  Returns the searchsorted-left index of
+// 0.9 * cumsum[-1] (n if none).
 static __device__ __noinline__ int weighted_index_f64(const float* st, int n, float now, double decay) {
     const int lane = lane_id();
     double w[4];
@@ -377,7 +419,9 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
         for (int r = 0; r < EPL; r++)
             if (s0 + r < n) sc.sw[rk[r]] = t[r];
         __syncwarp();
-        idx = weighted_index_f64(sc.sw, n, now, decay);
+        bool ambiguous;
+        idx = weighted_index_scan_f64(sc.sw, n, tmax, decay, &ambiguous);
+        if (ambiguous) idx = weighted_index_f64(sc.sw, n, now, decay);
     }
     idx = idx > n - 1 ? n - 1 : idx;  // reservoir.py:193-194
     // ---- p90 = np.percentile(values, 90): float32 'linear' rule of numpy >= 2
@@ -456,7 +500,7 @@ __device__ __forceinline__ void features_cached_epl(const float* __restrict__ va
         ranks_full_sort<EPL>(v, n, rk, sc, lane);
     } else {
         load_ranks<EPL>(ranks, lane, rk);
-        ranks_update<EPL>(v, rk, n, n_old, mws, stride, lane);
+        ranks_update<EPL>(v, rk, n, n_old, mws, stride, nchg, sc, lane);
     }
     store_ranks<EPL>(ranks, lane, rk);
     features_ranked<EPL>(v, t, rk, n, now, decay, log2_decay, sc, out);

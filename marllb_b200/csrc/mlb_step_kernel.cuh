@@ -38,7 +38,8 @@ enum : int {
     F_FLAGS,     // bit0/bit1: reservoir m touched this step
     F_NOLD,      // valid slots at step start: fct | flow_duration << 8
     F_CHG,       // 8 words: [metric][word] mask of reservoir slots written this step
-    NF = F_CHG + 8
+    F_LIST = F_CHG + 8,  // 2*SP uint16: compact list of (server*2 + metric) to re-evaluate
+    NF
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(int SP, bool alias) {
@@ -454,33 +455,59 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
     __syncwarp();
 
     // ---------------- phase B: statistics of touched reservoirs --------------
+    // Compact the dirty (server, metric) pairs into a list first: the loop body is then a
+    // plain counted loop and the next reservoir can be prefetched into L2 while this one is
+    // being evaluated.
     const bool all = d.feature_cache == 0;  // mode 0: recompute every reservoir
-#pragma unroll 1
-    for (int jb = 0; jb < SP; jb += 32) {
-        const int j = jb + lane;
-        const uint32_t fl = j < Sa ? (all ? 3u : sm[F_FLAGS * SP + j]) : 0u;
-#pragma unroll 1
-        for (int m = 0; m < 2; m++) {
-            unsigned todo = __ballot_sync(MLB_FULL, (fl >> m) & 1u);
-#pragma unroll 1
-            while (todo) {
-                const int jj = jb + __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t cnt = sm[(F_CNT0 + m) * SP + jj];
-                const int n = cnt < (uint32_t)d.K ? (int)cnt : d.K;
-                const int n_old = (int)((sm[F_NOLD * SP + jj] >> (8 * m)) & 255u);
-                const uint32_t* mws = sm + (F_CHG + m * 4) * SP + jj;
-                const int nchg = __popc(mws[0]) + __popc(mws[SP]) + __popc(mws[2 * SP]) + __popc(mws[3 * SP]);
-                const int rid = (jj * 2 + m) * d.KP;
-                float f[5];
-                warp_features_cached(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, n_old, mws, SP,
-                                     nchg, d.feature_cache != 1, t1, d.decay, d.log2_decay, scratch, f);
-                float mine = f[0];
+    uint16_t* dlist = reinterpret_cast<uint16_t*>(sm + F_LIST * SP);
+    int nd = 0;
 #pragma unroll
-                for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
-                if (lane < 5) g.obs[jj * MLB_OBS_COLS + 1 + 5 * m + lane] = mine;
-            }
+    for (int r = 0; r < R; r++) {
+        const int j = lane + 32 * r;
+        const uint32_t fl = j < Sa ? (all ? 3u : sm[F_FLAGS * SP + j]) : 0u;
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            const bool dirty = (fl >> m) & 1u;
+            const unsigned bal = __ballot_sync(MLB_FULL, dirty);
+            if (dirty) dlist[nd + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(j * 2 + m);
+            nd += __popc(bal);
         }
+    }
+    __syncwarp();
+    const int KP = d.KP;
+    if (nd > 0) {
+        const int rid0 = (int)dlist[0] * KP;
+        if (lane * 4 < KP) {
+            prefetch_l2(g.res_val + rid0 + lane * 4);
+            prefetch_l2(g.res_ts + rid0 + lane * 4);
+        }
+        if (lane == 0) prefetch_l2(g.res_rank + rid0);
+    }
+#pragma unroll 1
+    for (int i = 0; i < nd; i++) {
+        const int id = dlist[i];
+        if (i + 1 < nd) {
+            const int ridn = (int)dlist[i + 1] * KP;
+            if (lane * 4 < KP) {
+                prefetch_l2(g.res_val + ridn + lane * 4);
+                prefetch_l2(g.res_ts + ridn + lane * 4);
+            }
+            if (lane == 0) prefetch_l2(g.res_rank + ridn);
+        }
+        const int jj = id >> 1, m = id & 1;
+        const uint32_t cnt = sm[(F_CNT0 + m) * SP + jj];
+        const int n = cnt < (uint32_t)d.K ? (int)cnt : d.K;
+        const int n_old = (int)((sm[F_NOLD * SP + jj] >> (8 * m)) & 255u);
+        const uint32_t* mws = sm + (F_CHG + m * 4) * SP + jj;
+        const int nchg = __popc(mws[0]) + __popc(mws[SP]) + __popc(mws[2 * SP]) + __popc(mws[3 * SP]);
+        const int rid = id * KP;
+        float f[5];
+        warp_features_cached(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, n_old, mws, SP, nchg,
+                             d.feature_cache != 1, t1, d.decay, d.log2_decay, scratch, f);
+        float mine = f[0];
+#pragma unroll
+        for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
+        if (lane < 5) g.obs[jj * MLB_OBS_COLS + 1 + 5 * m + lane] = mine;
     }
     __syncwarp();
 
