@@ -1,0 +1,124 @@
+/*
+ * marllb_b200_policy.h -- C ABI of the batched policy kernels (QMIX / SAC-GRU rows of
+ * a13-a19).  All pointers are DEVICE pointers to float32 unless noted; every
+ * function is asynchronous on `stream` (cudaStream_t as void*) and returns 0 or a negative
+ * MLB_E* code (include/marllb_b200.h).
+ *
+ * Reference modules these kernels stand in for (paths relative to simulation-mode/):
+ *   problem-05-qmix/src/agent_network.py:63-87     AgentQNetwork.forward  (GRU cell + 3 linears)
+ *   problem-05-qmix/src/mixing_network.py:78-117   QMixingNetwork.forward (hypernets, |.|, bmm, ELU)
+ *   problem-05-qmix/src/qmix_agent.py:126-170,192-307  select_actions / update
+ *   problem-04-sac-gru/src/networks.py:82-147,209-237  PolicyNetwork.forward/sample, QNetwork.forward
+ *   problem-04-sac-gru/src/sac_agent.py:124-255    select_action / update_parameters
+ * Parameter tensors keep torch's layouts (nn.Linear weight [out][in]; nn.GRU weight_ih [3H][in],
+ * gate order r,z,n) so reference state_dicts load unchanged.
+ */
+#ifndef MARLLB_B200_POLICY_H
+#define MARLLB_B200_POLICY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MLB_ACT_NONE = 0, MLB_ACT_RELU = 1, MLB_ACT_ABS = 2 };
+
+/*
+ * Batched strided GEMM with fused bias / activation epilogue (fp32, FFMA):
+ *   C[b][m][n] = act( beta*C[b][m][n] + sum_k A[b](m,k) * B[b](k,n) + bias[b][n] )
+ *   A(m,k) = A[b*a_bs + m*a_rs + k*a_cs],  B(k,n) = B[b*b_bs + k*b_rs + n*b_cs],
+ *   C row-major with leading dimension ldc and batch stride c_bs; bias nullable, stride bias_bs.
+ * Covers nn.Linear forward (B = W^T: b_rs=1, b_cs=K), input gradients (B = W) and weight
+ * gradients (A = dY^T) with accumulation (beta = 1).
+ */
+int mlb_gemm(const float *A, int64_t a_bs, int64_t a_rs, int64_t a_cs,
+             const float *B, int64_t b_bs, int64_t b_rs, int64_t b_cs,
+             float *C, int64_t c_bs, int64_t ldc, const float *bias, int64_t bias_bs,
+             int32_t M, int32_t N, int32_t K, int32_t batch, float beta, int32_t act, void *stream);
+
+/* nn.GRU single step, gate part (torch gate order r,z,n):
+ *   gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (computed by mlb_gemm), both [M][3H];
+ *   r = sigmoid(gi_r+gh_r), z = sigmoid(gi_z+gh_z), n = tanh(gi_n + r*gh_n), h' = (1-z)*n + z*h.
+ * gates (nullable) receives [M][3H] = (r, z, n) for the backward pass. */
+int mlb_gru_gates_forward(const float *gi, const float *gh, const float *h, float *h_new,
+                          float *gates, int32_t M, int32_t H, void *stream);
+/* backward of the above: given dh_new, saved gates, h and gh_n (= gh[:, 2H:3H]) produce
+ * dgi [M][3H], dgh [M][3H] and dh_direct [M][H] (= dh_new * z; caller adds dgh W_hh). */
+int mlb_gru_gates_backward(const float *dh_new, const float *gates, const float *h, const float *gh,
+                           float *dgi, float *dgh, float *dh_direct, int32_t M, int32_t H, void *stream);
+
+/* elementwise / reductions */
+int mlb_relu_backward(const float *y, const float *dy, float *dx, int64_t n, void *stream); /* dx = dy*(y>0) */
+int mlb_colsum(const float *dy, float *db, int32_t M, int32_t N, int64_t ld, float beta, void *stream); /* db = beta*db + sum_m dy */
+int mlb_axpby(float a, const float *x, float b, float *y, int64_t n, void *stream);       /* y = a*x + b*y (soft update: networks.py:248-260) */
+int mlb_sumsq(const float *x, int64_t n, double *out_accum, void *stream);                 /* *out += sum x^2 (clip_grad_norm_) */
+int mlb_scale(float *x, int64_t n, const double *norm_sq, float max_norm, void *stream);   /* x *= min(1, max_norm/(sqrt(norm_sq)+1e-6)) */
+/* torch.optim.Adam step (no weight decay, no amsgrad): p, g, m, v of n elements; step = t >= 1 */
+int mlb_adam(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1,
+             float beta2, float eps, int32_t step, void *stream);
+
+/* QMIX epsilon-greedy selection (qmix_agent.py:159-164): q [M][K]; u [M] uniform draws,
+ * rnd [M] int32 pre-drawn random actions; action = u < epsilon ? rnd : argmax (first max). */
+int mlb_egreedy_select(const float *q, const float *u, const int32_t *rnd, float epsilon,
+                       int32_t *action, float *q_sel, int32_t M, int32_t K, void *stream);
+/* row max (target Q: qmix_agent.py:253) and gather q[m][idx[m]] */
+int mlb_row_max(const float *q, float *out, int32_t *argmax, int32_t M, int32_t K, void *stream);
+
+/* QMIX mixer core (mixing_network.py:104-116) for M samples, A agents, E embed:
+ *   hidden = elu(q[M][A] . w1[M][A][E] + b1[M][E]);  q_tot = hidden . w2[M][E] + b2[M]
+ * (w1, w2 already |.|'d by the hypernet epilogue).  hidden_out nullable [M][E]. */
+int mlb_mixer_forward(const float *q, const float *w1, const float *b1, const float *w2,
+                      const float *b2, float *q_tot, float *hidden_out, int32_t M, int32_t A,
+                      int32_t E, void *stream);
+/* backward: dq_tot [M] -> dq [M][A], dw1 [M][A][E], db1 [M][E], dw2 [M][E], db2 [M]
+ * (gradients w.r.t. the |.|'d tensors; the abs backward is sign(pre) applied by the caller op). */
+int mlb_mixer_backward(const float *dq_tot, const float *q, const float *w1, const float *w2,
+                       const float *hidden, float *dq, float *dw1, float *db1, float *dw2,
+                       float *db2, int32_t M, int32_t A, int32_t E, void *stream);
+int mlb_abs_backward(const float *pre, const float *dy, float *dx, int64_t n, void *stream); /* dx = dy*sign(pre) */
+
+/* SAC tanh-Gaussian head (networks.py:112-147) on [M][A] tensors:
+ *   log_std clamped to [lo,hi]; x = mean + exp(log_std)*eps; y = tanh(x); action = y*scale+bias;
+ *   logp[m] = sum_a( -0.5*eps^2 - log_std - 0.5*log(2pi) - log(scale*(1-y^2)+1e-6) );
+ *   mean_action = tanh(mean)*scale + bias. */
+int mlb_tanh_gaussian_forward(const float *mean, const float *log_std_raw, const float *eps,
+                              float lo, float hi, float scale, float bias, float *action,
+                              float *logp, float *mean_action, int32_t M, int32_t A, void *stream);
+/* backward: d_action [M][A] and d_logp [M] -> d_mean, d_log_std_raw (zero where clamped) */
+int mlb_tanh_gaussian_backward(const float *mean, const float *log_std_raw, const float *eps,
+                               float lo, float hi, float scale, const float *d_action,
+                               const float *d_logp, float *d_mean, float *d_log_std_raw,
+                               int32_t M, int32_t A, void *stream);
+
+int mlb_abs_forward(const float *x, float *y, int64_t n, void *stream);                     /* y = |x| (mixing_network.py:92,99) */
+
+/* QMIX TD loss (qmix_agent.py:263-278) over [B][T] row-major tensors:
+ *   targets = reward_sum + gamma*(1-done)*shift(target_q_tot)   (shift: t <- t+1, last column 0)
+ *   mask[b][t] = t < seq_len[b];  loss = sum((q_tot-targets)^2*mask)/sum(mask)
+ * writes targets, dq_tot = 2*(q_tot-targets)*mask/sum(mask) and stats[0..2] (double) =
+ * {loss, mean(q_tot), mean(targets)} (means over ALL B*T entries like the reference's .mean()). */
+int mlb_qmix_td_loss(const float *q_tot, const float *target_q_tot, const float *reward_sum,
+                     const float *done, const int32_t *seq_len, float gamma, float *targets,
+                     float *dq_tot, double *stats, int32_t B, int32_t T, void *stream);
+
+/* SAC critic target (sac_agent.py:180-190): y = r + (1-d)*gamma*(min(q1n,q2n) - alpha*logp_next) */
+int mlb_sac_q_target(const float *reward, const float *done, const float *q1n, const float *q2n,
+                     const float *logp_next, const float *alpha, float gamma, float *y, int32_t M,
+                     void *stream);
+/* F.mse_loss(q, y) (mean) and its gradient dq = 2*(q-y)/M; loss (double) accumulated into *loss */
+int mlb_mse_loss(const float *q, const float *y, float *dq, double *loss, int32_t M, void *stream);
+/* SAC actor loss (sac_agent.py:210-216): L = mean(alpha*logp - min(q1,q2));
+ * d_logp = alpha/M, dq1/dq2 = -1/M routed to the smaller critic (ties: q1, like torch.min). */
+int mlb_sac_policy_loss(const float *logp, const float *q1, const float *q2, const float *alpha,
+                        float *d_logp, float *dq1, float *dq2, double *loss, int32_t M, void *stream);
+/* temperature loss (sac_agent.py:223-231): L = -mean(log_alpha*(logp+target_entropy));
+ * writes d_log_alpha[0] = -mean(logp+target_entropy) and *loss. */
+int mlb_sac_alpha_loss(const float *logp, const float *log_alpha, float target_entropy,
+                       float *d_log_alpha, double *loss, int32_t M, void *stream);
+int mlb_exp_scalar(const float *x, float *y, void *stream);                                  /* y[0] = exp(x[0]) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

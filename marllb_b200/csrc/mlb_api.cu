@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -192,7 +193,7 @@ static const void* step_fn(int policy, int Sa) {
 static int launch_cfg(mlb_env* h) {
     const mlb_config& c = h->cfg;
     const int A = c.num_agents;
-    h->epb = A == 1 ? 4 : (A == 2 ? 2 : 1);
+    h->epb = A == 1 ? (getenv("MLB_EPB") ? atoi(getenv("MLB_EPB")) : 4) : (A == 2 ? 2 : 1);
     h->threads = 32 * A * h->epb;
     const int SP = 32 * lanes_r(c.servers_per_agent);
     const bool alias = c.policy == MLB_POLICY_ALIAS;
@@ -204,7 +205,9 @@ static int launch_cfg(mlb_env* h) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess) {
         // shared-memory carve-out sized for 8 resident blocks (the rest stays L1)
-        size_t want = 8 * (h->smem_bytes + 1024);
+        const int wpb = h->threads / 32;
+        const int blocks_wanted = wpb >= 32 ? 1 : 32 / wpb;  // aim for 32 resident warps (64 regs)
+        size_t want = (size_t)blocks_wanted * (h->smem_bytes + 1024);
         int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
         pct = pct > 100 ? 100 : pct;
         e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);

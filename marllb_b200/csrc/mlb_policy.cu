@@ -1,0 +1,619 @@
+// Batched policy kernels behind include/marllb_b200_policy.h (QMIX / SAC-GRU, fp32).
+//
+// Reference modules: problem-05-qmix/src/{agent_network,mixing_network,qmix_agent}.py and
+// problem-04-sac-gru/src/{networks,sac_agent}.py (paths under simulation-mode/).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/marllb_b200.h"
+#include "../../include/marllb_b200_policy.h"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;  // 256 threads, 4x4 outputs each
+
+// C = act(beta*C + A.B + bias), generic strides, fp32 FFMA, shared-memory tiled.
+__global__ void __launch_bounds__(256)
+gemm_kernel(const float* __restrict__ A, int64_t a_bs, int64_t a_rs, int64_t a_cs,
+            const float* __restrict__ B, int64_t b_bs, int64_t b_rs, int64_t b_cs,
+            float* __restrict__ C, int64_t c_bs, int64_t ldc, const float* __restrict__ bias,
+            int64_t bias_bs, int M, int N, int K, float beta, int act) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int b = blockIdx.z;
+    A += (int64_t)b * a_bs;
+    B += (int64_t)b * b_bs;
+    C += (int64_t)b * c_bs;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);  // 16 x 16
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+    const bool a_kfast = (a_cs == 1);  // k contiguous in A -> walk k fastest when loading
+    const bool b_nfast = (b_cs == 1);  // n contiguous in B
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / 256; i++) {
+            const int t = tid + i * 256;
+            const int ml = a_kfast ? t / BK : t % BM;
+            const int kl = a_kfast ? t % BK : t / BM;
+            const int m = m0 + ml, k = k0 + kl;
+            As[kl][ml] = (m < M && k < K) ? A[(int64_t)m * a_rs + (int64_t)k * a_cs] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * BK) / 256; i++) {
+            const int t = tid + i * 256;
+            const int nl = b_nfast ? t % BN : t / BK;
+            const int kl = b_nfast ? t / BN : t % BK;
+            const int n = n0 + nl, k = k0 + kl;
+            Bs[kl][nl] = (n < N && k < K) ? B[(int64_t)k * b_rs + (int64_t)n * b_cs] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float a[TM], bb[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i++) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; j++) bb[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    if (bias) bias += (int64_t)b * bias_bs;
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        const int m = m0 + ty * TM + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            const int n = n0 + tx * TN + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[n];
+            if (beta != 0.f) v += beta * C[(int64_t)m * ldc + n];
+            if (act == MLB_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (act == MLB_ACT_ABS) v = fabsf(v);
+            C[(int64_t)m * ldc + n] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void gru_gates_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                     const float* __restrict__ h, float* __restrict__ h_new,
+                                     float* __restrict__ gates, int M, int H) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * H) return;
+    const int m = (int)(i / H), c = (int)(i % H);
+    const float* gim = gi + (int64_t)m * 3 * H;
+    const float* ghm = gh + (int64_t)m * 3 * H;
+    const float r = sigmoidf_(gim[c] + ghm[c]);
+    const float z = sigmoidf_(gim[H + c] + ghm[H + c]);
+    const float n = tanhf(gim[2 * H + c] + r * ghm[2 * H + c]);
+    h_new[i] = (1.f - z) * n + z * h[i];
+    if (gates) {
+        float* gm = gates + (int64_t)m * 3 * H;
+        gm[c] = r; gm[H + c] = z; gm[2 * H + c] = n;
+    }
+}
+
+__global__ void gru_gates_bwd_kernel(const float* __restrict__ dh_new, const float* __restrict__ gates,
+                                     const float* __restrict__ h, const float* __restrict__ gh,
+                                     float* __restrict__ dgi, float* __restrict__ dgh,
+                                     float* __restrict__ dh_direct, int M, int H) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * H) return;
+    const int m = (int)(i / H), c = (int)(i % H);
+    const float* gm = gates + (int64_t)m * 3 * H;
+    const float r = gm[c], z = gm[H + c], n = gm[2 * H + c];
+    const float g = dh_new[i];
+    const float dn = g * (1.f - z);
+    const float dz = g * (h[i] - n);
+    const float dan = dn * (1.f - n * n);
+    const float ghn = gh[(int64_t)m * 3 * H + 2 * H + c];
+    const float dar = dan * ghn * r * (1.f - r);
+    const float daz = dz * z * (1.f - z);
+    float* dgim = dgi + (int64_t)m * 3 * H;
+    float* dghm = dgh + (int64_t)m * 3 * H;
+    dgim[c] = dar; dgim[H + c] = daz; dgim[2 * H + c] = dan;
+    dghm[c] = dar; dghm[H + c] = daz; dghm[2 * H + c] = dan * r;
+    dh_direct[i] = g * z;
+}
+
+__global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+__global__ void abs_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dy, float* __restrict__ dx, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float p = pre[i];
+        dx[i] = p > 0.f ? dy[i] : (p < 0.f ? -dy[i] : 0.f);  // torch.abs: grad * sign(x)
+    }
+}
+
+// db[n] = beta*db[n] + sum_m dy[m][n]; one block per 32 columns, 8 row-lanes
+__global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int N, int64_t ld, float beta) {
+    __shared__ float part[8][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (n < N)
+        for (int m = threadIdx.y; m < M; m += 8) s += dy[(int64_t)m * ld + n];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += part[k][threadIdx.x];
+        db[n] = (beta != 0.f ? beta * db[n] : 0.f) + t;
+    }
+}
+
+__global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a * x[i] + b * y[i];
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, double* out) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        s += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+__global__ void scale_kernel(float* __restrict__ x, int64_t n, const double* __restrict__ norm_sq, float max_norm) {
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+    const float total = (float)sqrt(*norm_sq);
+    float coef = max_norm / (total + 1e-6f);
+    coef = coef > 1.f ? 1.f : coef;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= coef;
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float beta1, float beta2, float eps,
+                            float step_size, float bc2_sqrt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;        // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;   // exp_avg_sq.mul_(beta2).addcmul_(g,g,1-beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+}
+
+__global__ void egreedy_kernel(const float* __restrict__ q, const float* __restrict__ u, const int32_t* __restrict__ rnd,
+                               float epsilon, int32_t* __restrict__ action, float* __restrict__ q_sel, int M, int K) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float* qm = q + (int64_t)m * K;
+    int best = 0;
+    float bv = qm[0];
+    for (int k = 1; k < K; k++)
+        if (qm[k] > bv) { bv = qm[k]; best = k; }   // first maximum
+    int a = best;
+    if (u && u[m] < epsilon) a = rnd[m];            // qmix_agent.py:159-161
+    action[m] = a;
+    if (q_sel) q_sel[m] = qm[a];
+}
+
+__global__ void row_max_kernel(const float* __restrict__ q, float* __restrict__ out, int32_t* __restrict__ arg, int M, int K) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float* qm = q + (int64_t)m * K;
+    int best = 0;
+    float bv = qm[0];
+    for (int k = 1; k < K; k++)
+        if (qm[k] > bv) { bv = qm[k]; best = k; }
+    out[m] = bv;
+    if (arg) arg[m] = best;
+}
+
+// one warp per sample
+__global__ void mixer_fwd_kernel(const float* __restrict__ q, const float* __restrict__ w1, const float* __restrict__ b1,
+                                 const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ q_tot,
+                                 float* __restrict__ hidden_out, int M, int A, int E) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (m >= M) return;
+    float acc = 0.f;
+    for (int e = lane; e < E; e += 32) {
+        float pre = b1[(int64_t)m * E + e];
+        for (int a = 0; a < A; a++) pre = fmaf(q[(int64_t)m * A + a], w1[((int64_t)m * A + a) * E + e], pre);
+        const float hdn = pre > 0.f ? pre : expm1f(pre);   // F.elu, alpha = 1
+        if (hidden_out) hidden_out[(int64_t)m * E + e] = hdn;
+        acc = fmaf(hdn, w2[(int64_t)m * E + e], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) q_tot[m] = acc + b2[m];
+}
+
+__global__ void mixer_bwd_kernel(const float* __restrict__ dq_tot, const float* __restrict__ q, const float* __restrict__ w1,
+                                 const float* __restrict__ w2, const float* __restrict__ hidden, float* __restrict__ dq,
+                                 float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
+                                 float* __restrict__ db2, int M, int A, int E) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float g = dq_tot[m];
+    if (lane == 0) db2[m] = g;
+    for (int a = 0; a < A; a++) {
+        float s = 0.f;
+        for (int e = lane; e < E; e += 32) {
+            const float hdn = hidden[(int64_t)m * E + e];
+            const float dpre = g * w2[(int64_t)m * E + e] * (hdn > 0.f ? 1.f : hdn + 1.f);
+            if (a == 0) {
+                dw2[(int64_t)m * E + e] = g * hdn;
+                db1[(int64_t)m * E + e] = dpre;
+            }
+            dw1[((int64_t)m * A + a) * E + e] = q[(int64_t)m * A + a] * dpre;
+            s = fmaf(w1[((int64_t)m * A + a) * E + e], dpre, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) dq[(int64_t)m * A + a] = s;
+    }
+}
+
+// one warp per sample
+__global__ void tanh_gauss_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ lsr, const float* __restrict__ eps,
+                                      float lo, float hi, float scale, float bias, float* __restrict__ action,
+                                      float* __restrict__ logp, float* __restrict__ mean_action, int M, int A) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (m >= M) return;
+    float lp = 0.f;
+    for (int a = lane; a < A; a += 32) {
+        const int64_t i = (int64_t)m * A + a;
+        const float mu = mean[i];
+        const float ls = fminf(fmaxf(lsr[i], lo), hi);         // networks.py:108
+        const float e = eps ? eps[i] : 0.f;
+        const float x = mu + expf(ls) * e;                     // rsample
+        const float y = tanhf(x);
+        if (action) action[i] = y * scale + bias;
+        if (mean_action) mean_action[i] = tanhf(mu) * scale + bias;
+        // Normal.log_prob(x) - log(scale*(1-y^2)+1e-6)          networks.py:138-141
+        lp += -0.5f * e * e - ls - 0.91893853320467274178f - logf(scale * (1.f - y * y) + 1e-6f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    if (lane == 0 && logp) logp[m] = lp;
+}
+
+__global__ void tanh_gauss_bwd_kernel(const float* __restrict__ mean, const float* __restrict__ lsr, const float* __restrict__ eps,
+                                      float lo, float hi, float scale, const float* __restrict__ d_action,
+                                      const float* __restrict__ d_logp, float* __restrict__ d_mean,
+                                      float* __restrict__ d_lsr, int M, int A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * A) return;
+    const int m = (int)(i / A);
+    const float raw = lsr[i];
+    const float ls = fminf(fmaxf(raw, lo), hi);
+    const float sd = expf(ls), e = eps[i];
+    const float y = tanhf(mean[i] + sd * e);
+    const float omy2 = 1.f - y * y;
+    const float gl = d_logp ? d_logp[m] : 0.f;
+    const float ga = d_action ? d_action[i] : 0.f;
+    // d/dx of -log(scale*(1-y^2)+1e-6) = 2*scale*y*(1-y^2) / (scale*(1-y^2)+1e-6)
+    const float dx = ga * scale * omy2 + gl * (2.f * scale * y * omy2) / (scale * omy2 + 1e-6f);
+    d_mean[i] = dx;
+    const float dls = dx * sd * e - gl;
+    d_lsr[i] = (raw >= lo && raw <= hi) ? dls : 0.f;          // torch.clamp passes gradient inside [lo, hi]
+}
+
+__global__ void abs_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fabsf(x[i]);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    __syncthreads();
+    return t;  // valid in thread 0
+}
+
+// single block: B*T is small (<= a few thousand)
+__global__ void qmix_td_loss_kernel(const float* __restrict__ q_tot, const float* __restrict__ tq, const float* __restrict__ rsum,
+                                    const float* __restrict__ done, const int32_t* __restrict__ seq_len, float gamma,
+                                    float* __restrict__ targets, float* __restrict__ dq, double* __restrict__ stats, int B, int T) {
+    __shared__ double sh[32];
+    __shared__ double s_msum;
+    const int n = B * T;
+    double msum = 0.0, lsum = 0.0, qsum = 0.0, tsum = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = i / T, t = i % T;
+        const float shifted = t + 1 < T ? tq[i + 1] : 0.f;                   // qmix_agent.py:264-265
+        const float y = rsum[i] + gamma * (1.f - done[i]) * shifted;         // :267-268
+        targets[i] = y;
+        const float mask = t < seq_len[b] ? 1.f : 0.f;                       // :271-273
+        const float df = q_tot[i] - y;
+        msum += mask;
+        lsum += (double)(df * df * mask);
+        qsum += q_tot[i];
+        tsum += y;
+    }
+    const double M = block_sum(msum, sh);
+    if (threadIdx.x == 0) s_msum = M;
+    const double L = block_sum(lsum, sh);
+    const double Qs = block_sum(qsum, sh);
+    const double Ts = block_sum(tsum, sh);
+    __syncthreads();
+    const float inv = (float)(1.0 / s_msum);
+    if (threadIdx.x == 0) {
+        stats[0] = L / s_msum;
+        stats[1] = Qs / n;
+        stats[2] = Ts / n;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = i / T, t = i % T;
+        const float mask = t < seq_len[b] ? 1.f : 0.f;
+        dq[i] = 2.f * (q_tot[i] - targets[i]) * mask * inv;
+    }
+}
+
+__global__ void sac_q_target_kernel(const float* __restrict__ r, const float* __restrict__ d, const float* __restrict__ q1n,
+                                    const float* __restrict__ q2n, const float* __restrict__ lp, const float* __restrict__ alpha,
+                                    float gamma, float* __restrict__ y, int M) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) y[i] = r[i] + (1.f - d[i]) * gamma * (fminf(q1n[i], q2n[i]) - alpha[0] * lp[i]);
+}
+
+__global__ void mse_loss_kernel(const float* __restrict__ q, const float* __restrict__ y, float* __restrict__ dq,
+                                double* __restrict__ loss, int M) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const float df = q[i] - y[i];
+        s += (double)(df * df);
+        dq[i] = 2.f * df / (float)M;
+    }
+    const double t = block_sum(s, sh);
+    if (threadIdx.x == 0) *loss = t / M;
+}
+
+__global__ void sac_policy_loss_kernel(const float* __restrict__ lp, const float* __restrict__ q1, const float* __restrict__ q2,
+                                       const float* __restrict__ alpha, float* __restrict__ dlp, float* __restrict__ dq1,
+                                       float* __restrict__ dq2, double* __restrict__ loss, int M) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    const float a = alpha[0], inv = 1.f / (float)M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const bool first = q1[i] <= q2[i];
+        s += (double)(a * lp[i] - (first ? q1[i] : q2[i]));
+        dlp[i] = a * inv;
+        dq1[i] = first ? -inv : 0.f;
+        dq2[i] = first ? 0.f : -inv;
+    }
+    const double t = block_sum(s, sh);
+    if (threadIdx.x == 0) *loss = t / M;
+}
+
+__global__ void sac_alpha_loss_kernel(const float* __restrict__ lp, const float* __restrict__ log_alpha, float target_entropy,
+                                      float* __restrict__ dla, double* __restrict__ loss, int M) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) s += (double)(lp[i] + target_entropy);
+    const double t = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+        dla[0] = (float)(-t / M);
+        *loss = -(double)log_alpha[0] * t / M;
+    }
+}
+
+__global__ void exp_scalar_kernel(const float* x, float* y) { y[0] = expf(x[0]); }
+
+inline int ok() { return cudaGetLastError() == cudaSuccess ? MLB_OK : MLB_ECUDA; }
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+extern "C" {
+
+int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_bs,
+             int64_t b_rs, int64_t b_cs, float* C, int64_t c_bs, int64_t ldc, const float* bias,
+             int64_t bias_bs, int32_t M, int32_t N, int32_t K, int32_t batch, float beta, int32_t act,
+             void* stream) {
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0 || batch < 1) return MLB_EINVAL;
+    if (M == 0 || N == 0) return MLB_OK;
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
+    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, a_bs, a_rs, a_cs, B, b_bs, b_rs, b_cs, C, c_bs, ldc,
+                                                        bias, bias_bs, M, N, K, beta, act);
+    return ok();
+}
+
+int mlb_gru_gates_forward(const float* gi, const float* gh, const float* h, float* h_new, float* gates,
+                          int32_t M, int32_t H, void* stream) {
+    if (!gi || !gh || !h || !h_new) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    gru_gates_fwd_kernel<<<nblk((int64_t)M * H, 256), 256, 0, (cudaStream_t)stream>>>(gi, gh, h, h_new, gates, M, H);
+    return ok();
+}
+
+int mlb_gru_gates_backward(const float* dh_new, const float* gates, const float* h, const float* gh,
+                           float* dgi, float* dgh, float* dh_direct, int32_t M, int32_t H, void* stream) {
+    if (!dh_new || !gates || !h || !gh || !dgi || !dgh || !dh_direct) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    gru_gates_bwd_kernel<<<nblk((int64_t)M * H, 256), 256, 0, (cudaStream_t)stream>>>(dh_new, gates, h, gh, dgi, dgh, dh_direct, M, H);
+    return ok();
+}
+
+int mlb_relu_backward(const float* y, const float* dy, float* dx, int64_t n, void* stream) {
+    if (!y || !dy || !dx) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    relu_bwd_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n);
+    return ok();
+}
+
+int mlb_abs_backward(const float* pre, const float* dy, float* dx, int64_t n, void* stream) {
+    if (!pre || !dy || !dx) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    abs_bwd_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(pre, dy, dx, n);
+    return ok();
+}
+
+int mlb_colsum(const float* dy, float* db, int32_t M, int32_t N, int64_t ld, float beta, void* stream) {
+    if (!dy || !db) return MLB_EINVAL;
+    if (N == 0) return MLB_OK;
+    colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, db, M, N, ld, beta);
+    return ok();
+}
+
+int mlb_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream) {
+    if (!x || !y) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    axpby_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(a, x, b, y, n);
+    return ok();
+}
+
+int mlb_sumsq(const float* x, int64_t n, double* out_accum, void* stream) {
+    if (!x || !out_accum) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    unsigned blocks = nblk(n, 256);
+    blocks = blocks > 1024 ? 1024 : blocks;
+    sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out_accum);
+    return ok();
+}
+
+int mlb_scale(float* x, int64_t n, const double* norm_sq, float max_norm, void* stream) {
+    if (!x || !norm_sq) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    scale_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, norm_sq, max_norm);
+    return ok();
+}
+
+int mlb_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+             float eps, int32_t step, void* stream) {
+    if (!p || !g || !m || !v || step < 1) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps,
+                                                                (float)((double)lr / bc1), (float)sqrt(bc2));
+    return ok();
+}
+
+int mlb_egreedy_select(const float* q, const float* u, const int32_t* rnd, float epsilon, int32_t* action,
+                       float* q_sel, int32_t M, int32_t K, void* stream) {
+    if (!q || !action || (u && !rnd) || K < 1) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    egreedy_kernel<<<nblk(M, 128), 128, 0, (cudaStream_t)stream>>>(q, u, rnd, epsilon, action, q_sel, M, K);
+    return ok();
+}
+
+int mlb_row_max(const float* q, float* out, int32_t* argmax, int32_t M, int32_t K, void* stream) {
+    if (!q || !out || K < 1) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    row_max_kernel<<<nblk(M, 128), 128, 0, (cudaStream_t)stream>>>(q, out, argmax, M, K);
+    return ok();
+}
+
+int mlb_mixer_forward(const float* q, const float* w1, const float* b1, const float* w2, const float* b2,
+                      float* q_tot, float* hidden_out, int32_t M, int32_t A, int32_t E, void* stream) {
+    if (!q || !w1 || !b1 || !w2 || !b2 || !q_tot) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    mixer_fwd_kernel<<<nblk((int64_t)M * 32, 128), 128, 0, (cudaStream_t)stream>>>(q, w1, b1, w2, b2, q_tot, hidden_out, M, A, E);
+    return ok();
+}
+
+int mlb_mixer_backward(const float* dq_tot, const float* q, const float* w1, const float* w2, const float* hidden,
+                       float* dq, float* dw1, float* db1, float* dw2, float* db2, int32_t M, int32_t A,
+                       int32_t E, void* stream) {
+    if (!dq_tot || !q || !w1 || !w2 || !hidden || !dq || !dw1 || !db1 || !dw2 || !db2) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    mixer_bwd_kernel<<<nblk((int64_t)M * 32, 128), 128, 0, (cudaStream_t)stream>>>(dq_tot, q, w1, w2, hidden, dq, dw1, db1, dw2, db2, M, A, E);
+    return ok();
+}
+
+int mlb_tanh_gaussian_forward(const float* mean, const float* log_std_raw, const float* eps, float lo, float hi,
+                              float scale, float bias, float* action, float* logp, float* mean_action,
+                              int32_t M, int32_t A, void* stream) {
+    if (!mean || !log_std_raw) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    tanh_gauss_fwd_kernel<<<nblk((int64_t)M * 32, 128), 128, 0, (cudaStream_t)stream>>>(mean, log_std_raw, eps, lo, hi, scale, bias,
+                                                                                         action, logp, mean_action, M, A);
+    return ok();
+}
+
+int mlb_tanh_gaussian_backward(const float* mean, const float* log_std_raw, const float* eps, float lo, float hi,
+                               float scale, const float* d_action, const float* d_logp, float* d_mean,
+                               float* d_log_std_raw, int32_t M, int32_t A, void* stream) {
+    if (!mean || !log_std_raw || !eps || !d_mean || !d_log_std_raw) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    tanh_gauss_bwd_kernel<<<nblk((int64_t)M * A, 256), 256, 0, (cudaStream_t)stream>>>(mean, log_std_raw, eps, lo, hi, scale,
+                                                                                       d_action, d_logp, d_mean, d_log_std_raw, M, A);
+    return ok();
+}
+
+int mlb_abs_forward(const float* x, float* y, int64_t n, void* stream) {
+    if (!x || !y) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    abs_fwd_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    return ok();
+}
+
+int mlb_qmix_td_loss(const float* q_tot, const float* target_q_tot, const float* reward_sum, const float* done,
+                     const int32_t* seq_len, float gamma, float* targets, float* dq_tot, double* stats,
+                     int32_t B, int32_t T, void* stream) {
+    if (!q_tot || !target_q_tot || !reward_sum || !done || !seq_len || !targets || !dq_tot || !stats) return MLB_EINVAL;
+    qmix_td_loss_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(q_tot, target_q_tot, reward_sum, done, seq_len, gamma, targets, dq_tot, stats, B, T);
+    return ok();
+}
+
+int mlb_sac_q_target(const float* reward, const float* done, const float* q1n, const float* q2n, const float* logp_next,
+                     const float* alpha, float gamma, float* y, int32_t M, void* stream) {
+    if (!reward || !done || !q1n || !q2n || !logp_next || !alpha || !y) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    sac_q_target_kernel<<<nblk(M, 256), 256, 0, (cudaStream_t)stream>>>(reward, done, q1n, q2n, logp_next, alpha, gamma, y, M);
+    return ok();
+}
+
+int mlb_mse_loss(const float* q, const float* y, float* dq, double* loss, int32_t M, void* stream) {
+    if (!q || !y || !dq || !loss || M < 1) return MLB_EINVAL;
+    mse_loss_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(q, y, dq, loss, M);
+    return ok();
+}
+
+int mlb_sac_policy_loss(const float* logp, const float* q1, const float* q2, const float* alpha, float* d_logp,
+                        float* dq1, float* dq2, double* loss, int32_t M, void* stream) {
+    if (!logp || !q1 || !q2 || !alpha || !d_logp || !dq1 || !dq2 || !loss || M < 1) return MLB_EINVAL;
+    sac_policy_loss_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(logp, q1, q2, alpha, d_logp, dq1, dq2, loss, M);
+    return ok();
+}
+
+int mlb_sac_alpha_loss(const float* logp, const float* log_alpha, float target_entropy, float* d_log_alpha,
+                       double* loss, int32_t M, void* stream) {
+    if (!logp || !log_alpha || !d_log_alpha || !loss || M < 1) return MLB_EINVAL;
+    sac_alpha_loss_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(logp, log_alpha, target_entropy, d_log_alpha, loss, M);
+    return ok();
+}
+
+int mlb_exp_scalar(const float* x, float* y, void* stream) {
+    if (!x || !y) return MLB_EINVAL;
+    exp_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(x, y);
+    return ok();
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Layers with explicit forward / backward on the marllb_b200 policy kernels.
+
+Parameters are float32 CUDA tensors in torch's layouts (nn.Linear weight [out, in]; nn.GRU
+weight_ih_l0 [3H, in], gate order r, z, n) and are exposed through `state_dict()` with the
+reference modules' key names, so checkpoints move between the reference and this package.
+Initialisation re-uses torch.nn's initialisers on the host in the reference's construction
+order (same RNG consumption as the reference for the same torch seed); no torch.nn module is
+on the compute path.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+
+
+class Params:
+    """Named float32 CUDA tensors + gradients + Adam moments."""
+
+    def __init__(self, device):
+        self.device = device
+        self.p = OrderedDict()
+        self.g = OrderedDict()
+
+    def add(self, name, tensor):
+        t = tensor.detach().to(device=self.device, dtype=torch.float32).contiguous().clone()
+        self.p[name] = t
+        self.g[name] = torch.zeros_like(t)
+        return t
+
+    def zero_grad(self):
+        for g in self.g.values():
+            g.zero_()
+
+    def state_dict(self, prefix=""):
+        return OrderedDict((prefix + k, v.detach().clone()) for k, v in self.p.items())
+
+    def load_state_dict(self, sd, prefix=""):
+        for k in self.p:
+            src = sd[prefix + k]
+            if tuple(src.shape) != tuple(self.p[k].shape):
+                raise RuntimeError(f"size mismatch for {prefix + k}: {tuple(src.shape)} vs {tuple(self.p[k].shape)}")
+            self.p[k].copy_(src.to(device=self.device, dtype=torch.float32))
+
+    def tensors(self):
+        return list(self.p.values())
+
+    def grads(self):
+        return list(self.g.values())
+
+
+class Adam:
+    """torch.optim.Adam (default betas / eps, no weight decay) over a list of (param, grad)."""
+
+    def __init__(self, params, grads, lr):
+        self.params, self.grads, self.lr = params, grads, lr
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.t = 0
+
+    def step(self):
+        self.t += 1
+        for p, g, m, v in zip(self.params, self.grads, self.m, self.v):
+            ops.adam_step(p, g, m, v, self.lr, self.t)
+
+    def state_dict(self):
+        return {"step": self.t, "exp_avg": [m.clone() for m in self.m], "exp_avg_sq": [v.clone() for v in self.v],
+                "lr": self.lr}
+
+    def load_state_dict(self, sd):
+        self.t = int(sd["step"])
+        for m, s in zip(self.m, sd["exp_avg"]):
+            m.copy_(s)
+        for v, s in zip(self.v, sd["exp_avg_sq"]):
+            v.copy_(s)
+
+
+def linear_backward(P, wname, bname, x, dy, need_dx=True):
+    """Accumulate dW += dy^T x, db += colsum(dy); return dx = dy W (x, dy 2-D)."""
+    ops.matmul_tn(dy, x, out=P.g[wname], beta=1.0)
+    ops.colsum(dy, out=P.g[bname], beta=1.0)
+    return ops.matmul_nn(dy, P.p[wname]) if need_dx else None
+
+
+class GRUCellSeq:
+    """nn.GRU(in, H, batch_first=True) run step by step (agent_network.py:41,76-78; networks.py:60,97)."""
+
+    def __init__(self, P: Params, prefix="gru."):
+        self.P, self.k = P, prefix
+
+    def step(self, x, h, save=False):
+        """x [B,in], h [B,H] -> h' [B,H]; with save=True also returns the tape entry."""
+        P, k = self.P.p, self.k
+        gi = ops.linear(x, P[k + "weight_ih_l0"], P[k + "bias_ih_l0"])
+        gh = ops.linear(h, P[k + "weight_hh_l0"], P[k + "bias_hh_l0"])
+        h_new, gates = ops.gru_gates_forward(gi, gh, h, save_gates=save)
+        return (h_new, (x, h, gh, gates)) if save else h_new
+
+    def forward_seq(self, xs, h0):
+        """xs [T,B,in] (time-major, contiguous), h0 [B,H] -> hs [T,B,H], tape."""
+        P, k = self.P.p, self.k
+        T, B, In = xs.shape
+        H = h0.shape[-1]
+        gi_all = ops.linear(xs.reshape(T * B, In), P[k + "weight_ih_l0"], P[k + "bias_ih_l0"]).reshape(T, B, 3 * H)
+        hs = torch.empty((T, B, H), dtype=torch.float32, device=xs.device)
+        hprev = torch.empty((T, B, H), dtype=torch.float32, device=xs.device)
+        ghs = torch.empty((T, B, 3 * H), dtype=torch.float32, device=xs.device)
+        gates = torch.empty((T, B, 3 * H), dtype=torch.float32, device=xs.device)
+        h = h0
+        for t in range(T):
+            hprev[t].copy_(h)
+            gh = ops.linear(h, P[k + "weight_hh_l0"], P[k + "bias_hh_l0"], out=ghs[t])
+            h_new, g = ops.gru_gates_forward(gi_all[t], gh, hprev[t], save_gates=True)
+            gates[t].copy_(g)
+            hs[t].copy_(h_new)
+            h = hs[t]
+        return hs, (xs, hprev, ghs, gates)
+
+    def backward_seq(self, dhs, tape, need_dx=False):
+        """dhs [T,B,H] gradient w.r.t. every hidden output; accumulates parameter gradients (BPTT)."""
+        P, k = self.P, self.k
+        xs, hprev, ghs, gates = tape
+        T, B, H = dhs.shape
+        dgi_all = torch.empty_like(gates)
+        dgh_all = torch.empty_like(gates)
+        dh_next = torch.zeros((B, H), dtype=torch.float32, device=dhs.device)
+        for t in range(T - 1, -1, -1):
+            dh = dhs[t].clone()
+            ops.axpby(1.0, dh_next, 1.0, dh)
+            dgi, dgh, dh_direct = ops.gru_gates_backward(dh, gates[t], hprev[t], ghs[t])
+            dgi_all[t].copy_(dgi)
+            dgh_all[t].copy_(dgh)
+            dh_next = ops.matmul_nn(dgh, P.p[k + "weight_hh_l0"])
+            ops.axpby(1.0, dh_direct, 1.0, dh_next)
+        In = xs.shape[-1]
+        dgi2, dgh2 = dgi_all.reshape(T * B, 3 * H), dgh_all.reshape(T * B, 3 * H)
+        ops.matmul_tn(dgi2, xs.reshape(T * B, In), out=P.g[k + "weight_ih_l0"], beta=1.0)
+        ops.colsum(dgi2, out=P.g[k + "bias_ih_l0"], beta=1.0)
+        ops.matmul_tn(dgh2, hprev.reshape(T * B, H), out=P.g[k + "weight_hh_l0"], beta=1.0)
+        ops.colsum(dgh2, out=P.g[k + "bias_hh_l0"], beta=1.0)
+        dxs = ops.matmul_nn(dgi2, P.p[k + "weight_ih_l0"]).reshape(T, B, In) if need_dx else None
+        return dxs, dh_next

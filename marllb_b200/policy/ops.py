@@ -1,0 +1,288 @@
+"""Thin torch-tensor wrappers over the policy C ABI (include/marllb_b200_policy.h).
+
+Tensors are float32, CUDA, contiguous; torch only owns the memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import check
+
+ACT_NONE, ACT_RELU, ACT_ABS = 0, 1, 2
+_bound = False
+
+
+def _L():
+    global _bound
+    L = _lib.load()
+    if not _bound:
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        sig = {
+            "mlb_gemm": [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, vp, i64, i32, i32, i32, i32, f32, i32, vp],
+            "mlb_gru_gates_forward": [vp, vp, vp, vp, vp, i32, i32, vp],
+            "mlb_gru_gates_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
+            "mlb_relu_backward": [vp, vp, vp, i64, vp],
+            "mlb_abs_backward": [vp, vp, vp, i64, vp],
+            "mlb_colsum": [vp, vp, i32, i32, i64, f32, vp],
+            "mlb_axpby": [f32, vp, f32, vp, i64, vp],
+            "mlb_sumsq": [vp, i64, vp, vp],
+            "mlb_scale": [vp, i64, vp, f32, vp],
+            "mlb_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp],
+            "mlb_egreedy_select": [vp, vp, vp, f32, vp, vp, i32, i32, vp],
+            "mlb_row_max": [vp, vp, vp, i32, i32, vp],
+            "mlb_mixer_forward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+            "mlb_mixer_backward": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+            "mlb_tanh_gaussian_forward": [vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, i32, i32, vp],
+            "mlb_tanh_gaussian_backward": [vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, i32, i32, vp],
+            "mlb_abs_forward": [vp, vp, i64, vp],
+            "mlb_qmix_td_loss": [vp, vp, vp, vp, vp, f32, vp, vp, vp, i32, i32, vp],
+            "mlb_sac_q_target": [vp, vp, vp, vp, vp, vp, f32, vp, i32, vp],
+            "mlb_mse_loss": [vp, vp, vp, vp, i32, vp],
+            "mlb_sac_policy_loss": [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+            "mlb_sac_alpha_loss": [vp, vp, f32, vp, vp, i32, vp],
+            "mlb_exp_scalar": [vp, vp, vp],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = C.c_int, args
+        _bound = True
+    return L
+
+
+POLICY_EXPORTS = ["mlb_gemm", "mlb_gru_gates_forward", "mlb_gru_gates_backward", "mlb_relu_backward",
+                  "mlb_abs_backward", "mlb_colsum", "mlb_axpby", "mlb_sumsq", "mlb_scale", "mlb_adam",
+                  "mlb_egreedy_select", "mlb_row_max", "mlb_mixer_forward", "mlb_mixer_backward",
+                  "mlb_tanh_gaussian_forward", "mlb_tanh_gaussian_backward", "mlb_abs_forward",
+                  "mlb_qmix_td_loss", "mlb_sac_q_target", "mlb_mse_loss", "mlb_sac_policy_loss",
+                  "mlb_sac_alpha_loss", "mlb_exp_scalar"]
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "float32 contiguous CUDA tensor required"
+    return t
+
+
+def linear(x, W, b=None, act=ACT_NONE, out=None):
+    """y = act(x W^T + b).  x [M,K] or [G,M,K]; W [N,K] or [G,N,K]; b [N] / [G,N] (nn.Linear layout)."""
+    _chk(x), _chk(W)
+    batched = x.dim() == 3
+    G = x.shape[0] if batched else 1
+    M, K = x.shape[-2], x.shape[-1]
+    N = W.shape[-2]
+    assert W.shape[-1] == K
+    if out is None:
+        out = torch.empty((G, M, N) if batched else (M, N), dtype=torch.float32, device=x.device)
+    check(_L().mlb_gemm(_p(x), M * K if batched else 0, K, 1,
+                        _p(W), N * K if (batched and W.dim() == 3) else 0, 1, K,
+                        _p(out), M * N, N, _p(b), N if (b is not None and b.dim() == 2) else 0,
+                        M, N, K, G, 0.0, act, _st()))
+    return out
+
+
+def matmul_nn(dy, W, out=None, beta=0.0):
+    """dx = dy W  (input gradient of nn.Linear).  dy [.,M,N], W [.,N,K] -> [.,M,K]."""
+    _chk(dy), _chk(W)
+    batched = dy.dim() == 3
+    G = dy.shape[0] if batched else 1
+    M, N = dy.shape[-2], dy.shape[-1]
+    K = W.shape[-1]
+    if out is None:
+        out = torch.empty((G, M, K) if batched else (M, K), dtype=torch.float32, device=dy.device)
+    check(_L().mlb_gemm(_p(dy), M * N if batched else 0, N, 1,
+                        _p(W), N * K if (batched and W.dim() == 3) else 0, K, 1,
+                        _p(out), M * K, K, None, 0, M, K, N, G, beta, ACT_NONE, _st()))
+    return out
+
+
+def matmul_tn(dy, x, out=None, beta=0.0):
+    """dW (+)= dy^T x  (weight gradient of nn.Linear).  dy [.,M,N], x [.,M,K] -> [.,N,K]."""
+    _chk(dy), _chk(x)
+    batched = dy.dim() == 3
+    G = dy.shape[0] if batched else 1
+    M, N = dy.shape[-2], dy.shape[-1]
+    K = x.shape[-1]
+    if out is None:
+        out = torch.zeros((G, N, K) if batched else (N, K), dtype=torch.float32, device=dy.device)
+        beta = 0.0
+    check(_L().mlb_gemm(_p(dy), M * N if batched else 0, 1, N,       # A(n, m) = dy[m][n]
+                        _p(x), M * K if batched else 0, K, 1,        # B(m, k) = x[m][k]
+                        _p(out), N * K, K, None, 0, N, K, M, G, beta, ACT_NONE, _st()))
+    return out
+
+
+def colsum(dy, out=None, beta=0.0):
+    """db (+)= sum over rows.  dy [M,N] (2-D only)."""
+    _chk(dy)
+    M, N = dy.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=dy.device)
+        beta = 0.0
+    check(_L().mlb_colsum(_p(dy), _p(out), M, N, N, beta, _st()))
+    return out
+
+
+def gru_gates_forward(gi, gh, h, save_gates=False):
+    M, H = h.shape[-2] * (h.shape[0] if h.dim() == 3 else 1), h.shape[-1]
+    h_new = torch.empty_like(h)
+    gates = torch.empty_like(gi) if save_gates else None
+    check(_L().mlb_gru_gates_forward(_p(_chk(gi)), _p(_chk(gh)), _p(_chk(h)), _p(h_new), _p(gates), M, H, _st()))
+    return h_new, gates
+
+
+def gru_gates_backward(dh_new, gates, h, gh):
+    M, H = h.shape[-2] * (h.shape[0] if h.dim() == 3 else 1), h.shape[-1]
+    dgi, dgh, dh = torch.empty_like(gates), torch.empty_like(gates), torch.empty_like(h)
+    check(_L().mlb_gru_gates_backward(_p(_chk(dh_new)), _p(gates), _p(h), _p(gh), _p(dgi), _p(dgh), _p(dh), M, H, _st()))
+    return dgi, dgh, dh
+
+
+def relu_backward(y, dy):
+    dx = torch.empty_like(dy)
+    check(_L().mlb_relu_backward(_p(_chk(y)), _p(_chk(dy)), _p(dx), y.numel(), _st()))
+    return dx
+
+
+def abs_backward(pre, dy):
+    dx = torch.empty_like(dy)
+    check(_L().mlb_abs_backward(_p(_chk(pre)), _p(_chk(dy)), _p(dx), pre.numel(), _st()))
+    return dx
+
+
+def axpby(a, x, b, y):
+    """y = a*x + b*y in place."""
+    check(_L().mlb_axpby(a, _p(_chk(x)), b, _p(_chk(y)), x.numel(), _st()))
+    return y
+
+
+def clip_grad_norm_(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ over a list of gradient tensors; returns the total norm tensor."""
+    acc = torch.zeros(1, dtype=torch.float64, device=grads[0].device)
+    for g in grads:
+        check(_L().mlb_sumsq(_p(_chk(g)), g.numel(), _p(acc), _st()))
+    for g in grads:
+        check(_L().mlb_scale(_p(g), g.numel(), _p(acc), float(max_norm), _st()))
+    return acc.sqrt()
+
+
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_L().mlb_adam(_p(_chk(p)), _p(_chk(g)), _p(_chk(m)), _p(_chk(v)), p.numel(), lr, beta1, beta2, eps, step, _st()))
+
+
+def egreedy_select(q, epsilon=0.0, u=None, rnd=None):
+    """q [M,K] -> (action int32 [M], q_sel [M]); u/rnd pre-drawn exploration randoms (optional)."""
+    M, K = q.shape
+    act = torch.empty(M, dtype=torch.int32, device=q.device)
+    qsel = torch.empty(M, dtype=torch.float32, device=q.device)
+    check(_L().mlb_egreedy_select(_p(_chk(q)), _p(u), _p(rnd), float(epsilon), _p(act), _p(qsel), M, K, _st()))
+    return act, qsel
+
+
+def row_max(q):
+    M, K = q.shape
+    out = torch.empty(M, dtype=torch.float32, device=q.device)
+    arg = torch.empty(M, dtype=torch.int32, device=q.device)
+    check(_L().mlb_row_max(_p(_chk(q)), _p(out), _p(arg), M, K, _st()))
+    return out, arg
+
+
+def mixer_forward(q, w1, b1, w2, b2, save_hidden=False):
+    M, A = q.shape
+    E = b1.shape[-1]
+    q_tot = torch.empty(M, dtype=torch.float32, device=q.device)
+    hidden = torch.empty((M, E), dtype=torch.float32, device=q.device) if save_hidden else None
+    check(_L().mlb_mixer_forward(_p(_chk(q)), _p(_chk(w1)), _p(_chk(b1)), _p(_chk(w2)), _p(_chk(b2)),
+                                 _p(q_tot), _p(hidden), M, A, E, _st()))
+    return q_tot, hidden
+
+
+def mixer_backward(dq_tot, q, w1, w2, hidden):
+    M, A = q.shape
+    E = hidden.shape[-1]
+    dq = torch.empty_like(q)
+    dw1 = torch.empty((M, A * E), dtype=torch.float32, device=q.device)
+    db1 = torch.empty((M, E), dtype=torch.float32, device=q.device)
+    dw2 = torch.empty((M, E), dtype=torch.float32, device=q.device)
+    db2 = torch.empty((M, 1), dtype=torch.float32, device=q.device)
+    check(_L().mlb_mixer_backward(_p(_chk(dq_tot)), _p(q), _p(w1), _p(w2), _p(hidden), _p(dq), _p(dw1), _p(db1),
+                                  _p(dw2), _p(db2), M, A, E, _st()))
+    return dq, dw1, db1, dw2, db2
+
+
+def tanh_gaussian_forward(mean, log_std_raw, eps, lo=-20.0, hi=2.0, scale=1.0, bias=0.0):
+    M, A = mean.shape
+    action = torch.empty_like(mean)
+    mean_action = torch.empty_like(mean)
+    logp = torch.empty((M, 1), dtype=torch.float32, device=mean.device)
+    check(_L().mlb_tanh_gaussian_forward(_p(_chk(mean)), _p(_chk(log_std_raw)), _p(eps), lo, hi, scale, bias,
+                                         _p(action), _p(logp), _p(mean_action), M, A, _st()))
+    return action, logp, mean_action
+
+
+def tanh_gaussian_backward(mean, log_std_raw, eps, d_action, d_logp, lo=-20.0, hi=2.0, scale=1.0):
+    M, A = mean.shape
+    d_mean, d_ls = torch.empty_like(mean), torch.empty_like(mean)
+    check(_L().mlb_tanh_gaussian_backward(_p(mean), _p(log_std_raw), _p(_chk(eps)), lo, hi, scale, _p(d_action),
+                                          _p(d_logp), _p(d_mean), _p(d_ls), M, A, _st()))
+    return d_mean, d_ls
+
+
+def abs_forward(x):
+    y = torch.empty_like(x)
+    check(_L().mlb_abs_forward(_p(_chk(x)), _p(y), x.numel(), _st()))
+    return y
+
+
+def qmix_td_loss(q_tot, target_q_tot, reward_sum, done, seq_len, gamma):
+    """[B,T] float32 tensors, seq_len int32 [B] -> (targets, dq_tot, stats float64[3] = loss, mean q_tot, mean targets)."""
+    B, T = q_tot.shape
+    targets, dq = torch.empty_like(q_tot), torch.empty_like(q_tot)
+    stats = torch.zeros(3, dtype=torch.float64, device=q_tot.device)
+    check(_L().mlb_qmix_td_loss(_p(_chk(q_tot)), _p(_chk(target_q_tot)), _p(_chk(reward_sum)), _p(_chk(done)),
+                                _p(seq_len), float(gamma), _p(targets), _p(dq), _p(stats), B, T, _st()))
+    return targets, dq, stats
+
+
+def sac_q_target(reward, done, q1n, q2n, logp_next, alpha, gamma):
+    y = torch.empty_like(reward)
+    check(_L().mlb_sac_q_target(_p(_chk(reward)), _p(_chk(done)), _p(_chk(q1n)), _p(_chk(q2n)), _p(_chk(logp_next)),
+                                _p(alpha), float(gamma), _p(y), reward.numel(), _st()))
+    return y
+
+
+def mse_loss(q, y):
+    dq = torch.empty_like(q)
+    loss = torch.zeros(1, dtype=torch.float64, device=q.device)
+    check(_L().mlb_mse_loss(_p(_chk(q)), _p(_chk(y)), _p(dq), _p(loss), q.numel(), _st()))
+    return loss, dq
+
+
+def sac_policy_loss(logp, q1, q2, alpha):
+    dlp, dq1, dq2 = torch.empty_like(logp), torch.empty_like(q1), torch.empty_like(q2)
+    loss = torch.zeros(1, dtype=torch.float64, device=q1.device)
+    check(_L().mlb_sac_policy_loss(_p(_chk(logp)), _p(_chk(q1)), _p(_chk(q2)), _p(alpha), _p(dlp), _p(dq1), _p(dq2),
+                                   _p(loss), logp.numel(), _st()))
+    return loss, dlp, dq1, dq2
+
+
+def sac_alpha_loss(logp, log_alpha, target_entropy):
+    d = torch.empty(1, dtype=torch.float32, device=logp.device)
+    loss = torch.zeros(1, dtype=torch.float64, device=logp.device)
+    check(_L().mlb_sac_alpha_loss(_p(_chk(logp)), _p(log_alpha), float(target_entropy), _p(d), _p(loss), logp.numel(), _st()))
+    return loss, d
+
+
+def exp_scalar(x):
+    y = torch.empty_like(x)
+    check(_L().mlb_exp_scalar(_p(x), _p(y), _st()))
+    return y

@@ -1,0 +1,381 @@
+"""SAC-GRU on the marllb_b200 policy kernels -- API mirror of simulation-mode/problem-04-sac-gru/src.
+
+  PolicyNetwork   networks.py:19-155    GRU -> fc1(ReLU) -> mean / log_std, tanh-Gaussian sample
+  QNetwork        networks.py:158-245   GRU over [state, action] -> fc1 -> fc2 -> fc3
+  ReplayBuffer    replay_buffer.py:13-102
+  SAC_GRU_Agent   sac_agent.py:19-318   select_action / update_parameters / save / load
+
+Reference behaviours kept on purpose: the stored *policy* hidden state is
+reused as the critics' hidden state and for next_states; the tanh correction is
+log(action_scale*(1-y^2)+1e-6).  Gaussian noise comes from torch's generator unless `eps` is
+passed (parity tests pass the reference's draws).
+"""
+from __future__ import annotations
+
+import random
+from collections import deque
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import ops
+from .nn import Adam, GRUCellSeq, Params, linear_backward
+from .qmix import _device
+
+
+def _init_like_reference(gru, linears):
+    for name, p in gru.named_parameters():                     # networks.py:69-80
+        if 'weight' in name:
+            torch.nn.init.orthogonal_(p)
+        else:
+            torch.nn.init.constant_(p, 0.0)
+    for fc in linears:
+        torch.nn.init.xavier_uniform_(fc.weight)
+        torch.nn.init.constant_(fc.bias, 0.0)
+
+
+class PolicyNetwork:
+    """networks.py:19-155."""
+
+    def __init__(self, state_dim, action_dim, hidden_dim=256, gru_dim=128, action_scale=1.0, action_bias=0.0,
+                 log_std_min=-20, log_std_max=2, device=None):
+        self.state_dim, self.action_dim, self.hidden_dim, self.gru_dim = state_dim, action_dim, hidden_dim, gru_dim
+        self.action_scale, self.action_bias = float(action_scale), float(action_bias)
+        self.log_std_min, self.log_std_max = float(log_std_min), float(log_std_max)
+        self.device = _device(device)
+        gru = torch.nn.GRU(state_dim, gru_dim, batch_first=True)
+        fc1 = torch.nn.Linear(gru_dim, hidden_dim)
+        fc_mean = torch.nn.Linear(hidden_dim, action_dim)
+        fc_logstd = torch.nn.Linear(hidden_dim, action_dim)
+        _init_like_reference(gru, [fc1, fc_mean, fc_logstd])
+        self.P = Params(self.device)
+        for name, p in gru.named_parameters():
+            self.P.add("gru." + name, p)
+        for n, fc in (("fc1", fc1), ("fc_mean", fc_mean), ("fc_logstd", fc_logstd)):
+            self.P.add(n + ".weight", fc.weight)
+            self.P.add(n + ".bias", fc.bias)
+        self.gru = GRUCellSeq(self.P)
+
+    def _heads(self, state, hidden, save):
+        P = self.P.p
+        x = state.to(self.device, torch.float32).reshape(-1, self.state_dim).contiguous()
+        h0 = hidden.to(self.device, torch.float32).reshape(-1, self.gru_dim).contiguous()
+        hs, tape = self.gru.forward_seq(x.unsqueeze(0), h0)
+        h1 = hs[0]
+        a1 = ops.linear(h1, P["fc1.weight"], P["fc1.bias"], ops.ACT_RELU)
+        mean = ops.linear(a1, P["fc_mean.weight"], P["fc_mean.bias"])
+        lsr = ops.linear(a1, P["fc_logstd.weight"], P["fc_logstd.bias"])
+        if save:
+            self._tape = (tape, h1, a1, mean, lsr)
+        return mean, lsr, h1
+
+    def forward(self, state, hidden):
+        """-> (mean, log_std clamped to [log_std_min, log_std_max], hidden_new [1,B,gru]); networks.py:82-110."""
+        mean, lsr, h1 = self._heads(state, hidden, save=False)
+        return mean, lsr.clamp(self.log_std_min, self.log_std_max), h1.unsqueeze(0)
+
+    def sample(self, state, hidden, eps=None, save=False):
+        """networks.py:112-147 -> (action, log_prob [B,1], mean_action, hidden_new)."""
+        mean, lsr, h1 = self._heads(state, hidden, save)
+        if eps is None:
+            eps = torch.randn(mean.shape, device=self.device, dtype=torch.float32)
+        eps = eps.to(self.device, torch.float32).contiguous()
+        action, logp, mean_action = ops.tanh_gaussian_forward(mean, lsr, eps, self.log_std_min, self.log_std_max,
+                                                              self.action_scale, self.action_bias)
+        if save:
+            self._eps = eps
+        return action, logp, mean_action, h1.unsqueeze(0)
+
+    def backward(self, d_action, d_logp):
+        """Gradients of a scalar loss w.r.t. the sampled action [B,A] and log_prob [B,1]."""
+        tape, h1, a1, mean, lsr = self._tape
+        d_mean, d_lsr = ops.tanh_gaussian_backward(mean, lsr, self._eps, d_action, d_logp, self.log_std_min,
+                                                   self.log_std_max, self.action_scale)
+        da1 = linear_backward(self.P, "fc_mean.weight", "fc_mean.bias", a1, d_mean)
+        ops.axpby(1.0, linear_backward(self.P, "fc_logstd.weight", "fc_logstd.bias", a1, d_lsr), 1.0, da1)
+        dh1 = linear_backward(self.P, "fc1.weight", "fc1.bias", h1, ops.relu_backward(a1, da1))
+        self.gru.backward_seq(dh1.unsqueeze(0).contiguous(), tape)
+        self._tape = None
+
+    def init_hidden(self, batch_size=1):
+        return torch.zeros(1, batch_size, self.gru_dim, device=self.device)
+
+    def to(self, device):
+        return self
+
+    def state_dict(self):
+        return self.P.state_dict()
+
+    def load_state_dict(self, sd):
+        self.P.load_state_dict(sd)
+
+    def parameters(self):
+        return self.P.tensors()
+
+
+class QNetwork:
+    """networks.py:158-245."""
+
+    def __init__(self, state_dim, action_dim, hidden_dim=256, gru_dim=128, device=None):
+        self.state_dim, self.action_dim, self.hidden_dim, self.gru_dim = state_dim, action_dim, hidden_dim, gru_dim
+        self.device = _device(device)
+        gru = torch.nn.GRU(state_dim + action_dim, gru_dim, batch_first=True)
+        fc1 = torch.nn.Linear(gru_dim, hidden_dim)
+        fc2 = torch.nn.Linear(hidden_dim, hidden_dim)
+        fc3 = torch.nn.Linear(hidden_dim, 1)
+        _init_like_reference(gru, [fc1, fc2, fc3])
+        self.P = Params(self.device)
+        for name, p in gru.named_parameters():
+            self.P.add("gru." + name, p)
+        for n, fc in (("fc1", fc1), ("fc2", fc2), ("fc3", fc3)):
+            self.P.add(n + ".weight", fc.weight)
+            self.P.add(n + ".bias", fc.bias)
+        self.gru = GRUCellSeq(self.P)
+
+    def forward(self, state, action, hidden, save=False):
+        """-> (q [B,1], hidden_new [1,B,gru]); networks.py:209-237."""
+        P = self.P.p
+        s = state.to(self.device, torch.float32).reshape(-1, self.state_dim)
+        a = action.to(self.device, torch.float32).reshape(-1, self.action_dim)
+        sa = torch.cat([s, a], dim=1).contiguous()
+        h0 = hidden.to(self.device, torch.float32).reshape(-1, self.gru_dim).contiguous()
+        hs, tape = self.gru.forward_seq(sa.unsqueeze(0), h0)
+        h1 = hs[0]
+        a1 = ops.linear(h1, P["fc1.weight"], P["fc1.bias"], ops.ACT_RELU)
+        a2 = ops.linear(a1, P["fc2.weight"], P["fc2.bias"], ops.ACT_RELU)
+        q = ops.linear(a2, P["fc3.weight"], P["fc3.bias"])
+        if save:
+            self._tape = (tape, h1, a1, a2)
+        return q, h1.unsqueeze(0)
+
+    __call__ = forward
+
+    def backward(self, dq, need_daction=False):
+        tape, h1, a1, a2 = self._tape
+        dq = dq.reshape(-1, 1).contiguous()
+        da2 = ops.relu_backward(a2, linear_backward(self.P, "fc3.weight", "fc3.bias", a2, dq))
+        da1 = ops.relu_backward(a1, linear_backward(self.P, "fc2.weight", "fc2.bias", a1, da2))
+        dh1 = linear_backward(self.P, "fc1.weight", "fc1.bias", h1, da1)
+        dxs, _ = self.gru.backward_seq(dh1.unsqueeze(0).contiguous(), tape, need_dx=need_daction)
+        self._tape = None
+        return dxs[0][:, self.state_dim:].contiguous() if need_daction else None
+
+    def init_hidden(self, batch_size=1):
+        return torch.zeros(1, batch_size, self.gru_dim, device=self.device)
+
+    def to(self, device):
+        return self
+
+    def state_dict(self):
+        return self.P.state_dict()
+
+    def load_state_dict(self, sd):
+        self.P.load_state_dict(sd)
+
+    def parameters(self):
+        return self.P.tensors()
+
+
+def soft_update(source, target, tau):
+    """networks.py:248-260: target = tau*source + (1-tau)*target."""
+    for ps, pt in zip(source.P.tensors(), target.P.tensors()):
+        ops.axpby(tau, ps, 1.0 - tau, pt)
+
+
+def hard_update(source, target):
+    target.load_state_dict(source.state_dict())
+
+
+class ReplayBuffer:
+    """replay_buffer.py:13-102 (host-side storage, same sampling call on Python's `random`)."""
+
+    def __init__(self, capacity=1_000_000, seed=None):
+        self.capacity = capacity
+        self.buffer = deque(maxlen=capacity)
+        if seed is not None:
+            random.seed(seed)
+            np.random.seed(seed)
+
+    def push(self, state, action, reward, next_state, done, hidden=None):
+        conv = lambda x: x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
+        self.buffer.append((conv(state), conv(action), reward, conv(next_state), done,
+                            conv(hidden) if hidden is not None else None))
+
+    def sample(self, batch_size, device='cpu'):
+        batch = random.sample(self.buffer, batch_size)                                # replay_buffer.py:70
+        states, actions, rewards, next_states, dones, hiddens = zip(*batch)
+        f = lambda x: torch.as_tensor(np.array(x), dtype=torch.float32).to(device)
+        out = [f(states), f(actions), f(rewards).unsqueeze(1), f(next_states), f(dones).unsqueeze(1)]
+        if hiddens[0] is not None:
+            h = np.array(hiddens)
+            if h.ndim == 4:
+                h = np.expand_dims(h.squeeze(axis=2).squeeze(axis=1), axis=0)
+            elif h.ndim == 2:
+                h = np.expand_dims(h, axis=0)
+            out.append(torch.as_tensor(h, dtype=torch.float32).to(device))
+        else:
+            out.append(None)
+        return tuple(out)
+
+    def __len__(self):
+        return len(self.buffer)
+
+    def is_ready(self, batch_size):
+        return len(self.buffer) >= batch_size
+
+
+class SAC_GRU_Agent:
+    """sac_agent.py:19-318."""
+
+    def __init__(self, state_dim, action_dim, hidden_dim=256, gru_dim=128, lr_policy=3e-4, lr_q=3e-4,
+                 lr_alpha=3e-4, gamma=0.99, tau=0.005, alpha=0.2, auto_entropy_tuning=True, target_entropy=None,
+                 buffer_size=1_000_000, batch_size=256, device=None):
+        self.state_dim, self.action_dim = state_dim, action_dim
+        self.gamma, self.tau, self.batch_size = gamma, tau, batch_size
+        self.auto_entropy_tuning = auto_entropy_tuning
+        self.device = _device(device)
+        self.policy = PolicyNetwork(state_dim, action_dim, hidden_dim, gru_dim, device=self.device)
+        self.q1 = QNetwork(state_dim, action_dim, hidden_dim, gru_dim, self.device)
+        self.q2 = QNetwork(state_dim, action_dim, hidden_dim, gru_dim, self.device)
+        self.q1_target = QNetwork(state_dim, action_dim, hidden_dim, gru_dim, self.device)
+        self.q2_target = QNetwork(state_dim, action_dim, hidden_dim, gru_dim, self.device)
+        hard_update(self.q1, self.q1_target)
+        hard_update(self.q2, self.q2_target)
+        self.policy_optimizer = Adam(self.policy.P.tensors(), self.policy.P.grads(), lr_policy)
+        self.q1_optimizer = Adam(self.q1.P.tensors(), self.q1.P.grads(), lr_q)
+        self.q2_optimizer = Adam(self.q2.P.tensors(), self.q2.P.grads(), lr_q)
+        if auto_entropy_tuning:
+            self.target_entropy = -action_dim if target_entropy is None else target_entropy   # sac_agent.py:99-102
+            self.log_alpha = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._log_alpha_grad = torch.zeros_like(self.log_alpha)
+            self.alpha = ops.exp_scalar(self.log_alpha)
+            self.alpha_optimizer = Adam([self.log_alpha], [self._log_alpha_grad], lr_alpha)
+        else:
+            self.alpha = torch.tensor([alpha], dtype=torch.float32, device=self.device)
+            self.target_entropy = None
+        self.replay_buffer = ReplayBuffer(capacity=buffer_size)
+        self.total_steps = 0
+        self.training_stats = {'q1_loss': [], 'q2_loss': [], 'policy_loss': [], 'alpha_loss': [], 'alpha': []}
+
+    def select_action(self, state, hidden, evaluate=False, eps=None):
+        """sac_agent.py:124-149 -> (action numpy [action_dim], hidden_new [1,1,gru])."""
+        if isinstance(state, np.ndarray):
+            state = torch.as_tensor(state, dtype=torch.float32).unsqueeze(0)
+        if hidden is None:
+            hidden = self.policy.init_hidden(1)
+        action, _, mean_action, hidden_new = self.policy.sample(state, hidden, eps=eps)
+        out = mean_action if evaluate else action
+        return out.cpu().numpy()[0], hidden_new
+
+    def select_action_batch(self, states, hiddens=None, evaluate=False, eps=None):
+        """Batched rollout form: states [E, state_dim] CUDA -> (actions [E, action_dim], hiddens [1,E,gru])."""
+        if hiddens is None:
+            hiddens = self.policy.init_hidden(states.shape[0])
+        action, _, mean_action, hidden_new = self.policy.sample(states, hiddens, eps=eps)
+        return (mean_action if evaluate else action), hidden_new
+
+    def update_parameters(self, updates=1, batch=None, eps_next=None, eps_new=None):
+        """sac_agent.py:151-255.  `batch`, `eps_next`, `eps_new` may be supplied for parity tests."""
+        if batch is None and not self.replay_buffer.is_ready(self.batch_size):
+            return None
+        losses = {'q1': 0, 'q2': 0, 'policy': 0, 'alpha': 0}
+        for _ in range(updates):
+            b = batch if batch is not None else self.replay_buffer.sample(self.batch_size, self.device)
+            states, actions, rewards, next_states, dones, hiddens = [None if x is None else x.to(self.device) for x in b]
+            B = states.shape[0]
+            if hiddens is None:
+                policy_hidden = self.policy.init_hidden(B)
+                q_hidden = self.q1.init_hidden(B)
+            else:
+                policy_hidden = q_hidden = hiddens                                    # sac_agent.py:171-172
+            # ---- critic targets (no gradient), :175-190
+            next_actions, next_logp, _, _ = self.policy.sample(next_states, policy_hidden, eps=eps_next)
+            q1n, _ = self.q1_target.forward(next_states, next_actions, q_hidden)
+            q2n, _ = self.q2_target.forward(next_states, next_actions, q_hidden)
+            y = ops.sac_q_target(rewards.reshape(-1).contiguous(), dones.reshape(-1).contiguous(),
+                                 q1n.reshape(-1), q2n.reshape(-1), next_logp.reshape(-1), self.alpha, self.gamma)
+            # ---- critics, :193-207
+            q_losses = []
+            for qnet, opt in ((self.q1, self.q1_optimizer), (self.q2, self.q2_optimizer)):
+                q_cur, _ = qnet.forward(states, actions, q_hidden, save=True)
+                loss, dq = ops.mse_loss(q_cur.reshape(-1), y)
+                qnet.P.zero_grad()
+                qnet.backward(dq)
+                opt.step()
+                q_losses.append(loss)
+            # ---- actor, :210-220
+            new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)
+            q1_new, _ = self.q1.forward(states, new_actions, q_hidden, save=True)
+            q2_new, _ = self.q2.forward(states, new_actions, q_hidden, save=True)
+            p_loss, d_logp, dq1, dq2 = ops.sac_policy_loss(logp.reshape(-1), q1_new.reshape(-1), q2_new.reshape(-1), self.alpha)
+            d_action = self.q1.backward(dq1, need_daction=True)
+            ops.axpby(1.0, self.q2.backward(dq2, need_daction=True), 1.0, d_action)
+            self.policy.P.zero_grad()
+            self.policy.backward(d_action, d_logp)
+            self.policy_optimizer.step()
+            # ---- temperature, :223-231
+            a_loss = None
+            if self.auto_entropy_tuning:
+                a_loss, d_la = ops.sac_alpha_loss(logp.reshape(-1), self.log_alpha, float(self.target_entropy))
+                self._log_alpha_grad.copy_(d_la)
+                self.alpha_optimizer.step()
+                self.alpha = ops.exp_scalar(self.log_alpha)
+            # ---- targets, :234-235
+            soft_update(self.q1, self.q1_target, self.tau)
+            soft_update(self.q2, self.q2_target, self.tau)
+            losses['q1'] += float(q_losses[0].item())
+            losses['q2'] += float(q_losses[1].item())
+            losses['policy'] += float(p_loss.item())
+            if a_loss is not None:
+                losses['alpha'] += float(a_loss.item())
+            self.total_steps += 1
+        for k in losses:
+            losses[k] /= updates
+        self.training_stats['q1_loss'].append(losses['q1'])
+        self.training_stats['q2_loss'].append(losses['q2'])
+        self.training_stats['policy_loss'].append(losses['policy'])
+        self.training_stats['alpha_loss'].append(losses['alpha'])
+        self.training_stats['alpha'].append(float(self.alpha.item()))
+        return losses
+
+    def save(self, filepath):
+        """sac_agent.py:257-287 (same checkpoint keys)."""
+        filepath = Path(filepath)
+        filepath.parent.mkdir(parents=True, exist_ok=True)
+        ck = {'policy_state_dict': self.policy.state_dict(), 'q1_state_dict': self.q1.state_dict(),
+              'q2_state_dict': self.q2.state_dict(), 'q1_target_state_dict': self.q1_target.state_dict(),
+              'q2_target_state_dict': self.q2_target.state_dict(),
+              'policy_optimizer_state_dict': self.policy_optimizer.state_dict(),
+              'q1_optimizer_state_dict': self.q1_optimizer.state_dict(),
+              'q2_optimizer_state_dict': self.q2_optimizer.state_dict(), 'total_steps': self.total_steps,
+              'config': {'state_dim': self.state_dim, 'action_dim': self.action_dim, 'gamma': self.gamma,
+                         'tau': self.tau, 'auto_entropy_tuning': self.auto_entropy_tuning,
+                         'target_entropy': self.target_entropy}}
+        if self.auto_entropy_tuning:
+            ck['log_alpha'] = self.log_alpha
+            ck['alpha_optimizer_state_dict'] = self.alpha_optimizer.state_dict()
+        torch.save(ck, filepath)
+        print(f"Agent saved to {filepath}")
+
+    def load(self, filepath):
+        ck = torch.load(filepath, map_location=self.device)
+        self.policy.load_state_dict(ck['policy_state_dict'])
+        self.q1.load_state_dict(ck['q1_state_dict'])
+        self.q2.load_state_dict(ck['q2_state_dict'])
+        self.q1_target.load_state_dict(ck['q1_target_state_dict'])
+        self.q2_target.load_state_dict(ck['q2_target_state_dict'])
+        for name, opt in (('policy_optimizer_state_dict', self.policy_optimizer),
+                          ('q1_optimizer_state_dict', self.q1_optimizer), ('q2_optimizer_state_dict', self.q2_optimizer)):
+            if isinstance(ck.get(name), dict) and 'exp_avg' in ck[name]:
+                opt.load_state_dict(ck[name])
+        if self.auto_entropy_tuning and 'log_alpha' in ck:
+            self.log_alpha.copy_(ck['log_alpha'].detach().to(self.device))
+            self.alpha = ops.exp_scalar(self.log_alpha)
+            if isinstance(ck.get('alpha_optimizer_state_dict'), dict) and 'exp_avg' in ck['alpha_optimizer_state_dict']:
+                self.alpha_optimizer.load_state_dict(ck['alpha_optimizer_state_dict'])
+        self.total_steps = ck['total_steps']
+        print(f"Agent loaded from {filepath}")
+
+    def get_stats(self):
+        return {'total_updates': self.total_steps, 'alpha': float(self.alpha.item()), 'training_stats': self.training_stats}

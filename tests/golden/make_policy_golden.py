@@ -1,0 +1,139 @@
+"""Generate tests/golden/policy_*.npz by running the UNMODIFIED reference agents (torch CPU).
+
+Run in the build container only:  python tests/golden/make_policy_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_import  # noqa: E402
+
+
+def sd_np(prefix, sd):
+    return {f"{prefix}{k}": v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"wrote {name}.npz ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def qmix():
+    an = ref_import.load("agent_network", "problem-05-qmix")
+    mn = ref_import.load("mixing_network", "problem-05-qmix")
+    qa = ref_import.load("qmix_agent", "problem-05-qmix")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    out = {}
+    # --- AgentQNetwork.forward, two chained steps
+    net = an.AgentQNetwork(obs_dim=20, action_dim=6, hidden_dim=128, gru_dim=64)
+    obs = torch.randn(5, 20)
+    q1, h1 = net(obs, net.init_hidden(5))
+    q2, h2 = net(obs * 0.5, h1)
+    out.update(sd_np("net.", net.state_dict()))
+    out.update(net_obs=obs.numpy(), net_q1=q1.detach().numpy(), net_h1=h1.detach().numpy(),
+               net_q2=q2.detach().numpy(), net_h2=h2.detach().numpy())
+    # --- QMixingNetwork.forward
+    mix = mn.QMixingNetwork(num_agents=3, state_dim=9, mixing_embed_dim=32, hypernet_embed_dim=64)
+    aq, st = torch.randn(7, 3), torch.randn(7, 9)
+    out.update(sd_np("mix.", mix.state_dict()))
+    out.update(mix_q=aq.numpy(), mix_state=st.numpy(), mix_out=mix(aq, st).detach().numpy())
+    # --- select_actions (greedy + epsilon-greedy with numpy's global RNG)
+    agent = qa.QMIXAgent(num_agents=3, state_dim=9, obs_dim=12, action_dim=5, hidden_dim=32, gru_dim=16,
+                         mixing_embed_dim=8, hypernet_embed_dim=16, batch_size=4, max_seq_len=6, device="cpu",
+                         target_update_interval=2)
+    for i, n in enumerate(agent.agent_networks):
+        out.update(sd_np(f"ag{i}.", n.state_dict()))
+    out.update(sd_np("agmix.", agent.mixer.state_dict()))
+    obs_list = [np.random.randn(12).astype(np.float32) for _ in range(3)]
+    np.random.seed(123)
+    acts, hids, qv = agent.select_actions(obs_list, None, evaluate=False, epsilon=0.5)
+    acts_g, _, qv_g = agent.select_actions(obs_list, hids, evaluate=True)
+    out.update(sel_obs=np.stack(obs_list), sel_acts=np.array(acts), sel_q=np.array(qv, np.float64),
+               sel_acts_greedy=np.array(acts_g), sel_q_greedy=np.array(qv_g, np.float64),
+               sel_h=np.stack([h.detach().numpy() for h in hids]))
+    # --- update(): fixed batch, ragged lengths; two updates (second one triggers the hard target sync)
+    rng = np.random.RandomState(5)
+    B, T, A, K = 4, 6, 3, 5
+    batch = {'observations': rng.randn(B, T, A, 12), 'actions': rng.randint(0, K, (B, T, A, 1)).astype(np.float64),
+             'rewards': rng.rand(B, T, A), 'states': rng.randn(B, T, 9),
+             'dones': np.zeros((B, T)), 'seq_lengths': np.array([6, 4, 6, 3], np.int32)}
+    for b, L in enumerate(batch['seq_lengths']):
+        batch['observations'][b, L:] = 0; batch['actions'][b, L:] = 0; batch['rewards'][b, L:] = 0
+        batch['states'][b, L:] = 0
+        batch['dones'][b, L - 1] = 1.0
+    agent.episode_buffer.is_ready = lambda n: True
+    agent.episode_buffer.sample_batch = lambda n, m: batch
+    for k, v in batch.items():
+        out["batch_" + k] = v
+    for u in (1, 2):
+        stats = agent.update()
+        out[f"upd{u}_stats"] = np.array([stats['loss'], stats['q_tot'], stats['target_q_tot']])
+        for i, n in enumerate(agent.agent_networks):
+            out.update(sd_np(f"upd{u}.ag{i}.", n.state_dict()))
+        out.update(sd_np(f"upd{u}.agmix.", agent.mixer.state_dict()))
+        out.update(sd_np(f"upd{u}.tgt0.", agent.agent_networks_target[0].state_dict()))
+    save("policy_qmix", **out)
+
+
+def sac():
+    nw = ref_import.load("networks", "problem-04-sac-gru")
+    sa = ref_import.load("sac_agent", "problem-04-sac-gru")
+    torch.manual_seed(1)
+    np.random.seed(1)
+    out = {}
+    S, A, B = 22, 4, 8
+    agent = sa.SAC_GRU_Agent(state_dim=S, action_dim=A, hidden_dim=64, gru_dim=32, batch_size=B, device="cpu")
+    out.update(sd_np("policy.", agent.policy.state_dict()))
+    out.update(sd_np("q1.", agent.q1.state_dict()))
+    out.update(sd_np("q2.", agent.q2.state_dict()))
+    # --- PolicyNetwork.sample / QNetwork.forward with known noise
+    states = torch.randn(B, S)
+    hidden = torch.randn(1, B, 32) * 0.3
+    torch.manual_seed(77)
+    eps = torch.randn(B, A)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        action, logp, mean_a, hn = agent.policy.sample(states, hidden)
+        mean, log_std, _ = agent.policy.forward(states, hidden)
+        assert torch.allclose(action, torch.tanh(mean + log_std.exp() * eps), atol=1e-6), "noise replay mismatch"
+        q, qh = agent.q1.forward(states, action, hidden)
+    out.update(fw_states=states.numpy(), fw_hidden=hidden.numpy(), fw_eps=eps.numpy(), fw_action=action.numpy(),
+               fw_logp=logp.numpy(), fw_mean_action=mean_a.numpy(), fw_hn=hn.numpy(), fw_mean=mean.numpy(),
+               fw_log_std=log_std.numpy(), fw_q=q.numpy(), fw_qh=qh.numpy())
+    # --- update_parameters on a fixed batch, two updates
+    rng = np.random.RandomState(9)
+    fixed = (torch.as_tensor(rng.randn(B, S), dtype=torch.float32),
+             torch.as_tensor(np.tanh(rng.randn(B, A)), dtype=torch.float32),
+             torch.as_tensor(rng.rand(B, 1), dtype=torch.float32),
+             torch.as_tensor(rng.randn(B, S), dtype=torch.float32),
+             torch.as_tensor((rng.rand(B, 1) < 0.2).astype(np.float32)),
+             torch.as_tensor(rng.randn(1, B, 32) * 0.2, dtype=torch.float32))
+    for n, t in zip(("states", "actions", "rewards", "next_states", "dones", "hiddens"), fixed):
+        out["batch_" + n] = t.numpy()
+    agent.replay_buffer.is_ready = lambda n: True
+    agent.replay_buffer.sample = lambda n, d: fixed
+    for u in (1, 2):
+        torch.manual_seed(100 + u)
+        e_next, e_new = torch.randn(B, A), torch.randn(B, A)      # rsample order: next_states first, then states
+        torch.manual_seed(100 + u)
+        losses = agent.update_parameters(1)
+        out[f"upd{u}_eps_next"], out[f"upd{u}_eps_new"] = e_next.numpy(), e_new.numpy()
+        out[f"upd{u}_losses"] = np.array([losses['q1'], losses['q2'], losses['policy'], losses['alpha']])
+        out[f"upd{u}_alpha"] = np.array([agent.alpha.item()])
+        out.update(sd_np(f"upd{u}.policy.", agent.policy.state_dict()))
+        out.update(sd_np(f"upd{u}.q1.", agent.q1.state_dict()))
+        out.update(sd_np(f"upd{u}.q2.", agent.q2.state_dict()))
+        out.update(sd_np(f"upd{u}.q1t.", agent.q1_target.state_dict()))
+    save("policy_sac", **out)
+
+
+if __name__ == "__main__":
+    qmix()
+    sac()

@@ -11,8 +11,8 @@ from conftest import ROOT
 from marllb_b200 import _build, _lib
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "marllb_b200.h")).read()
+def header_functions(name="marllb_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(mlb_[a-z0-9_]+)\s*\(", src)))
 
@@ -27,6 +27,17 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in include/marllb_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == [n for n in names if n in _lib.EXPORTS]
     assert set(names) == set(_lib.EXPORTS), set(names) ^ set(_lib.EXPORTS)
+
+
+def test_policy_header_symbols_are_exported_and_bound():
+    from marllb_b200.policy import ops
+    L = C.CDLL(_build.build())
+    names = header_functions("marllb_b200_policy.h")
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/marllb_b200_policy.h but not exported"
+    assert set(names) == set(ops.POLICY_EXPORTS), set(names) ^ set(ops.POLICY_EXPORTS)
+    ops._L()    # binds argtypes for every entry point
 
 
 def test_library_contains_sm100a_code_only():
