@@ -17,6 +17,10 @@ __device__ __forceinline__ uint32_t f32_orderable(float f) {
     return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
 }
 
+__device__ __forceinline__ float f32_from_orderable(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MLB_FULL, v, o);

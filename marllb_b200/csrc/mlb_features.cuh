@@ -157,10 +157,9 @@ __device__ __forceinline__ void store_ranks(uint8_t* __restrict__ base, int lane
     }
 }
 
-// per-warp shared-memory scratch: sv[128] (values by rank), sw[128] (weights by rank)
+// per-warp shared-memory scratch: 128 (value, weight) pairs in rank order
 struct WarpScratch {
-    float* sv;
-    float* sw;
+    float2* vw;
 };
 #define MLB_SCRATCH_BYTES 1024
 
@@ -175,7 +174,7 @@ struct SlotVals {
 };
 
 template <int EPL>
-__device__ __noinline__ uint32_t ranks_full_sort_packed(SlotVals<EPL> v, int n, float* sw) {
+__device__ __noinline__ uint32_t ranks_full_sort_packed(SlotVals<EPL> v, int n, float2* scratch) {
     const int lane = lane_id();
     float k[EPL], p[EPL];
 #pragma unroll
@@ -185,7 +184,7 @@ __device__ __noinline__ uint32_t ranks_full_sort_packed(SlotVals<EPL> v, int n, 
         p[r] = __int_as_float(slot);
     }
     bitonic_sort_kv<EPL>(k, p, lane);
-    uint8_t* sb = reinterpret_cast<uint8_t*>(sw);
+    uint8_t* sb = reinterpret_cast<uint8_t*>(scratch);
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
         const int pos = lane * EPL + r;
@@ -201,92 +200,92 @@ __device__ __noinline__ uint32_t ranks_full_sort_packed(SlotVals<EPL> v, int n, 
 
 template <int EPL>
 __device__ __forceinline__ void ranks_full_sort(const float (&v)[EPL], int n, int (&rk)[EPL],
-                                                const WarpScratch& sc, int lane) {
+                                                const WarpScratch& sc) {
     SlotVals<EPL> sv;
 #pragma unroll
     for (int r = 0; r < EPL; r++) sv.x[r] = v[r];
-    const uint32_t packed = ranks_full_sort_packed<EPL>(sv, n, sc.sw);
+    const uint32_t packed = ranks_full_sort_packed<EPL>(sv, n, sc.vw);
 #pragma unroll
     for (int r = 0; r < EPL; r++) rk[r] = (packed >> (8 * r)) & 255u;
-    (void)lane;
 }
 
-// Incremental rank maintenance.  `mw` = bit mask (warp-uniform) of the slots Algorithm R
-// wrote this step; slots < n_old existed before (their stored rank is removed), every
-// changed slot < n_new is (re-)inserted by counting the present elements below it.
-// Ties are ordered by slot index; any order of equal values is a valid sorted order.
+// ---------------------------------------------------------------------------
+// Incremental rank maintenance for a FULL reservoir (all 32*EPL slots valid) in which
+// Algorithm R replaced a few slots.  v[] already holds the new values, rk[] the ranks of
+// the previous contents.  Order is the strict total order on (value, slot), so equal
+// values rank by slot index (any order of equal values is a valid sorted order).
+//
+// One replaced slot c (the common case): remove its old rank, count the elements below
+// the new value, shift the ones above.  ~45 instructions.
 template <int EPL>
-__device__ __forceinline__ void ranks_update(const float (&v)[EPL], int (&rk)[EPL], int n_new, int n_old,
-                                             const uint32_t* mws, int stride, int nchg,
-                                             const WarpScratch& sc, int lane) {
-    // mws[k * stride], k = 0..3: mask words in shared memory (warp-uniform addresses).
-    // Every changed slot is published as (new value, slot, old rank) in a small shared list;
-    // then each lane fixes the ranks of its own slots in ONE pass over that list:
-    //   unchanged slot i : rank - #{removed with lower old rank} + #{inserted (x,c) < (v_i,i)}
-    //   changed slot c   : #{unchanged (v_i,i) < (x_c,c)} + #{inserted (x,c') < (x_c,c)}
-    constexpr int NW = EPL == 4 ? 4 : EPL;  // words that can hold slots < 32*EPL
+__device__ __forceinline__ void rank_replace_one(const float (&v)[EPL], int (&rk)[EPL], int c, int lane) {
     const int s0 = lane * EPL;
-    const int wi = s0 >> 5;
-    uint32_t word = mws[0];
-    int below = 0;
-    if constexpr (NW >= 2) {
-        const uint32_t m1 = mws[stride];
-        below = wi >= 1 ? __popc(word) : 0;
-        word = wi == 1 ? m1 : word;
-        if constexpr (NW == 4) {
-            const uint32_t m2 = mws[2 * stride], m3 = mws[3 * stride];
-            below += wi >= 2 ? __popc(m1) : 0;
-            below += wi >= 3 ? __popc(m2) : 0;
-            word = wi == 2 ? m2 : (wi == 3 ? m3 : word);
-        }
-    }
-    const uint32_t chg = (word >> (s0 & 31)) & ((1u << EPL) - 1u);
-    below += __popc(word & ((1u << (s0 & 31)) - 1u));
-    float* Lx = sc.sv;
-    int* Lc = reinterpret_cast<int*>(sc.sw);
-    int* Lr = Lc + 32;
+    const float x = slot_fetch<EPL>(v, c);
+    const int r_old = slot_fetch<EPL>(rk, c);
+    bool before[EPL];
+    int cnt = 0;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        if ((chg >> r) & 1u) {
-            Lx[below] = v[r];
-            Lc[below] = s0 + r;
-            Lr[below] = s0 + r < n_old ? rk[r] : 1000;  // 1000: did not exist, removes nothing
-            below++;
-        }
+        before[r] = v[r] < x || (v[r] == x && s0 + r < c);  // (v_i, i) < (x, c); false for i == c
+        cnt += before[r] ? 1 : 0;
     }
-    __syncwarp();
-    int adj[EPL], self[EPL];
+    const int r_new = __reduce_add_sync(MLB_FULL, cnt);
 #pragma unroll
-    for (int r = 0; r < EPL; r++) { adj[r] = 0; self[r] = 0; }
+    for (int r = 0; r < EPL; r++) {
+        const int nr = rk[r] - (rk[r] > r_old ? 1 : 0) + (before[r] ? 0 : 1);
+        rk[r] = (s0 + r == c) ? r_new : nr;
+    }
+}
+
+// General form (`list` = up to three slot ids, one per byte; slots >= n_old are appended, not
+// replaced; absent slots carry rank -1): first every old rank is taken out, then the new
+// values are inserted one at a time among the elements present so far.  Each sub-step leaves
+// a valid ranking of the present set.
+template <int EPL>
+__device__ __forceinline__ void rank_replace_few(const float (&v)[EPL], int (&rk)[EPL], uint32_t list, int nchg,
+                                                 int n_old, int lane) {
+    const int s0 = lane * EPL;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) rk[r] = s0 + r < n_old ? rk[r] : -1;
 #pragma unroll 1
     for (int k = 0; k < nchg; k++) {
-        const float x = Lx[k];
-        const int c = Lc[k], rold = Lr[k];
+        const int c = (list >> (8 * k)) & 255;
+        if (c >= n_old) continue;  // appended slot: nothing to remove
+        const int r_old = slot_fetch<EPL>(rk, c);
+#pragma unroll
+        for (int r = 0; r < EPL; r++) {
+            rk[r] -= rk[r] > r_old ? 1 : 0;
+            rk[r] = (s0 + r == c) ? -1 : rk[r];
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < nchg; k++) {
+        const int c = (list >> (8 * k)) & 255;
+        const float x = slot_fetch<EPL>(v, c);
+        bool after[EPL];
         int cnt = 0;
 #pragma unroll
         for (int r = 0; r < EPL; r++) {
-            const int slot = s0 + r;
-            const bool lt = x < v[r] || (x == v[r] && c < slot);  // (x_k, c_k) < (v_i, i)
-            const bool unchanged = slot < n_new && !((chg >> r) & 1u);
-            adj[r] += lt ? 1 : 0;
-            adj[r] -= (unchanged && rk[r] > rold) ? 1 : 0;
-            cnt += (unchanged && !lt) ? 1 : 0;  // strict total order: !lt <=> (v_i, i) < (x_k, c_k)
+            const bool present = rk[r] >= 0;
+            const bool before = v[r] < x || (v[r] == x && s0 + r < c);
+            after[r] = present && !before;
+            cnt += (present && before) ? 1 : 0;
         }
-        const int tot = __reduce_add_sync(MLB_FULL, cnt);
+        const int r_new = __reduce_add_sync(MLB_FULL, cnt);
 #pragma unroll
-        for (int r = 0; r < EPL; r++) self[r] = (s0 + r == c) ? tot : self[r];
+        for (int r = 0; r < EPL; r++) {
+            rk[r] += after[r] ? 1 : 0;
+            rk[r] = (s0 + r == c) ? r_new : rk[r];
+        }
     }
-#pragma unroll
-    for (int r = 0; r < EPL; r++) rk[r] = (((chg >> r) & 1u) ? self[r] : rk[r]) + adj[r];
-    __syncwarp();  // the list lives in the scratch that features_ranked overwrites next
 }
 
 // Cold paths of the weighted percentile, taken when the float32 cumulative weights come
-// within MLB_WP_MARGIN of the cutoff.  st = timestamps in rank order (shared memory), n <= 128.
+// within MLB_WP_MARGIN of the cutoff.  st[p].y = timestamp of the element at rank p, n <= 128.
 //
 // Tier 2: float64 weights 2^(log2(decay) * (tmax - t)) and a float64 warp scan; decides unless
 // a cumulative weight is within 1e-9 (relative) of the cutoff, i.e. a genuine tie.
-static __device__ __noinline__ int weighted_index_scan_f64(const float* st, int n, float tmax, double decay,
+static __device__ __noinline__ int weighted_index_scan_f64(const float2* st, int n, float tmax, double decay,
                                                            bool* ambiguous) {
     const int lane = lane_id();
     const double l2d = log2(decay);
@@ -295,7 +294,7 @@ static __device__ __noinline__ int weighted_index_scan_f64(const float* st, int 
 #pragma unroll
     for (int k = 0; k < 4; k++) {  // position p = k*32 + lane
         const int pos = k * 32 + lane;
-        w[k] = pos < n ? exp2(l2d * ((double)tmax - (double)st[pos])) : 0.0;
+        w[k] = pos < n ? exp2(l2d * ((double)tmax - (double)st[pos].y)) : 0.0;
         double sc = w[k];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -322,13 +321,13 @@ static __device__ __noinline__ int weighted_index_scan_f64(const float* st, int 
 // Tier 3: the reference's own arithmetic (reservoir.py:148-149,181-196): w = pow(decay, now - t)
 // and a strictly sequential cumsum in value order.  Returns the searchsorted-left index of
 // 0.9 * cumsum[-1] (n if none).
-static __device__ __noinline__ int weighted_index_f64(const float* st, int n, float now, double decay) {
+static __device__ __noinline__ int weighted_index_f64(const float2* st, int n, float now, double decay) {
     const int lane = lane_id();
     double w[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int pos = k * 32 + lane;
-        w[k] = pos < n ? pow(decay, (double)now - (double)st[pos]) : 0.0;
+        w[k] = pos < n ? pow(decay, (double)now - (double)st[pos].y) : 0.0;
     }
     double c = 0.0;
 #pragma unroll 1
@@ -353,75 +352,105 @@ static __device__ __noinline__ int weighted_index_f64(const float* st, int n, fl
     return idx;
 }
 
-// The five features given slot-ordered values/timestamps and valid ranks.
+// Both float64 tiers; out of line so the steady-state loop stays small.
 template <int EPL>
+__device__ __noinline__ int weighted_index_exact(SlotVals<EPL> t, uint32_t rk_packed, int n, float tmax, float now,
+                                                 double decay, float2* vw) {
+    const int s0 = lane_id() * EPL;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < EPL; r++)
+        if (s0 + r < n) vw[(rk_packed >> (8 * r)) & 255u].y = t.x[r];  // weights are no longer needed
+    __syncwarp();
+    bool ambiguous;
+    int idx = weighted_index_scan_f64(vw, n, tmax, decay, &ambiguous);
+    if (ambiguous) idx = weighted_index_f64(vw, n, now, decay);
+    return idx;
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// The five features given slot-ordered values/timestamps and valid ranks.
+// FULL: all 32*EPL slots are valid (n == 32*EPL), which makes n and everything derived from
+// it (p90 positions, interpolation weight, 1/n) compile-time constants.
+template <int EPL, bool FULL>
 __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const float (&t)[EPL],
-                                                const int (&rk)[EPL], int n, float now, double decay,
+                                                const int (&rk)[EPL], int n_, float now, double decay,
                                                 float log2_decay, const WarpScratch& sc, float (&out)[5]) {
     const int lane = lane_id();
     const int s0 = lane * EPL;
-    // ---- mean / std (np.mean, np.std on float32: reservoir.py:143,145)
+    const int n = FULL ? 32 * EPL : n_;
+    // ---- mean (np.mean on float32: reservoir.py:143), newest timestamp
     float s = 0.f, tmax = -MLB_INF;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const bool valid = s0 + r < n;
+        const bool valid = FULL || s0 + r < n;
         s += valid ? v[r] : 0.f;
         tmax = valid ? fmaxf(tmax, t[r]) : tmax;
     }
     const float nf = (float)n;
     const float mean = warp_sum(s) / nf;
-    tmax = warp_max(tmax);
-    // ---- decay weights relative to the newest sample (float32 fast path), scatter by rank
+    tmax = f32_from_orderable(__reduce_max_sync(MLB_FULL, f32_orderable(tmax)));
+    // ---- std (np.std, two passes: reservoir.py:145); decay weights relative to the newest
+    //      sample (float32 fast path); (value, weight) scattered by rank
     float s2 = 0.f, svw = 0.f;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const bool valid = s0 + r < n;
+        const bool valid = FULL || s0 + r < n;
         const float d = v[r] - mean;
         s2 += valid ? d * d : 0.f;
         const float w = valid ? fast_exp2(log2_decay * (tmax - t[r])) : 0.f;
         svw += valid ? v[r] * w : 0.f;
         const int pos = valid ? rk[r] : s0 + r;  // ranks cover [0,n); slots >= n pad positions >= n
-        sc.sv[pos] = v[r];
-        sc.sw[pos] = w;
+        sc.vw[pos] = make_float2(v[r], w);
     }
-    const float sd = sqrtf(warp_sum(s2) / nf);
+    const float sd = fast_sqrt(warp_sum(s2) / nf);
     svw = warp_sum(svw);
     __syncwarp();
     // ---- weighted percentile: blocked read of weights in rank order + warp scan
-    float wq[EPL], cum[EPL];
-    load_smem_block<EPL>(sc.sw, lane, wq);
+    float cum[EPL];
     float sw = 0.f;
 #pragma unroll
-    for (int r = 0; r < EPL; r++) {
-        sw += wq[r];
-        cum[r] = sw;
+    for (int r = 0; r < EPL; r += 2) {
+        if constexpr (EPL == 1) {
+            sw += sc.vw[s0].y;
+            cum[0] = sw;
+        } else {
+            const float4 q = *reinterpret_cast<const float4*>(sc.vw + s0 + r);
+            sw += q.y;
+            cum[r] = sw;
+            sw += q.w;
+            cum[r + 1] = sw;
+        }
     }
     const float incl = warp_scan_incl(sw, lane);
     const float W = __shfl_sync(MLB_FULL, incl, 31);
-    const float excl = incl - sw;
-    const float mean_decay = svw / W;
-    const float cutoff = 0.9f * W;
+    const float mean_decay = __fdividef(svw, W);
+    const float rel = 0.9f * W - (incl - sw);  // cutoff relative to this lane's first position
     int below = 0;
     float dmin = MLB_INF;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const bool valid = s0 + r < n;  // here s0+r is a POSITION in rank order
-        const float c = excl + cum[r];
-        below += (valid && c < cutoff) ? 1 : 0;
-        dmin = valid ? fminf(dmin, fabsf(c - cutoff)) : dmin;
+        const bool valid = FULL || s0 + r < n;  // here s0+r is a POSITION in rank order
+        below += (valid && cum[r] < rel) ? 1 : 0;
+        dmin = valid ? fminf(dmin, fabsf(cum[r] - rel)) : dmin;
     }
     int idx = __reduce_add_sync(MLB_FULL, below);
     const uint32_t dmin_bits = __reduce_min_sync(MLB_FULL, __float_as_uint(dmin));
     if (__uint_as_float(dmin_bits) < MLB_WP_MARGIN * W) {
         // ---- not trusted: redo the decision in the reference's float64 arithmetic
-        __syncwarp();
+        SlotVals<EPL> tv;
+        uint32_t packed = 0;
 #pragma unroll
-        for (int r = 0; r < EPL; r++)
-            if (s0 + r < n) sc.sw[rk[r]] = t[r];
-        __syncwarp();
-        bool ambiguous;
-        idx = weighted_index_scan_f64(sc.sw, n, tmax, decay, &ambiguous);
-        if (ambiguous) idx = weighted_index_f64(sc.sw, n, now, decay);
+        for (int r = 0; r < EPL; r++) {
+            tv.x[r] = t[r];
+            packed |= (uint32_t)(rk[r] & 255) << (8 * r);
+        }
+        idx = weighted_index_exact<EPL>(tv, packed, n, tmax, now, decay, sc.vw);
     }
     idx = idx > n - 1 ? n - 1 : idx;  // reservoir.py:193-194
     // ---- p90 = np.percentile(values, 90): float32 'linear' rule of numpy >= 2
@@ -431,8 +460,8 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
     if (vidx >= (float)(n - 1)) { lo = n - 1; hi = n - 1; }
     hi = hi > n - 1 ? n - 1 : hi;
     const float gamma = vidx - fl;
-    const float a = sc.sv[lo], b = sc.sv[hi];
-    const float p90_decay = sc.sv[idx];
+    const float a = sc.vw[lo].x, b = sc.vw[hi].x;
+    const float p90_decay = sc.vw[idx].x;
     const float diff = __fsub_rn(b, a);
     float p90 = __fadd_rn(a, __fmul_rn(diff, gamma));
     if (gamma >= 0.5f) p90 = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
@@ -444,83 +473,77 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
     out[4] = p90_decay;
 }
 
-// Stateless form: ranks from scratch every time.  n = min(count, K), may be 0.
-__device__ __forceinline__ void warp_features(const float* __restrict__ vals,
-                                              const float* __restrict__ tss, int n, float now,
-                                              double decay, float log2_decay, const WarpScratch& sc,
-                                              float (&out)[5]) {
-    const int lane = lane_id();
-    if (n <= 0) {  // reservoir.py:127-134
-#pragma unroll
-        for (int q = 0; q < 5; q++) out[q] = 0.f;
-    } else if (n <= 32) {
-        float v[1], t[1];
-        int rk[1];
-        load_slots<1>(vals, lane, v);
-        load_slots<1>(tss, lane, t);
-        ranks_full_sort<1>(v, n, rk, sc, lane);
-        features_ranked<1>(v, t, rk, n, now, decay, log2_decay, sc, out);
-    } else if (n <= 64) {
-        float v[2], t[2];
-        int rk[2];
-        load_slots<2>(vals, lane, v);
-        load_slots<2>(tss, lane, t);
-        ranks_full_sort<2>(v, n, rk, sc, lane);
-        features_ranked<2>(v, t, rk, n, now, decay, log2_decay, sc, out);
-    } else {
-        float v[4], t[4];
-        int rk[4];
-        load_slots<4>(vals, lane, v);
-        load_slots<4>(tss, lane, t);
-        ranks_full_sort<4>(v, n, rk, sc, lane);
-        features_ranked<4>(v, t, rk, n, now, decay, log2_decay, sc, out);
-    }
-}
-
-// Stateful form used by the env step: ranks live in global memory next to the reservoir
-// and are updated incrementally when only a few slots changed.
-//   n_old  valid slots when the stored ranks were computed (0: no ranks yet)
-//   mws    mask (4 words, shared memory, word k at mws[k*stride]) of slots written since then
-//   force_full: ignore stored ranks (feature_cache modes 0 / 2)
+// Ranks from scratch, then the features: the stateless form (reservoir_features_kernel) and
+// every case of the env step that is not "full reservoir, a few replaced slots".  `ranks`
+// (may be null) receives the ranks for later incremental updates.  n = min(count, K) >= 1.
 template <int EPL>
-__device__ __forceinline__ void features_cached_epl(const float* __restrict__ vals, const float* __restrict__ tss,
-                                                    uint8_t* __restrict__ ranks, int n, int n_old,
-                                                    const uint32_t* mws, int stride, int nchg, bool force_full,
-                                                    float now, double decay, float log2_decay,
-                                                    const WarpScratch& sc, float (&out)[5]) {
+__device__ __forceinline__ void features_sorted_epl(const float* __restrict__ vals, const float* __restrict__ tss,
+                                                    uint8_t* __restrict__ ranks, int n, float now, double decay,
+                                                    float log2_decay, const WarpScratch& sc, float (&out)[5]) {
     const int lane = lane_id();
     float v[EPL], t[EPL];
     int rk[EPL];
     load_slots<EPL>(vals, lane, v);
     load_slots<EPL>(tss, lane, t);
-    // stored ranks are only meaningful if they were laid out for a population that this
-    // EPL variant also covers (n_old <= 32*EPL always holds since n_old <= n)
-    constexpr int kMaxIncremental = EPL == 1 ? 2 : (EPL == 2 ? 5 : 10);  // ~50 instr per slot vs the sort
-    if (force_full || n_old == 0 || nchg > kMaxIncremental) {
-        ranks_full_sort<EPL>(v, n, rk, sc, lane);
-    } else {
-        load_ranks<EPL>(ranks, lane, rk);
-        ranks_update<EPL>(v, rk, n, n_old, mws, stride, nchg, sc, lane);
-    }
-    store_ranks<EPL>(ranks, lane, rk);
-    features_ranked<EPL>(v, t, rk, n, now, decay, log2_decay, sc, out);
+    ranks_full_sort<EPL>(v, n, rk, sc);
+    if (ranks) store_ranks<EPL>(ranks, lane, rk);
+    if (n == 32 * EPL)
+        features_ranked<EPL, true>(v, t, rk, n, now, decay, log2_decay, sc, out);
+    else
+        features_ranked<EPL, false>(v, t, rk, n, now, decay, log2_decay, sc, out);
 }
 
-__device__ __forceinline__ void warp_features_cached(const float* __restrict__ vals, const float* __restrict__ tss,
-                                                     uint8_t* __restrict__ ranks, int n, int n_old,
-                                                     const uint32_t* mws, int stride, int nchg, bool force_full,
-                                                     float now, double decay, float log2_decay,
-                                                     const WarpScratch& sc, float (&out)[5]) {
-    if (n <= 0) {
+// lane q < 5 keeps feature q (the lane that stores it)
+__device__ __forceinline__ float feature_of_lane(const float (&f)[5], int lane) {
+    float mine = f[0];
 #pragma unroll
-        for (int q = 0; q < 5; q++) out[q] = 0.f;
+    for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
+    return mine;
+}
+
+// Returns feature `lane` in lanes 0..4.
+static __device__ __noinline__ float warp_features_sorted(const float* __restrict__ vals, const float* __restrict__ tss,
+                                                          uint8_t* __restrict__ ranks, int n, float now, double decay,
+                                                          float log2_decay, float2* scratch) {
+    const WarpScratch sc{scratch};
+    float f[5];
+    if (n <= 0) {  // reservoir.py:127-134
+#pragma unroll
+        for (int q = 0; q < 5; q++) f[q] = 0.f;
     } else if (n <= 32) {
-        features_cached_epl<1>(vals, tss, ranks, n, n_old, mws, stride, nchg, force_full, now, decay, log2_decay, sc, out);
+        features_sorted_epl<1>(vals, tss, ranks, n, now, decay, log2_decay, sc, f);
     } else if (n <= 64) {
-        features_cached_epl<2>(vals, tss, ranks, n, n_old, mws, stride, nchg, force_full, now, decay, log2_decay, sc, out);
+        features_sorted_epl<2>(vals, tss, ranks, n, now, decay, log2_decay, sc, f);
     } else {
-        features_cached_epl<4>(vals, tss, ranks, n, n_old, mws, stride, nchg, force_full, now, decay, log2_decay, sc, out);
+        features_sorted_epl<4>(vals, tss, ranks, n, now, decay, log2_decay, sc, f);
     }
+    return feature_of_lane(f, lane_id());
+}
+
+// Steady state of the env step: a reservoir of 65..128 valid slots whose ranks live in global
+// memory next to it and in which Algorithm R wrote `nchg` <= 3 slots (ids in `list`, one per
+// byte; slots >= n_old are appends of the fill phase) since those ranks were stored.
+// Returns feature `lane` in lanes 0..4.
+__device__ __forceinline__ float warp_features_incremental(const float* __restrict__ vals, const float* __restrict__ tss,
+                                                           uint8_t* __restrict__ ranks, int n, int n_old, uint32_t list,
+                                                           int nchg, float now, double decay, float log2_decay,
+                                                           const WarpScratch& sc) {
+    const int lane = lane_id();
+    float v[4], t[4], f[5];
+    int rk[4];
+    load_slots<4>(vals, lane, v);
+    load_slots<4>(tss, lane, t);
+    load_ranks<4>(ranks, lane, rk);
+    if (n_old == 128 && nchg == 1)
+        rank_replace_one<4>(v, rk, (int)(list & 255u), lane);
+    else
+        rank_replace_few<4>(v, rk, list, nchg, n_old, lane);
+    store_ranks<4>(ranks, lane, rk);
+    if (n == 128)
+        features_ranked<4, true>(v, t, rk, 128, now, decay, log2_decay, sc, f);
+    else
+        features_ranked<4, false>(v, t, rk, n, now, decay, log2_decay, sc, f);
+    return feature_of_lane(f, lane);
 }
 
 }  // namespace mlb

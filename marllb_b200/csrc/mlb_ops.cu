@@ -45,13 +45,8 @@ __global__ void reservoir_features_kernel(const float* __restrict__ values, cons
     if (r >= R) return;
     const uint32_t c = count[r];
     const int n = c < (uint32_t)K ? (int)c : K;
-    float* scr = scratch[threadIdx.x >> 5];
-    const WarpScratch sc{scr, scr + 128};
-    float f[5];
-    warp_features(values + (size_t)r * KP, ts + (size_t)r * KP, n, now[r], decay, log2_decay, sc, f);
-    float mine = f[0];
-#pragma unroll
-    for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
+    const float mine = warp_features_sorted(values + (size_t)r * KP, ts + (size_t)r * KP, nullptr, n, now[r], decay,
+                                            log2_decay, reinterpret_cast<float2*>(scratch[threadIdx.x >> 5]));
     if (lane < 5) out[(size_t)r * 5 + lane] = mine;
 }
 

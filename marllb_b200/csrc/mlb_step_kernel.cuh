@@ -37,8 +37,8 @@ enum : int {
     F_CUR0, F_CUR1,  // MT19937 replay cursors
     F_FLAGS,     // bit0/bit1: reservoir m touched this step
     F_NOLD,      // valid slots at step start: fct | flow_duration << 8
-    F_CHG,       // 8 words: [metric][word] mask of reservoir slots written this step
-    F_LIST = F_CHG + 8,  // 2*SP uint16: compact list of (server*2 + metric) to re-evaluate
+    F_CHG,       // 2 words: per metric, slots written this step: count << 24 | up to three slot ids
+    F_LIST = F_CHG + 2,  // 2*SP uint16: compact list of (server*2 + metric) to re-evaluate
     NF
 };
 
@@ -113,7 +113,15 @@ __device__ __forceinline__ void res_add(const DevState& d, uint32_t* sm, const W
         g.res_val[at] = value;
         g.res_ts[at] = ts;
         sm[F_FLAGS * SP + j] |= (1u << m);
-        sm[(F_CHG + m * 4 + (slot >> 5)) * SP + j] |= 1u << (slot & 31);
+        // remember which slot changed (first three distinct ones; more -> ranks are re-sorted)
+        uint32_t w = sm[(F_CHG + m) * SP + j];
+        const uint32_t nc = w >> 24;
+        const bool dup = (nc >= 1 && (w & 255u) == (uint32_t)slot) || (nc >= 2 && ((w >> 8) & 255u) == (uint32_t)slot) ||
+                         (nc >= 3 && ((w >> 16) & 255u) == (uint32_t)slot);
+        if (!dup && nc < 255u) {
+            if (nc < 3) w |= (uint32_t)slot << (8 * nc);
+            sm[(F_CHG + m) * SP + j] = w + (1u << 24);
+        }
     }
 }
 
@@ -251,7 +259,7 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
     uint32_t* sm = reinterpret_cast<uint32_t*>(wbase);
     float* smf = reinterpret_cast<float*>(wbase);
     float* scr = reinterpret_cast<float*>(wbase + (size_t)NF * SP * 4);
-    const WarpScratch scratch{scr, scr + 128};
+    const WarpScratch scratch{reinterpret_cast<float2*>(scr)};
     double* a_prob = reinterpret_cast<double*>(wbase + (size_t)NF * SP * 4 + MLB_SCRATCH_BYTES);
     int32_t* a_alias = reinterpret_cast<int32_t*>(a_prob + SP);
     float* rv = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * wbytes) + (size_t)env_in_blk * 2 * S;
@@ -314,8 +322,8 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
             }
             sm[F_NOLD * SP + j] = nold;
             sm[F_FLAGS * SP + j] = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) sm[(F_CHG + k) * SP + j] = 0;
+            sm[F_CHG * SP + j] = 0;
+            sm[(F_CHG + 1) * SP + j] = 0;
         }
     }
     __syncwarp();
@@ -498,15 +506,16 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
         const uint32_t cnt = sm[(F_CNT0 + m) * SP + jj];
         const int n = cnt < (uint32_t)d.K ? (int)cnt : d.K;
         const int n_old = (int)((sm[F_NOLD * SP + jj] >> (8 * m)) & 255u);
-        const uint32_t* mws = sm + (F_CHG + m * 4) * SP + jj;
-        const int nchg = __popc(mws[0]) + __popc(mws[SP]) + __popc(mws[2 * SP]) + __popc(mws[3 * SP]);
+        const uint32_t chg = sm[(F_CHG + m) * SP + jj];
+        const int nchg = (int)(chg >> 24);
         const int rid = id * KP;
-        float f[5];
-        warp_features_cached(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, n_old, mws, SP, nchg,
-                             d.feature_cache != 1, t1, d.decay, d.log2_decay, scratch, f);
-        float mine = f[0];
-#pragma unroll
-        for (int q = 1; q < 5; q++) mine = lane == q ? f[q] : mine;
+        float mine;
+        if (n_old > 0 && n > 64 && nchg <= 3 && nchg > 0 && d.feature_cache == 1)
+            mine = warp_features_incremental(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, n_old, chg, nchg,
+                                             t1, d.decay, d.log2_decay, scratch);
+        else
+            mine = warp_features_sorted(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, t1, d.decay,
+                                        d.log2_decay, scratch.vw);
         if (lane < 5) g.obs[jj * MLB_OBS_COLS + 1 + 5 * m + lane] = mine;
     }
     __syncwarp();
