@@ -34,8 +34,9 @@ struct mlb_env {
     void* d_action = nullptr;
     size_t action_bytes = 0;
     uint8_t* d_mask = nullptr;
-    size_t smem_bytes = 0;
-    int epb = 1, threads = 32;
+    size_t ev_smem = 0, ft_smem = 0;   // dynamic shared memory of the event / feature kernel
+    int ev_threads = 128;              // event kernel: independent warps
+    int epb = 1, ft_threads = 32;      // feature kernel: epb envs x A agent warps per block
     size_t state_bytes[MLB_F_COUNT_] = {0};
     void* state_ptr[MLB_F_COUNT_] = {nullptr};
 };
@@ -172,46 +173,60 @@ __global__ void gen_poisson_kernel(float* __restrict__ time, float* __restrict__
 
 // ------------------------------------------------------------------ helpers
 template <int POLICY>
-static const void* step_fn_r(int R) {
+static const void* event_fn_r(int R) {
     switch (R) {
-    case 1: return (const void*)step_kernel<POLICY, 1>;
-    case 2: return (const void*)step_kernel<POLICY, 2>;
-    case 4: return (const void*)step_kernel<POLICY, 4>;
-    default: return (const void*)step_kernel<POLICY, 8>;
+    case 1: return (const void*)event_kernel<POLICY, 1>;
+    case 2: return (const void*)event_kernel<POLICY, 2>;
+    case 4: return (const void*)event_kernel<POLICY, 4>;
+    default: return (const void*)event_kernel<POLICY, 8>;
     }
 }
 static int lanes_r(int Sa) { return Sa <= 32 ? 1 : (Sa <= 64 ? 2 : (Sa <= 128 ? 4 : 8)); }
-static const void* step_fn(int policy, int Sa) {
+static const void* event_fn(int policy, int Sa) {
     const int R = lanes_r(Sa);
     switch (policy) {
-    case MLB_POLICY_SED: return step_fn_r<MLB_POLICY_SED>(R);
-    case MLB_POLICY_LSQ: return step_fn_r<MLB_POLICY_LSQ>(R);
-    default: return step_fn_r<MLB_POLICY_ALIAS>(R);
+    case MLB_POLICY_SED: return event_fn_r<MLB_POLICY_SED>(R);
+    case MLB_POLICY_LSQ: return event_fn_r<MLB_POLICY_LSQ>(R);
+    default: return event_fn_r<MLB_POLICY_ALIAS>(R);
     }
+}
+static const void* feature_fn(int Sa) {
+    switch (lanes_r(Sa)) {
+    case 1: return (const void*)feature_kernel<1>;
+    case 2: return (const void*)feature_kernel<2>;
+    case 4: return (const void*)feature_kernel<4>;
+    default: return (const void*)feature_kernel<8>;
+    }
+}
+
+// dynamic shared memory + carve-out sized for `warps_wanted` resident warps (the rest stays L1)
+static cudaError_t set_smem(const void* fn, size_t block_bytes, int threads, int warps_wanted) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_bytes);
+    if (e != cudaSuccess) return e;
+    const int wpb = threads / 32;
+    const int blocks_wanted = wpb >= warps_wanted ? 1 : warps_wanted / wpb;
+    const size_t want = (size_t)blocks_wanted * (block_bytes + 1024);
+    int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
+    pct = pct > 100 ? 100 : pct;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 static int launch_cfg(mlb_env* h) {
     const mlb_config& c = h->cfg;
     const int A = c.num_agents;
-    h->epb = A == 1 ? (getenv("MLB_EPB") ? atoi(getenv("MLB_EPB")) : 4) : (A == 2 ? 2 : 1);
-    h->threads = 32 * A * h->epb;
     const int SP = 32 * lanes_r(c.servers_per_agent);
     const bool alias = c.policy == MLB_POLICY_ALIAS;
-    h->smem_bytes = (size_t)(h->threads / 32) * warp_smem_bytes(SP, alias) +
-                    (size_t)h->epb * 2 * h->d.S * 4;
-    if (h->smem_bytes > 227 * 1024) return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)", h->smem_bytes);
-    if (h->threads > 1024) return fail(h, MLB_EINVAL, "num_agents > 32 not supported");
-    const void* fn = step_fn(c.policy, c.servers_per_agent);
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-    if (e == cudaSuccess) {
-        // shared-memory carve-out sized for 8 resident blocks (the rest stays L1)
-        const int wpb = h->threads / 32;
-        const int blocks_wanted = wpb >= 32 ? 1 : 32 / wpb;  // aim for 32 resident warps (64 regs)
-        size_t want = (size_t)blocks_wanted * (h->smem_bytes + 1024);
-        int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
-        pct = pct > 100 ? 100 : pct;
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
+    h->ev_threads = 128;
+    h->ev_smem = (size_t)(h->ev_threads / 32) * event_warp_smem_bytes(SP, alias);
+    h->epb = A == 1 ? (getenv("MLB_EPB") ? atoi(getenv("MLB_EPB")) : 4) : (A == 2 ? 2 : 1);
+    h->ft_threads = 32 * A * h->epb;
+    h->ft_smem = (size_t)(h->ft_threads / 32) * feature_warp_smem_bytes(SP) + (size_t)h->epb * 2 * h->d.S * 4;
+    if (h->ft_threads > 1024) return fail(h, MLB_EINVAL, "num_agents > 32 not supported");
+    if (h->ft_smem > 227 * 1024 || h->ev_smem > 227 * 1024)
+        return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)",
+                    h->ft_smem > h->ev_smem ? h->ft_smem : h->ev_smem);
+    cudaError_t e = set_smem(event_fn(c.policy, c.servers_per_agent), h->ev_smem, h->ev_threads, 32);
+    if (e == cudaSuccess) e = set_smem(feature_fn(c.servers_per_agent), h->ft_smem, h->ft_threads, 32);
     if (e != cudaSuccess) return fail(h, MLB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return MLB_OK;
 }
@@ -323,6 +338,7 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     CKC(dalloc(h, &d.res_count, ES * 2));
     CKC(dalloc(h, &d.res_cursor, ES * 2));
     CKC(dalloc(h, &d.res_rank, ES * 2 * d.KP));
+    CKC(dalloc(h, &d.res_chg, ES * 2));
     CKC(dalloc(h, &d.ring_arr, ES * d.Q));
     CKC(dalloc(h, &d.ring_fin, ES * d.Q));
     CKC(dalloc(h, &d.obs, ES * MLB_OBS_COLS));
@@ -560,14 +576,18 @@ int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, dou
         CK(h, cudaMemcpyAsync(h->d_action, action, h->action_bytes, cudaMemcpyHostToDevice, st));
         dact = h->d_action;
     }
-    const int blocks = (d.E + h->epb - 1) / h->epb;
     {
         DevState dv = d;
         const void* act = dact;
-        void* args[] = {&dv, &act};
-        CK(h, cudaLaunchKernel(step_fn(d.policy, d.Sa), dim3(blocks), dim3(h->threads), args, h->smem_bytes, st));
+        void* ev_args[] = {&dv, &act};
+        const int wpb = h->ev_threads / 32;
+        const int ev_blocks = (int)(((int64_t)d.E * d.A + wpb - 1) / wpb);
+        CK(h, cudaLaunchKernel(event_fn(d.policy, d.Sa), dim3(ev_blocks), dim3(h->ev_threads), ev_args, h->ev_smem, st));
+        void* ft_args[] = {&dv};
+        const int ft_blocks = (d.E + h->epb - 1) / h->epb;
+        CK(h, cudaLaunchKernel(feature_fn(d.Sa), dim3(ft_blocks), dim3(h->ft_threads), ft_args, h->ft_smem, st));
     }
-    h->launches++;
+    h->launches += 2;
     CK(h, cudaGetLastError());
     const cudaMemcpyKind kind = out_loc == MLB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const size_t ES = (size_t)d.E * d.S;

@@ -68,6 +68,16 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// Ampere-style asynchronous global -> shared copies (LDGSTS); .cg bypasses L1
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // streaming (evict-first) global accesses for data touched once per step
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     return __ldcs(reinterpret_cast<const float4*>(p));

@@ -237,7 +237,7 @@ __device__ __forceinline__ void rank_replace_one(const float (&v)[EPL], int (&rk
     }
 }
 
-// General form (`list` = up to three slot ids, one per byte; slots >= n_old are appended, not
+// General form (`list` = up to three 7-bit slot ids; slots >= n_old are appended, not
 // replaced; absent slots carry rank -1): first every old rank is taken out, then the new
 // values are inserted one at a time among the elements present so far.  Each sub-step leaves
 // a valid ranking of the present set.
@@ -249,7 +249,7 @@ __device__ __forceinline__ void rank_replace_few(const float (&v)[EPL], int (&rk
     for (int r = 0; r < EPL; r++) rk[r] = s0 + r < n_old ? rk[r] : -1;
 #pragma unroll 1
     for (int k = 0; k < nchg; k++) {
-        const int c = (list >> (8 * k)) & 255;
+        const int c = (list >> (7 * k)) & 127;
         if (c >= n_old) continue;  // appended slot: nothing to remove
         const int r_old = slot_fetch<EPL>(rk, c);
 #pragma unroll
@@ -260,7 +260,7 @@ __device__ __forceinline__ void rank_replace_few(const float (&v)[EPL], int (&rk
     }
 #pragma unroll 1
     for (int k = 0; k < nchg; k++) {
-        const int c = (list >> (8 * k)) & 255;
+        const int c = (list >> (7 * k)) & 127;
         const float x = slot_fetch<EPL>(v, c);
         bool after[EPL];
         int cnt = 0;
@@ -368,6 +368,11 @@ __device__ __noinline__ int weighted_index_exact(SlotVals<EPL> t, uint32_t rk_pa
     return idx;
 }
 
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float fast_sqrt(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -377,8 +382,11 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // The five features given slot-ordered values/timestamps and valid ranks.
 // FULL: all 32*EPL slots are valid (n == 32*EPL), which makes n and everything derived from
 // it (p90 positions, interpolation weight, 1/n) compile-time constants.
-template <int EPL, bool FULL>
-__device__ __forceinline__ void features_ranked(const float (&v)[EPL], const float (&t)[EPL],
+// DEFER: when the float32 weighted-percentile decision is not trusted, return false without
+// resolving it (the caller re-evaluates that reservoir on its cold path) instead of calling the
+// float64 tiers here, so that a hot loop contains no calls.
+template <int EPL, bool FULL, bool DEFER = false>
+__device__ __forceinline__ bool features_ranked(const float (&v)[EPL], const float (&t)[EPL],
                                                 const int (&rk)[EPL], int n_, float now, double decay,
                                                 float log2_decay, const WarpScratch& sc, float (&out)[5]) {
     const int lane = lane_id();
@@ -429,7 +437,7 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
     }
     const float incl = warp_scan_incl(sw, lane);
     const float W = __shfl_sync(MLB_FULL, incl, 31);
-    const float mean_decay = __fdividef(svw, W);
+    const float mean_decay = svw * fast_rcp(W);
     const float rel = 0.9f * W - (incl - sw);  // cutoff relative to this lane's first position
     int below = 0;
     float dmin = MLB_INF;
@@ -443,6 +451,10 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
     const uint32_t dmin_bits = __reduce_min_sync(MLB_FULL, __float_as_uint(dmin));
     if (__uint_as_float(dmin_bits) < MLB_WP_MARGIN * W) {
         // ---- not trusted: redo the decision in the reference's float64 arithmetic
+        if constexpr (DEFER) {
+            __syncwarp();  // scratch is reused by the next reservoir
+            return false;
+        }
         SlotVals<EPL> tv;
         uint32_t packed = 0;
 #pragma unroll
@@ -471,6 +483,7 @@ __device__ __forceinline__ void features_ranked(const float (&v)[EPL], const flo
     out[2] = sd;
     out[3] = mean_decay;
     out[4] = p90_decay;
+    return true;
 }
 
 // Ranks from scratch, then the features: the stateless form (reservoir_features_kernel) and
@@ -521,29 +534,29 @@ static __device__ __noinline__ float warp_features_sorted(const float* __restric
 }
 
 // Steady state of the env step: a reservoir of 65..128 valid slots whose ranks live in global
-// memory next to it and in which Algorithm R wrote `nchg` <= 3 slots (ids in `list`, one per
-// byte; slots >= n_old are appends of the fill phase) since those ranks were stored.
-// Returns feature `lane` in lanes 0..4.
-__device__ __forceinline__ float warp_features_incremental(const float* __restrict__ vals, const float* __restrict__ tss,
-                                                           uint8_t* __restrict__ ranks, int n, int n_old, uint32_t list,
-                                                           int nchg, float now, double decay, float log2_decay,
-                                                           const WarpScratch& sc) {
+// memory next to it and in which Algorithm R wrote `nchg` <= 3 slots (7-bit ids in `list`; slots >= n_old are appends of the fill phase) since those ranks were stored.
+// v, t, rk: this lane's four slots (already loaded); lane_ranks = &ranks[4 * lane].
+// Feature `lane` goes to `mine` in lanes 0..4; returns false if the weighted-percentile
+// decision was not trusted (the caller then re-evaluates the reservoir with warp_features_sorted).
+__device__ __forceinline__ bool warp_features_incremental(const float (&v)[4], const float (&t)[4], int (&rk)[4],
+                                                          uint8_t* __restrict__ lane_ranks, int n, int n_old,
+                                                          uint32_t list, int nchg, float now, double decay,
+                                                          float log2_decay, const WarpScratch& sc, float& mine) {
     const int lane = lane_id();
-    float v[4], t[4], f[5];
-    int rk[4];
-    load_slots<4>(vals, lane, v);
-    load_slots<4>(tss, lane, t);
-    load_ranks<4>(ranks, lane, rk);
+    float f[5];
     if (n_old == 128 && nchg == 1)
-        rank_replace_one<4>(v, rk, (int)(list & 255u), lane);
+        rank_replace_one<4>(v, rk, (int)(list & 127u), lane);
     else
         rank_replace_few<4>(v, rk, list, nchg, n_old, lane);
-    store_ranks<4>(ranks, lane, rk);
+    *reinterpret_cast<uint32_t*>(lane_ranks) = (uint32_t)(rk[0] & 255) | ((uint32_t)(rk[1] & 255) << 8) |
+                                               ((uint32_t)(rk[2] & 255) << 16) | ((uint32_t)rk[3] << 24);
+    bool ok;
     if (n == 128)
-        features_ranked<4, true>(v, t, rk, 128, now, decay, log2_decay, sc, f);
+        ok = features_ranked<4, true, true>(v, t, rk, 128, now, decay, log2_decay, sc, f);
     else
-        features_ranked<4, false>(v, t, rk, n, now, decay, log2_decay, sc, f);
-    return feature_of_lane(f, lane);
+        ok = features_ranked<4, false, true>(v, t, rk, n, now, decay, log2_decay, sc, f);
+    mine = feature_of_lane(f, lane);
+    return ok;
 }
 
 }  // namespace mlb

@@ -1,15 +1,19 @@
-// The fused env-step kernel: one warp per (env, LB agent).
+// The env step as two kernels, one warp per (env, LB agent) in both.
 //
 // Stands in for LoadBalanceEnv.step (reference:
 // simulation-mode/problem-03-rl-environment/src/env.py:215-286) executed for
-// E envs at once, with the flow-level dynamics of SURVEY.md App. B:
+// E envs at once, with the flow-level dynamics of SURVEY.md App. B.
+//
+// event_kernel  (integer / pointer-chasing work, latency-bound)
 //   phase 0  action -> weights (env.py:334-353); per-server scalars -> shared memory
 //   phase A  per arrival (time order): retire finished flows (n_flow_on--, fct
 //            sample -> Algorithm-R add, reservoir.py:50-85), choose a server
 //            (SED / LSQ / alias, src/vpp/lb/node.c:393-460) with REDUX argmin,
 //            push on that server's FIFO ring; the window end is one more
 //            (pseudo-)event of the same loop
-//   phase C  one flow_duration sample per still-active flow, state write-back
+//   phase C  one flow_duration sample per still-active flow, state write-back,
+//            one "changed slots" word per reservoir for the feature kernel
+// feature_kernel  (float work, streams the touched reservoirs)
 //   phase B  reservoir statistics of every reservoir touched this step
 //            (reservoir.py:105-196) -> obs columns (features.py:256-286)
 //   phase R  reward over the env's active servers (rewards.py:329-381), done flag
@@ -19,6 +23,8 @@
 // finish time of the oldest flow, the assignment score) lives in registers,
 // R = ceil(Sa/32) per lane; what changes only on events lives in shared memory.
 // Phase B is warp-cooperative per reservoir with warp-uniform control flow.
+// The split keeps each kernel's live state inside 64 registers (32 resident
+// warps per SM) and each hot loop inside the instruction cache.
 #pragma once
 #include "mlb_common.cuh"
 #include "mlb_env.cuh"
@@ -27,7 +33,7 @@
 
 namespace mlb {
 
-// per-server shared-memory fields (4 bytes each), field f of server j at smem[f*SP + j]
+// ---- event kernel: per-server shared-memory fields (4 bytes each), field f of server j at smem[f*SP + j]
 enum : int {
     F_NON = 0,   // n_flow_on
     F_LASTFIN,   // finish time of the newest queued flow
@@ -35,15 +41,27 @@ enum : int {
     F_ACT,       // discrete action index (or float weight bits for continuous actions)
     F_CNT0, F_CNT1,  // reservoir counts   (fct, flow_duration)
     F_CUR0, F_CUR1,  // MT19937 replay cursors
-    F_FLAGS,     // bit0/bit1: reservoir m touched this step
-    F_NOLD,      // valid slots at step start: fct | flow_duration << 8
-    F_CHG,       // 2 words: per metric, slots written this step: count << 24 | up to three slot ids
-    F_LIST = F_CHG + 2,  // 2*SP uint16: compact list of (server*2 + metric) to re-evaluate
+    F_CHG0, F_CHG1,  // changed-slot word of each reservoir (see chg_* below)
     NF
 };
 
-__host__ __device__ inline size_t warp_smem_bytes(int SP, bool alias) {
-    return (size_t)NF * SP * 4 + MLB_SCRATCH_BYTES + (alias ? (size_t)SP * (8 + 4 + 8) : 0);
+// "changed slots" word of one reservoir, event kernel -> feature kernel:
+//   [0:7) [7:14) [14:21)  the first three distinct slots Algorithm R wrote this step
+//   [21:24)               how many distinct slots were written (saturates at 7; > 3: re-sort)
+//   [24:32)               n_old = valid slots at step start
+__device__ __forceinline__ uint32_t chg_count(uint32_t w) { return (w >> 21) & 7u; }
+__device__ __forceinline__ uint32_t chg_nold(uint32_t w) { return w >> 24; }
+
+__host__ __device__ inline size_t event_warp_smem_bytes(int SP, bool alias) {
+    return (size_t)NF * SP * 4 + (alias ? (size_t)SP * (8 + 4 + 8 + 4) : 0);
+}
+
+// ---- feature kernel: per-warp shared memory = dirty list | rank-order scratch | staging buffer
+// staging buffer: values[128] | timestamps[128] | ranks[128 bytes] of the NEXT reservoir,
+// filled by cp.async while the current one is being evaluated
+#define MLB_STAGE_BYTES 1152
+__host__ __device__ inline size_t feature_warp_smem_bytes(int SP) {
+    return (size_t)2 * SP * 8 + MLB_SCRATCH_BYTES + MLB_STAGE_BYTES;
 }
 
 // Assignment score of one server as an order-preserving uint.
@@ -92,10 +110,8 @@ __device__ __forceinline__ int res_draw_slot(uint32_t cnt, uint32_t& cur, const 
 struct WarpGlobals {
     float* res_val;     // this agent's reservoirs [Sa][2][KP]
     float* res_ts;
-    uint8_t* res_rank;
     float* ring_arr;    // [Sa][Q]
     float* ring_fin;
-    float* obs;         // [Sa][11]
     const uint32_t* mt; // replay rows of this agent's servers [Sa][L]
 };
 
@@ -112,15 +128,14 @@ __device__ __forceinline__ void res_add(const DevState& d, uint32_t* sm, const W
         const int at = (j * 2 + m) * d.KP + slot;
         g.res_val[at] = value;
         g.res_ts[at] = ts;
-        sm[F_FLAGS * SP + j] |= (1u << m);
         // remember which slot changed (first three distinct ones; more -> ranks are re-sorted)
-        uint32_t w = sm[(F_CHG + m) * SP + j];
-        const uint32_t nc = w >> 24;
-        const bool dup = (nc >= 1 && (w & 255u) == (uint32_t)slot) || (nc >= 2 && ((w >> 8) & 255u) == (uint32_t)slot) ||
-                         (nc >= 3 && ((w >> 16) & 255u) == (uint32_t)slot);
-        if (!dup && nc < 255u) {
-            if (nc < 3) w |= (uint32_t)slot << (8 * nc);
-            sm[(F_CHG + m) * SP + j] = w + (1u << 24);
+        uint32_t w = sm[(F_CHG0 + m) * SP + j];
+        const uint32_t nc = chg_count(w);
+        const bool dup = (nc >= 1 && (w & 127u) == (uint32_t)slot) || (nc >= 2 && ((w >> 7) & 127u) == (uint32_t)slot) ||
+                         (nc >= 3 && ((w >> 14) & 127u) == (uint32_t)slot);
+        if (!dup && nc < 7u) {
+            if (nc < 3u) w |= (uint32_t)slot << (7 * nc);
+            sm[(F_CHG0 + m) * SP + j] = w + (1u << 21);
         }
     }
 }
@@ -236,34 +251,29 @@ __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint
     return -(sqrt(var) / (mean + eps));
 }
 
-// R = servers per lane (Sa <= 32*R), SP = 32*R.
+// ---------------------------------------------------------------------------
+// event_kernel: R = servers per lane (Sa <= 32*R), SP = 32*R.  Warps are independent.
 template <int POLICY, int R>
-__global__ void __launch_bounds__(1024, 1)
-step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action) {
+__global__ void __launch_bounds__(128, 8)
+event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SP = 32 * R;
     constexpr bool kAlias = (POLICY == MLB_POLICY_ALIAS);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int A = d.A, Sa = d.Sa, S = d.S;
-    const int nwarps = blockDim.x >> 5;
-    const int epb = nwarps / A;
-    const int env_in_blk = warp / A;
-    const int agent = warp - env_in_blk * A;
-    const int e = blockIdx.x * epb + env_in_blk;
-    if (e >= d.E) return;  // whole env (all its warps) leaves together
+    const int ea = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ea >= d.E * A) return;
+    const int e = ea / A;
+    const int agent = ea - e * A;
 
-    // ---- shared memory: [per warp: fields | scratch | alias] ... [per env: reward staging]
-    const size_t wbytes = warp_smem_bytes(SP, kAlias);
+    const size_t wbytes = event_warp_smem_bytes(SP, kAlias);
     unsigned char* wbase = smem_raw + (size_t)warp * wbytes;
     uint32_t* sm = reinterpret_cast<uint32_t*>(wbase);
     float* smf = reinterpret_cast<float*>(wbase);
-    float* scr = reinterpret_cast<float*>(wbase + (size_t)NF * SP * 4);
-    const WarpScratch scratch{reinterpret_cast<float2*>(scr)};
-    double* a_prob = reinterpret_cast<double*>(wbase + (size_t)NF * SP * 4 + MLB_SCRATCH_BYTES);
-    int32_t* a_alias = reinterpret_cast<int32_t*>(a_prob + SP);
-    float* rv = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * wbytes) + (size_t)env_in_blk * 2 * S;
-    uint32_t* ra = reinterpret_cast<uint32_t*>(rv + S);
+    double* a_prob = reinterpret_cast<double*>(wbase + (size_t)NF * SP * 4);
+    int32_t* a_alias = reinterpret_cast<int32_t*>(a_prob + SP);   // [SP] alias + [2*SP] builder stack
+    float* a_w = reinterpret_cast<float*>(a_alias + 3 * SP);      // [SP] weights
 
     const int step = d.step[e] + 1;                       // env.py:230
     const float t1 = __fmul_rn((float)step, d.dt);        // window end
@@ -272,10 +282,8 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
     WarpGlobals g;
     g.res_val = d.res_val + sbase * 2 * d.KP;
     g.res_ts = d.res_ts + sbase * 2 * d.KP;
-    g.res_rank = d.res_rank + sbase * 2 * d.KP;
     g.ring_arr = d.ring_arr + sbase * d.Q;
     g.ring_fin = d.ring_fin + sbase * d.Q;
-    g.obs = d.obs + sbase * MLB_OBS_COLS;
     g.mt = d.mt_table + (size_t)seed0 * d.L;
     const int Q = d.Q;
 
@@ -311,35 +319,29 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
             }
             sm[F_ACT * SP + j] = act;
             if (!kAlias) sc[r] = server_score<POLICY>(d, n, act);
-            uint32_t nold = 0;
 #pragma unroll
             for (int m = 0; m < 2; m++) {
                 const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
                 const uint32_t cnt = d.res_count[c];
                 sm[(F_CNT0 + m) * SP + j] = cnt;
                 sm[(F_CUR0 + m) * SP + j] = d.res_cursor[c];
-                nold |= (cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K) << (8 * m);
+                sm[(F_CHG0 + m) * SP + j] = (cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K) << 24;
             }
-            sm[F_NOLD * SP + j] = nold;
-            sm[F_FLAGS * SP + j] = 0;
-            sm[F_CHG * SP + j] = 0;
-            sm[(F_CHG + 1) * SP + j] = 0;
         }
     }
     __syncwarp();
     if (kAlias) {
-        // weights as floats for the alias builder, staged in the scratch area
+        // weights as floats for the alias builder
         for (int j = lane; j < Sa; j += 32) {
             const uint32_t act = sm[F_ACT * SP + j];
-            scr[j] = d.action_kind == MLB_ACTION_CONTINUOUS_F32 ? __uint_as_float(act) : d.dw[act];
+            a_w[j] = d.action_kind == MLB_ACTION_CONTINUOUS_F32 ? __uint_as_float(act) : d.dw[act];
         }
         __syncwarp();
-        if (lane == 0) alias_build(a_prob, a_alias, a_alias + SP, scr, Sa);
+        if (lane == 0) alias_build(a_prob, a_alias, a_alias + SP, a_w, Sa);
         __syncwarp();
     }
 
     // ---------------- phase A: events of this window, in time order ----------
-    const int ea = e * A + agent;
     const int64_t aoff = d.arr_off[ea];
     const int an = d.arr_n[ea];
     int cur = d.arr_cur[ea];
@@ -436,6 +438,7 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
     if (lane == 0) d.arr_cur[ea] = cur;
 
     // ---------------- phase C: flow_duration samples, state write-back -------
+    float* obs = d.obs + sbase * MLB_OBS_COLS;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int j = lane + 32 * r;
@@ -446,7 +449,7 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
             d.n_on[gi] = n;
             d.last_fin[gi] = smf[F_LASTFIN * SP + j];
             d.head[gi] = pos;
-            g.obs[j * MLB_OBS_COLS] = (float)n;                             // features.py:274
+            obs[j * MLB_OBS_COLS] = (float)n;                               // features.py:274
             for (int q = 0; q < n; q++) {  // lbhash.h:131-135, one sample per active flow per step
                 const float arr = g.ring_arr[j * Q + pos];
                 res_add<SP>(d, sm, g, 1, j, __fsub_rn(t1, arr), t1);
@@ -457,73 +460,154 @@ step_kernel(const __grid_constant__ DevState d, const void* __restrict__ action)
                 const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
                 d.res_count[c] = sm[(F_CNT0 + m) * SP + j];
                 d.res_cursor[c] = sm[(F_CUR0 + m) * SP + j];
+                d.res_chg[c] = sm[(F_CHG0 + m) * SP + j];
             }
         }
     }
-    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// feature_kernel: block = epb envs x A agent warps (the reward needs all agents of an env).
+template <int R>
+__global__ void __launch_bounds__(1024, 1)
+feature_kernel(const __grid_constant__ DevState d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SP = 32 * R;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int A = d.A, Sa = d.Sa, S = d.S;
+    const int nwarps = blockDim.x >> 5;
+    const int epb = nwarps / A;
+    const int env_in_blk = warp / A;
+    const int agent = warp - env_in_blk * A;
+    const int e = blockIdx.x * epb + env_in_blk;
+    if (e >= d.E) return;  // whole env (all its warps) leaves together
+
+    // ---- shared memory: [per warp: dirty list | scratch | stage] ... [per env: reward staging]
+    const size_t wbytes = feature_warp_smem_bytes(SP);
+    unsigned char* wbase = smem_raw + (size_t)warp * wbytes;
+    uint2* dlist = reinterpret_cast<uint2*>(wbase);
+    const WarpScratch scratch{reinterpret_cast<float2*>(wbase + (size_t)2 * SP * 8)};
+    unsigned char* stage = wbase + (size_t)2 * SP * 8 + MLB_SCRATCH_BYTES;
+    float* rv = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * wbytes) + (size_t)env_in_blk * 2 * S;
+    uint32_t* ra = reinterpret_cast<uint32_t*>(rv + S);
+
+    const int step = d.step[e] + 1;                       // env.py:230
+    const float t1 = __fmul_rn((float)step, d.dt);        // window end
+    const size_t sbase = (size_t)e * S + (size_t)agent * Sa;
+    const int seed0 = agent * Sa;
+    float* const res_val = d.res_val + sbase * 2 * d.KP;
+    float* const res_ts = d.res_ts + sbase * 2 * d.KP;
+    uint8_t* const res_rank = d.res_rank + sbase * 2 * d.KP;
+    float* const obs = d.obs + sbase * MLB_OBS_COLS;
 
     // ---------------- phase B: statistics of touched reservoirs --------------
-    // Compact the dirty (server, metric) pairs into a list first: the loop body is then a
-    // plain counted loop and the next reservoir can be prefetched into L2 while this one is
-    // being evaluated.
+    // The dirty (server, metric) pairs are first compacted into a list, every lane describing
+    // its own servers: entry = { changed-slot word, id | n << 9 | incremental << 17 }.
+    // The loop over that list is then a plain counted loop in which the NEXT reservoir
+    // (values, timestamps, ranks: 1152 B) is copied into the warp's staging buffer with
+    // cp.async while the current one is evaluated from registers.
     const bool all = d.feature_cache == 0;  // mode 0: recompute every reservoir
-    uint16_t* dlist = reinterpret_cast<uint16_t*>(sm + F_LIST * SP);
+    const int KP = d.KP;
+    const bool staged = KP == 128 && d.feature_cache == 1;
     int nd = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int j = lane + 32 * r;
-        const uint32_t fl = j < Sa ? (all ? 3u : sm[F_FLAGS * SP + j]) : 0u;
 #pragma unroll
         for (int m = 0; m < 2; m++) {
-            const bool dirty = (fl >> m) & 1u;
+            uint32_t chg = 0, cnt = 0;
+            if (j < Sa) {
+                const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
+                chg = __ldcs(d.res_chg + c);
+                cnt = __ldcs(d.res_count + c);
+            }
+            const uint32_t nchg = chg_count(chg);
+            const bool dirty = j < Sa && (all || nchg > 0);
             const unsigned bal = __ballot_sync(MLB_FULL, dirty);
-            if (dirty) dlist[nd + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(j * 2 + m);
+            if (dirty) {
+                const uint32_t n = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
+                const bool inc = staged && chg_nold(chg) > 0 && n > 64 && nchg >= 1 && nchg <= 3;
+                dlist[nd + __popc(bal & ((1u << lane) - 1u))] =
+                    make_uint2(chg, (uint32_t)(j * 2 + m) | (n << 9) | ((inc ? 1u : 0u) << 17));
+            }
             nd += __popc(bal);
         }
     }
     __syncwarp();
-    const int KP = d.KP;
-    if (nd > 0) {
-        const int rid0 = (int)dlist[0] * KP;
-        if (lane * 4 < KP) {
-            prefetch_l2(g.res_val + rid0 + lane * 4);
-            prefetch_l2(g.res_ts + rid0 + lane * 4);
-        }
-        if (lane == 0) prefetch_l2(g.res_rank + rid0);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const float* stage_f = reinterpret_cast<const float*>(stage);
+    const char* lane_val = reinterpret_cast<const char*>(res_val + lane * 4);
+    const char* lane_ts = reinterpret_cast<const char*>(res_ts + lane * 4);
+    uint8_t* lane_rank = res_rank + lane * 4;
+    float* lane_obs = obs + 1 + lane;
+    if (staged && nd > 0) {
+        const uint32_t id0 = dlist[0].y & 511u;
+        cp_async16(stage_s + lane * 16, lane_val + (size_t)(id0 * 512u));
+        cp_async16(stage_s + 512 + lane * 16, lane_ts + (size_t)(id0 * 512u));
+        cp_async4(stage_s + 1024 + lane * 4, lane_rank + (size_t)(id0 * 128u));
+        cp_async_commit();
     }
+    int ncold = 0;
 #pragma unroll 1
     for (int i = 0; i < nd; i++) {
-        const int id = dlist[i];
-        if (i + 1 < nd) {
-            const int ridn = (int)dlist[i + 1] * KP;
-            if (lane * 4 < KP) {
-                prefetch_l2(g.res_val + ridn + lane * 4);
-                prefetch_l2(g.res_ts + ridn + lane * 4);
+        const uint2 ent = dlist[i];
+        const uint32_t id = ent.y & 511u;
+        const int n = (int)((ent.y >> 9) & 255u);
+        const bool inc = (ent.y >> 17) & 1u;
+        float v[4], t[4];
+        int rk[4];
+        if (staged) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (inc) {
+                const float4 qv = *reinterpret_cast<const float4*>(stage_f + lane * 4);
+                const float4 qt = *reinterpret_cast<const float4*>(stage_f + 128 + lane * 4);
+                const uint32_t qr = reinterpret_cast<const uint32_t*>(stage_f + 256)[lane];
+                v[0] = qv.x; v[1] = qv.y; v[2] = qv.z; v[3] = qv.w;
+                t[0] = qt.x; t[1] = qt.y; t[2] = qt.z; t[3] = qt.w;
+                rk[0] = qr & 255; rk[1] = (qr >> 8) & 255; rk[2] = (qr >> 16) & 255; rk[3] = qr >> 24;
             }
-            if (lane == 0) prefetch_l2(g.res_rank + ridn);
+            __syncwarp();
+            if (i + 1 < nd) {
+                const uint32_t idn = dlist[i + 1].y & 511u;
+                cp_async16(stage_s + lane * 16, lane_val + (size_t)(idn * 512u));
+                cp_async16(stage_s + 512 + lane * 16, lane_ts + (size_t)(idn * 512u));
+                cp_async4(stage_s + 1024 + lane * 4, lane_rank + (size_t)(idn * 128u));
+                cp_async_commit();
+            }
         }
-        const int jj = id >> 1, m = id & 1;
-        const uint32_t cnt = sm[(F_CNT0 + m) * SP + jj];
-        const int n = cnt < (uint32_t)d.K ? (int)cnt : d.K;
-        const int n_old = (int)((sm[F_NOLD * SP + jj] >> (8 * m)) & 255u);
-        const uint32_t chg = sm[(F_CHG + m) * SP + jj];
-        const int nchg = (int)(chg >> 24);
-        const int rid = id * KP;
+        // anything that is not "a few replaced slots, trusted float32 decision" is deferred to the
+        // cold loop below (entries are re-packed at the front of the list), so this loop has no calls
+        bool ok = false;
         float mine;
-        if (n_old > 0 && n > 64 && nchg <= 3 && nchg > 0 && d.feature_cache == 1)
-            mine = warp_features_incremental(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, n_old, chg, nchg,
-                                             t1, d.decay, d.log2_decay, scratch);
-        else
-            mine = warp_features_sorted(g.res_val + rid, g.res_ts + rid, g.res_rank + rid, n, t1, d.decay,
-                                        d.log2_decay, scratch.vw);
-        if (lane < 5) g.obs[jj * MLB_OBS_COLS + 1 + 5 * m + lane] = mine;
+        if (inc)
+            ok = warp_features_incremental(v, t, rk, lane_rank + (size_t)(id * 128u), n, (int)chg_nold(ent.x), ent.x,
+                                           (int)chg_count(ent.x), t1, d.decay, d.log2_decay, scratch, mine);
+        if (ok) {
+            if (lane < 5) lane_obs[(id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u] = mine;
+        } else {
+            if (lane == 0) dlist[ncold] = ent;
+            ncold++;
+        }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < ncold; i++) {
+        const uint2 ent = dlist[i];
+        const uint32_t id = ent.y & 511u;
+        const int n = (int)((ent.y >> 9) & 255u);
+        const int rid = (int)id * KP;
+        const float mine = warp_features_sorted(res_val + rid, res_ts + rid, res_rank + rid, n, t1, d.decay,
+                                                d.log2_decay, scratch.vw);
+        if (lane < 5) lane_obs[(id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u] = mine;
     }
     __syncwarp();
 
     // ---------------- phase R: reward over the env's active servers ----------
 #pragma unroll 1
     for (int j = lane; j < Sa; j += 32) {
-        const float* row = g.obs + j * MLB_OBS_COLS;
+        const float* row = obs + j * MLB_OBS_COLS;
         bool active = false;  // env.py:410-413
         float x = 0.f;
 #pragma unroll
