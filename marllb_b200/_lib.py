@@ -62,8 +62,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or (os.environ.get("MARLLB_B200_REBUILD") == "1"):
+    path = os.environ.get("MARLLB_B200_LIB") or _build.LIB_PATH   # override: A/B builds of the same library
+    if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("MARLLB_B200_REBUILD") == "1"):
         path = _build.build()
     L = C.CDLL(path)
     vp, i32, i64, u64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double

@@ -225,7 +225,7 @@ static int launch_cfg(mlb_env* h) {
     if (h->ft_smem > 227 * 1024 || h->ev_smem > 227 * 1024)
         return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)",
                     h->ft_smem > h->ev_smem ? h->ft_smem : h->ev_smem);
-    cudaError_t e = set_smem(event_fn(c.policy, c.servers_per_agent), h->ev_smem, h->ev_threads, 32);
+    cudaError_t e = set_smem(event_fn(c.policy, c.servers_per_agent), h->ev_smem, h->ev_threads, 4 * MLB_EV_MINBLOCKS);
     if (e == cudaSuccess) e = set_smem(feature_fn(c.servers_per_agent), h->ft_smem, h->ft_threads, 32);
     if (e != cudaSuccess) return fail(h, MLB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return MLB_OK;
@@ -339,8 +339,7 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     CKC(dalloc(h, &d.res_cursor, ES * 2));
     CKC(dalloc(h, &d.res_rank, ES * 2 * d.KP));
     CKC(dalloc(h, &d.res_chg, ES * 2));
-    CKC(dalloc(h, &d.ring_arr, ES * d.Q));
-    CKC(dalloc(h, &d.ring_fin, ES * d.Q));
+    CKC(dalloc(h, &d.ring, ES * d.Q));
     CKC(dalloc(h, &d.obs, ES * MLB_OBS_COLS));
     CKC(dalloc(h, &d.reward, (size_t)d.E));
     CKC(dalloc(h, &d.done, (size_t)d.E));

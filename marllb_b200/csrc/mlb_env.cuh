@@ -33,8 +33,7 @@ struct DevState {
     uint8_t* res_rank;     // [E][S][2][KP] rank of each slot's value (order statistics cache)
     uint32_t* res_chg;     // [E][2][S] slots written this step (event kernel -> feature kernel)
     // ---- FIFO rings [E][S][Q]
-    float* ring_arr;
-    float* ring_fin;
+    float2* ring;          // (arrival time, finish time) of every in-system flow
     // ---- outputs
     float* obs;            // [E][S][11]
     double* reward;        // [E]

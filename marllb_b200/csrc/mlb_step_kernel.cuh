@@ -42,6 +42,7 @@ enum : int {
     F_CNT0, F_CNT1,  // reservoir counts   (fct, flow_duration)
     F_CUR0, F_CUR1,  // MT19937 replay cursors
     F_CHG0, F_CHG1,  // changed-slot word of each reservoir (see chg_* below)
+    F_SPEED,     // processing speed
     NF
 };
 
@@ -110,8 +111,7 @@ __device__ __forceinline__ int res_draw_slot(uint32_t cnt, uint32_t& cur, const 
 struct WarpGlobals {
     float* res_val;     // this agent's reservoirs [Sa][2][KP]
     float* res_ts;
-    float* ring_arr;    // [Sa][Q]
-    float* ring_fin;
+    float2* ring;       // [Sa][Q] (arrival, finish)
     const uint32_t* mt; // replay rows of this agent's servers [Sa][L]
 };
 
@@ -253,8 +253,11 @@ __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint
 
 // ---------------------------------------------------------------------------
 // event_kernel: R = servers per lane (Sa <= 32*R), SP = 32*R.  Warps are independent.
+#ifndef MLB_EV_MINBLOCKS
+#define MLB_EV_MINBLOCKS 10
+#endif
 template <int POLICY, int R>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, MLB_EV_MINBLOCKS)
 event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SP = 32 * R;
@@ -282,18 +285,19 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
     WarpGlobals g;
     g.res_val = d.res_val + sbase * 2 * d.KP;
     g.res_ts = d.res_ts + sbase * 2 * d.KP;
-    g.ring_arr = d.ring_arr + sbase * d.Q;
-    g.ring_fin = d.ring_fin + sbase * d.Q;
+    g.ring = d.ring + sbase * d.Q;
     g.mt = d.mt_table + (size_t)seed0 * d.L;
     const int Q = d.Q;
 
     // ---------------- phase 0: load state, action -> weights -----------------
     float hf[R];       // finish time of the oldest in-system flow (INF: idle)
+    float ha[R];       // its arrival time
     uint32_t sc[R];    // assignment score as an order-preserving uint
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int j = lane + 32 * r;
         hf[r] = MLB_INF;
+        ha[r] = 0.f;
         sc[r] = 0xffffffffu;
         if (j < Sa) {
             const size_t gi = sbase + j;
@@ -302,7 +306,13 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
             sm[F_NON * SP + j] = (uint32_t)n;
             smf[F_LASTFIN * SP + j] = d.last_fin[gi];
             sm[F_HEAD * SP + j] = h;
-            if (n > 0) hf[r] = g.ring_fin[j * Q + h];
+            smf[F_SPEED * SP + j] = d.speed[gi];
+            if (n > 0) {
+                const float2 hd = g.ring[j * Q + h];
+                ha[r] = hd.x;
+                hf[r] = hd.y;
+                if (n > 1) prefetch_l2(g.ring + j * Q + (h + 1 == (uint32_t)Q ? 0u : h + 1));
+            }
             uint32_t act;
             if (d.action_kind == MLB_ACTION_CONTINUOUS_F32) {
                 const float x = reinterpret_cast<const float*>(action)[gi];
@@ -351,7 +361,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
         const unsigned bal = __ballot_sync(MLB_FULL, at < t1);
         const int nv = (bal == MLB_FULL) ? 32 : (__ffs(~bal) - 1);
         const bool last = nv < 32;
-        const float awk = lane < nv ? __ldcs(d.arr_work + aoff + idx) : 0.f;
+        const float awk = idx < an ? __ldcs(d.arr_work + aoff + idx) : 0.f;  // issued together with the times
         int abk = 0;
         float au = 0.f;
         if (kAlias && lane < nv) {
@@ -371,15 +381,18 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     const int j = lane + 32 * r;
                     uint32_t h = sm[F_HEAD * SP + j];
                     int n = (int)sm[F_NON * SP + j];
-                    float fin = hf[r];
+                    float fin = hf[r], arr = ha[r];
                     do {
-                        const float arr = g.ring_arr[j * Q + h];
                         h = (h + 1 == (uint32_t)Q) ? 0u : h + 1;
                         n -= 1;                                             // src/vpp/lb/lbhash.h:120
+                        float2 nx = make_float2(0.f, MLB_INF);
+                        if (n > 0) nx = g.ring[j * Q + h];                  // in flight during the add
                         res_add<SP>(d, sm, g, 0, j, __fsub_rn(fin, arr), fin);  // lbhash.h:122-124
-                        fin = n > 0 ? g.ring_fin[j * Q + h] : MLB_INF;
+                        arr = nx.x;
+                        fin = nx.y;
                     } while (fin < a);
                     hf[r] = fin;
+                    ha[r] = arr;
                     sm[F_HEAD * SP + j] = h;
                     sm[F_NON * SP + j] = (uint32_t)n;
                     if (!kAlias) sc[r] = server_score<POLICY>(d, n, sm[F_ACT * SP + j]);
@@ -411,11 +424,10 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     atomicAdd(d.dropped + sbase + k, 1u);                   // [B] drop-and-count
                 } else {
                     const float start = fmaxf(smf[F_LASTFIN * SP + k], a);
-                    const float fin = __fadd_rn(start, __fdiv_rn(wk, __ldg(d.speed + sbase + k)));
+                    const float fin = __fadd_rn(start, __fdiv_rn(wk, smf[F_SPEED * SP + k]));
                     uint32_t pos = sm[F_HEAD * SP + k] + (uint32_t)n;
                     if (pos >= (uint32_t)Q) pos -= (uint32_t)Q;
-                    g.ring_arr[k * Q + pos] = a;
-                    g.ring_fin[k * Q + pos] = fin;
+                    g.ring[k * Q + pos] = make_float2(a, fin);
                     smf[F_LASTFIN * SP + k] = fin;
                     sm[F_NON * SP + k] = (uint32_t)(n + 1);                 // lbhash.h:142,167
                     uint32_t nsc = 0;
@@ -423,7 +435,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         if ((k >> 5) == r) {
-                            if (n == 0) hf[r] = fin;
+                            if (n == 0) { hf[r] = fin; ha[r] = a; }
                             sc[r] = nsc;
                         }
                     }
@@ -450,10 +462,13 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
             d.last_fin[gi] = smf[F_LASTFIN * SP + j];
             d.head[gi] = pos;
             obs[j * MLB_OBS_COLS] = (float)n;                               // features.py:274
+            float arr = ha[r];  // the oldest flow is in registers
             for (int q = 0; q < n; q++) {  // lbhash.h:131-135, one sample per active flow per step
-                const float arr = g.ring_arr[j * Q + pos];
-                res_add<SP>(d, sm, g, 1, j, __fsub_rn(t1, arr), t1);
                 pos = (pos + 1 == (uint32_t)Q) ? 0u : pos + 1;
+                float nx = 0.f;
+                if (q + 1 < n) nx = g.ring[j * Q + pos].x;                  // in flight during the add
+                res_add<SP>(d, sm, g, 1, j, __fsub_rn(t1, arr), t1);
+                arr = nx;
             }
 #pragma unroll
             for (int m = 0; m < 2; m++) {
