@@ -295,6 +295,8 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     if (c.reward_metric < 0 || c.reward_metric >= MLB_REWARD_COUNT_) return fail(nullptr, MLB_EINVAL, "Unsupported metric: %d", c.reward_metric);  // rewards.py:321-323
     if (c.reward_field < 0 || c.reward_field > 10) return fail(nullptr, MLB_EINVAL, "reward_field must be an obs column 0..10");
     if (!(c.dt > 0.f) || !(c.decay > 0.0)) return fail(nullptr, MLB_EINVAL, "dt and decay must be positive");
+    if ((double)c.num_envs * c.num_agents * c.servers_per_agent * 2.0 * (((c.reservoir_k + 31) & ~31) / 4) >= 4294967296.0)
+        return fail(nullptr, MLB_EINVAL, "num_envs * servers * 2 * K/4 must stay below 2^32 (32-bit reservoir offsets)");
 
     mlb_env* h = new (std::nothrow) mlb_env();
     if (!h) return fail(nullptr, MLB_ENOMEM, "host allocation failed");

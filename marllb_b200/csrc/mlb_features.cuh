@@ -237,6 +237,32 @@ __device__ __forceinline__ void rank_replace_one(const float (&v)[EPL], int (&rk
     }
 }
 
+// The same on the four ranks of a lane packed one per byte (full reservoir: every rank < 128),
+// with SWAR arithmetic for the shifts.  Returns the updated packed ranks.  ~45 instructions.
+__device__ __forceinline__ uint32_t rank_replace_one_packed(const float (&v)[4], uint32_t rkp, int c, int lane) {
+    const int sub = c & 3, lc = c >> 2;
+    const float xs = slot_fetch<4>(v, c);
+    const float x = xs + 0.0f;  // -0 -> +0, so that the integer successor below is the next float up
+    const uint32_t r_old = (__shfl_sync(MLB_FULL, rkp, lc) >> (8 * sub)) & 255u;
+    // (v_i, i) < (x, c)  <=>  v_i < x or (v_i == x and i < c)  <=>  v_i < (i < c ? nextup(x) : x)
+    const uint32_t xb = __float_as_uint(x);
+    const float xup = __uint_as_float((xb >> 31) ? xb - 1u : xb + 1u);
+    const int dl = c - lane * 4;  // slots r < dl of this lane lie before c
+    uint32_t bef = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const float xr = r < dl ? xup : x;
+        bef |= v[r] < xr ? (1u << (8 * r)) : 0u;
+    }
+    const uint32_t r_new = (uint32_t)__reduce_add_sync(MLB_FULL, __popc(bef));
+    // ranks above the removed one move down (bytes <= 127, so the borrow never crosses a byte),
+    // ranks at or above the inserted one move up
+    const uint32_t gt = (((rkp | 0x80808080u) - (r_old + 1u) * 0x01010101u) >> 7) & 0x01010101u;
+    rkp = rkp - gt + (bef ^ 0x01010101u);
+    if (lane == lc) rkp = (rkp & ~(255u << (8 * sub))) | (r_new << (8 * sub));
+    return rkp;
+}
+
 // General form (`list` = up to three 7-bit slot ids; slots >= n_old are appended, not
 // replaced; absent slots carry rank -1): first every old rank is taken out, then the new
 // values are inserted one at a time among the elements present so far.  Each sub-step leaves
@@ -534,29 +560,29 @@ static __device__ __noinline__ float warp_features_sorted(const float* __restric
 }
 
 // Steady state of the env step: a reservoir of 65..128 valid slots whose ranks live in global
-// memory next to it and in which Algorithm R wrote `nchg` <= 3 slots (7-bit ids in `list`; slots >= n_old are appends of the fill phase) since those ranks were stored.
-// v, t, rk: this lane's four slots (already loaded); lane_ranks = &ranks[4 * lane].
-// Feature `lane` goes to `mine` in lanes 0..4; returns false if the weighted-percentile
-// decision was not trusted (the caller then re-evaluates the reservoir with warp_features_sorted).
-__device__ __forceinline__ bool warp_features_incremental(const float (&v)[4], const float (&t)[4], int (&rk)[4],
-                                                          uint8_t* __restrict__ lane_ranks, int n, int n_old,
+// memory next to it and in which Algorithm R wrote `nchg` <= 3 slots (7-bit ids in `list`;
+// slots >= n_old are appends of the fill phase) since those ranks were stored.
+// v, t: this lane's four slots; rkp: their stored ranks, one per byte; rank_out = &ranks[4 * lane].
+// Returns false if the weighted-percentile decision was not trusted (the caller then
+// re-evaluates the reservoir with warp_features_sorted); all lanes hold the same f[].
+__device__ __forceinline__ bool warp_features_incremental(const float (&v)[4], const float (&t)[4], uint32_t rkp,
+                                                          uint32_t* __restrict__ rank_out, int n, int n_old,
                                                           uint32_t list, int nchg, float now, double decay,
-                                                          float log2_decay, const WarpScratch& sc, float& mine) {
+                                                          float log2_decay, const WarpScratch& sc, float (&f)[5]) {
     const int lane = lane_id();
-    float f[5];
-    if (n_old == 128 && nchg == 1)
-        rank_replace_one<4>(v, rk, (int)(list & 127u), lane);
-    else
+    int rk[4];
+    if (n_old == 128 && nchg == 1) {
+        rkp = rank_replace_one_packed(v, rkp, (int)(list & 127u), lane);
+    } else {
+        rk[0] = rkp & 255; rk[1] = (rkp >> 8) & 255; rk[2] = (rkp >> 16) & 255; rk[3] = rkp >> 24;
         rank_replace_few<4>(v, rk, list, nchg, n_old, lane);
-    *reinterpret_cast<uint32_t*>(lane_ranks) = (uint32_t)(rk[0] & 255) | ((uint32_t)(rk[1] & 255) << 8) |
-                                               ((uint32_t)(rk[2] & 255) << 16) | ((uint32_t)rk[3] << 24);
-    bool ok;
-    if (n == 128)
-        ok = features_ranked<4, true, true>(v, t, rk, 128, now, decay, log2_decay, sc, f);
-    else
-        ok = features_ranked<4, false, true>(v, t, rk, n, now, decay, log2_decay, sc, f);
-    mine = feature_of_lane(f, lane);
-    return ok;
+        rkp = (uint32_t)(rk[0] & 255) | ((uint32_t)(rk[1] & 255) << 8) | ((uint32_t)(rk[2] & 255) << 16) |
+              ((uint32_t)rk[3] << 24);
+    }
+    *rank_out = rkp;
+    rk[0] = rkp & 255; rk[1] = (rkp >> 8) & 255; rk[2] = (rkp >> 16) & 255; rk[3] = rkp >> 24;
+    if (n == 128) return features_ranked<4, true, true>(v, t, rk, 128, now, decay, log2_decay, sc, f);
+    return features_ranked<4, false, true>(v, t, rk, n, now, decay, log2_decay, sc, f);
 }
 
 }  // namespace mlb

@@ -550,63 +550,67 @@ feature_kernel(const __grid_constant__ DevState d) {
         }
     }
     __syncwarp();
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-    const float* stage_f = reinterpret_cast<const float*>(stage);
-    const char* lane_val = reinterpret_cast<const char*>(res_val + lane * 4);
-    const char* lane_ts = reinterpret_cast<const char*>(res_ts + lane * 4);
-    uint8_t* lane_rank = res_rank + lane * 4;
-    float* lane_obs = obs + 1 + lane;
-    if (staged && nd > 0) {
-        const uint32_t id0 = dlist[0].y & 511u;
-        cp_async16(stage_s + lane * 16, lane_val + (size_t)(id0 * 512u));
-        cp_async16(stage_s + 512 + lane * 16, lane_ts + (size_t)(id0 * 512u));
-        cp_async4(stage_s + 1024 + lane * 4, lane_rank + (size_t)(id0 * 128u));
-        cp_async_commit();
-    }
+    float* const warp_obs = obs + 1;
     int ncold = 0;
+    if (staged) {
+        // 32-bit offsets from the array bases (mlb_create checks that they fit): one number
+        // addresses this lane's four slots of a reservoir in all three arrays
+        //   values / timestamps: float4 index;  ranks: uint32 index
+        const float4* const val4 = reinterpret_cast<const float4*>(d.res_val);
+        const float4* const ts4 = reinterpret_cast<const float4*>(d.res_ts);
+        uint32_t* const rank4 = reinterpret_cast<uint32_t*>(d.res_rank);
+        const uint32_t off0 = (uint32_t)(sbase * 2 * 32) + (uint32_t)lane;
+        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + lane * 16;
+        const float4* stage_v = reinterpret_cast<const float4*>(stage) + lane;
+        if (nd > 0) {
+            const uint32_t off = off0 + (dlist[0].y & 511u) * 32u;
+            cp_async16(stage_s, val4 + off);
+            cp_async16(stage_s + 512, ts4 + off);
+            cp_async4(stage_s + 1024 - lane * 12, rank4 + off);
+            cp_async_commit();
+        }
 #pragma unroll 1
-    for (int i = 0; i < nd; i++) {
-        const uint2 ent = dlist[i];
-        const uint32_t id = ent.y & 511u;
-        const int n = (int)((ent.y >> 9) & 255u);
-        const bool inc = (ent.y >> 17) & 1u;
-        float v[4], t[4];
-        int rk[4];
-        if (staged) {
+        for (int i = 0; i < nd; i++) {
+            const uint2 ent = dlist[i];
             cp_async_wait_all();
             __syncwarp();
-            if (inc) {
-                const float4 qv = *reinterpret_cast<const float4*>(stage_f + lane * 4);
-                const float4 qt = *reinterpret_cast<const float4*>(stage_f + 128 + lane * 4);
-                const uint32_t qr = reinterpret_cast<const uint32_t*>(stage_f + 256)[lane];
-                v[0] = qv.x; v[1] = qv.y; v[2] = qv.z; v[3] = qv.w;
-                t[0] = qt.x; t[1] = qt.y; t[2] = qt.z; t[3] = qt.w;
-                rk[0] = qr & 255; rk[1] = (qr >> 8) & 255; rk[2] = (qr >> 16) & 255; rk[3] = qr >> 24;
-            }
+            const float4 qv = stage_v[0];
+            const float4 qt = stage_v[32];
+            const uint32_t rkp = reinterpret_cast<const uint32_t*>(stage_v - lane + 64)[lane];
             __syncwarp();
             if (i + 1 < nd) {
-                const uint32_t idn = dlist[i + 1].y & 511u;
-                cp_async16(stage_s + lane * 16, lane_val + (size_t)(idn * 512u));
-                cp_async16(stage_s + 512 + lane * 16, lane_ts + (size_t)(idn * 512u));
-                cp_async4(stage_s + 1024 + lane * 4, lane_rank + (size_t)(idn * 128u));
+                const uint32_t off = off0 + (dlist[i + 1].y & 511u) * 32u;
+                cp_async16(stage_s, val4 + off);
+                cp_async16(stage_s + 512, ts4 + off);
+                cp_async4(stage_s + 1024 - lane * 12, rank4 + off);
                 cp_async_commit();
             }
+            // anything that is not "a few replaced slots, trusted float32 decision" is deferred to
+            // the cold loop below (entries re-packed at the front of the list): no calls in here
+            bool ok = false;
+            if ((ent.y >> 17) & 1u) {
+                const uint32_t id = ent.y & 511u;
+                const float v[4] = {qv.x, qv.y, qv.z, qv.w};
+                const float t[4] = {qt.x, qt.y, qt.z, qt.w};
+                float f[5];
+                ok = warp_features_incremental(v, t, rkp, rank4 + (off0 + id * 32u), (int)((ent.y >> 9) & 255u),
+                                               (int)chg_nold(ent.x), ent.x, (int)chg_count(ent.x), t1, d.decay,
+                                               d.log2_decay, scratch, f);
+                if (ok && lane == 0) {
+                    float* o = warp_obs + (id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) o[q] = f[q];
+                }
+            }
+            if (!ok) {
+                if (lane == 0) dlist[ncold] = ent;
+                ncold++;
+            }
         }
-        // anything that is not "a few replaced slots, trusted float32 decision" is deferred to the
-        // cold loop below (entries are re-packed at the front of the list), so this loop has no calls
-        bool ok = false;
-        float mine;
-        if (inc)
-            ok = warp_features_incremental(v, t, rk, lane_rank + (size_t)(id * 128u), n, (int)chg_nold(ent.x), ent.x,
-                                           (int)chg_count(ent.x), t1, d.decay, d.log2_decay, scratch, mine);
-        if (ok) {
-            if (lane < 5) lane_obs[(id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u] = mine;
-        } else {
-            if (lane == 0) dlist[ncold] = ent;
-            ncold++;
-        }
+        __syncwarp();
+    } else {
+        ncold = nd;
     }
-    __syncwarp();
 #pragma unroll 1
     for (int i = 0; i < ncold; i++) {
         const uint2 ent = dlist[i];
@@ -615,7 +619,7 @@ feature_kernel(const __grid_constant__ DevState d) {
         const int rid = (int)id * KP;
         const float mine = warp_features_sorted(res_val + rid, res_ts + rid, res_rank + rid, n, t1, d.decay,
                                                 d.log2_decay, scratch.vw);
-        if (lane < 5) lane_obs[(id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u] = mine;
+        if (lane < 5) warp_obs[(id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u + lane] = mine;
     }
     __syncwarp();
 
