@@ -37,6 +37,12 @@ struct mlb_env {
     size_t ev_smem = 0, ft_smem = 0;   // dynamic shared memory of the event / feature kernel
     int ev_threads = 128;              // event kernel: independent warps
     int epb = 1, ft_threads = 32;      // feature kernel: epb envs x A agent warps per block
+    cudaStream_t copy_stream = nullptr;   // device->host copies of the chunked host-buffer step
+    cudaEvent_t copy_done = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    int host_chunks = 8;
+    std::vector<cudaEvent_t> prof_ev;  // 3 events per profiled step
+    int prof_cap = 0, prof_n = 0;
     size_t state_bytes[MLB_F_COUNT_] = {0};
     void* state_ptr[MLB_F_COUNT_] = {nullptr};
 };
@@ -216,6 +222,7 @@ static int launch_cfg(mlb_env* h) {
     const int A = c.num_agents;
     const int SP = 32 * lanes_r(c.servers_per_agent);
     const bool alias = c.policy == MLB_POLICY_ALIAS;
+    if (getenv("MLB_HOST_CHUNKS")) h->host_chunks = atoi(getenv("MLB_HOST_CHUNKS"));
     h->ev_threads = 128;
     h->ev_smem = (size_t)(h->ev_threads / 32) * event_warp_smem_bytes(SP, alias);
     h->epb = A == 1 ? (getenv("MLB_EPB") ? atoi(getenv("MLB_EPB")) : 4) : (A == 2 ? 2 : 1);
@@ -272,10 +279,47 @@ const char* mlb_last_error(const mlb_env* h) { return h ? h->err.c_str() : g_cre
 
 int64_t mlb_launch_count(const mlb_env* h) { return h ? h->launches : 0; }
 
+int mlb_profile_begin(mlb_env* h, int max_steps) {
+    if (!h || max_steps < 0) return MLB_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    while ((int)h->prof_ev.size() < 3 * max_steps) {
+        cudaEvent_t e;
+        CK(h, cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_cap = max_steps;
+    h->prof_n = 0;
+    return MLB_OK;
+}
+
+int mlb_profile_end(mlb_env* h, double* event_ms, double* feature_ms, int* steps) {
+    if (!h) return MLB_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    double ev = 0.0, ft = 0.0;
+    for (int i = 0; i < h->prof_n; i++) {
+        float a = 0.f, b = 0.f;
+        CK(h, cudaEventSynchronize(h->prof_ev[(size_t)3 * i + 2]));
+        CK(h, cudaEventElapsedTime(&a, h->prof_ev[(size_t)3 * i], h->prof_ev[(size_t)3 * i + 1]));
+        CK(h, cudaEventElapsedTime(&b, h->prof_ev[(size_t)3 * i + 1], h->prof_ev[(size_t)3 * i + 2]));
+        ev += a;
+        ft += b;
+    }
+    if (event_ms) *event_ms = ev;
+    if (feature_ms) *feature_ms = ft;
+    if (steps) *steps = h->prof_n;
+    h->prof_cap = 0;
+    h->prof_n = 0;
+    return MLB_OK;
+}
+
 int mlb_destroy(mlb_env* h) {
     if (!h) return MLB_OK;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
+    if (h->copy_done) cudaEventDestroy(h->copy_done);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return MLB_OK;
 }
@@ -565,6 +609,26 @@ int mlb_reset(mlb_env* h, const uint8_t* env_mask, void* stream) {
     return MLB_OK;
 }
 
+// the two kernels of one env step over envs [e0, e1)
+static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_t st, cudaEvent_t* pe) {
+    DevState dv = h->d;
+    dv.e0 = e0;
+    dv.e1 = e1;
+    const void* act = dact;
+    void* ev_args[] = {&dv, &act};
+    const int wpb = h->ev_threads / 32;
+    const int ev_blocks = (int)(((int64_t)(e1 - e0) * dv.A + wpb - 1) / wpb);
+    if (pe) CK(h, cudaEventRecord(pe[0], st));
+    CK(h, cudaLaunchKernel(event_fn(dv.policy, dv.Sa), dim3(ev_blocks), dim3(h->ev_threads), ev_args, h->ev_smem, st));
+    if (pe) CK(h, cudaEventRecord(pe[1], st));
+    void* ft_args[] = {&dv};
+    const int ft_blocks = (e1 - e0 + h->epb - 1) / h->epb;
+    CK(h, cudaLaunchKernel(feature_fn(dv.Sa), dim3(ft_blocks), dim3(h->ft_threads), ft_args, h->ft_smem, st));
+    if (pe) CK(h, cudaEventRecord(pe[2], st));
+    h->launches += 2;
+    return MLB_OK;
+}
+
 int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, double* out_reward,
              uint8_t* out_done, int out_loc, void* stream) {
     if (!h || !action) return fail(h, MLB_EINVAL, "null argument");
@@ -572,23 +636,56 @@ int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, dou
     CK(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const DevState& d = h->d;
+    const size_t S = (size_t)d.S;
+    const size_t asz = action_elem(d.action_kind);
+
+    // ---- host buffers on both sides and enough envs: pipeline the step in chunks of envs, so
+    // that the device->host copy of chunk c's observations (the bulk of the bytes) overlaps the
+    // kernels of chunk c+1.  Envs are independent, so any split gives the same result.
+    const int n_chunks = h->host_chunks;
+    if (action_loc == MLB_HOST && out_loc == MLB_HOST && out_obs && n_chunks > 1 && d.E >= n_chunks * 1024) {
+        if (!h->copy_stream) {
+            CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            CK(h, cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming));
+        }
+        while ((int)h->chunk_ev.size() < n_chunks) {
+            cudaEvent_t e;
+            CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->chunk_ev.push_back(e);
+        }
+        const int per = ((d.E + n_chunks - 1) / n_chunks + h->epb - 1) / h->epb * h->epb;
+        int c = 0;
+        for (int e0 = 0; e0 < d.E; e0 += per, c++) {
+            const int e1 = e0 + per < d.E ? e0 + per : d.E;
+            const size_t ne = (size_t)(e1 - e0);
+            CK(h, cudaMemcpyAsync((char*)h->d_action + (size_t)e0 * S * asz, (const char*)action + (size_t)e0 * S * asz,
+                                  ne * S * asz, cudaMemcpyHostToDevice, st));
+            const int rc = launch_step(h, h->d_action, e0, e1, st, nullptr);
+            if (rc != MLB_OK) return rc;
+            CK(h, cudaEventRecord(h->chunk_ev[c], st));
+            CK(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[c], 0));
+            CK(h, cudaMemcpyAsync(out_obs + (size_t)e0 * S * MLB_OBS_COLS, d.obs + (size_t)e0 * S * MLB_OBS_COLS,
+                                  ne * S * MLB_OBS_COLS * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        CK(h, cudaGetLastError());
+        if (out_reward) CK(h, cudaMemcpyAsync(out_reward, d.reward, (size_t)d.E * 8, cudaMemcpyDeviceToHost, st));
+        if (out_done) CK(h, cudaMemcpyAsync(out_done, d.done, (size_t)d.E, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaEventRecord(h->copy_done, h->copy_stream));
+        CK(h, cudaStreamWaitEvent(st, h->copy_done, 0));  // the caller's stream covers the copies too
+        return MLB_OK;
+    }
+
     const void* dact = action;
     if (action_loc == MLB_HOST) {
         CK(h, cudaMemcpyAsync(h->d_action, action, h->action_bytes, cudaMemcpyHostToDevice, st));
         dact = h->d_action;
     }
+    const bool prof = h->prof_n < h->prof_cap;
     {
-        DevState dv = d;
-        const void* act = dact;
-        void* ev_args[] = {&dv, &act};
-        const int wpb = h->ev_threads / 32;
-        const int ev_blocks = (int)(((int64_t)d.E * d.A + wpb - 1) / wpb);
-        CK(h, cudaLaunchKernel(event_fn(d.policy, d.Sa), dim3(ev_blocks), dim3(h->ev_threads), ev_args, h->ev_smem, st));
-        void* ft_args[] = {&dv};
-        const int ft_blocks = (d.E + h->epb - 1) / h->epb;
-        CK(h, cudaLaunchKernel(feature_fn(d.Sa), dim3(ft_blocks), dim3(h->ft_threads), ft_args, h->ft_smem, st));
+        const int rc = launch_step(h, dact, 0, d.E, st, prof ? &h->prof_ev[(size_t)3 * h->prof_n] : nullptr);
+        if (rc != MLB_OK) return rc;
+        if (prof) h->prof_n++;
     }
-    h->launches += 2;
     CK(h, cudaGetLastError());
     const cudaMemcpyKind kind = out_loc == MLB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const size_t ES = (size_t)d.E * d.S;

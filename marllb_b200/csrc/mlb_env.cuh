@@ -10,6 +10,7 @@ enum : int { ST_ERR_RNG = 1, ST_ERR_ACTION = 2 };
 struct DevState {
     // ---- configuration
     int E, A, Sa, S;       // envs, agents/env, servers/agent, S = A*Sa
+    int e0, e1;            // env range [e0, e1) of this launch (host-buffer steps are pipelined in chunks)
     int K, KP, Q;          // reservoir capacity, padded stride (mult. of 32), queue cap
     int policy, action_kind, n_discrete;
     int reward_metric, reward_field, max_steps;

@@ -265,8 +265,8 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int A = d.A, Sa = d.Sa, S = d.S;
-    const int ea = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (ea >= d.E * A) return;
+    const int ea = d.e0 * A + blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ea >= d.e1 * A) return;
     const int e = ea / A;
     const int agent = ea - e * A;
 
@@ -495,8 +495,8 @@ feature_kernel(const __grid_constant__ DevState d) {
     const int epb = nwarps / A;
     const int env_in_blk = warp / A;
     const int agent = warp - env_in_blk * A;
-    const int e = blockIdx.x * epb + env_in_blk;
-    if (e >= d.E) return;  // whole env (all its warps) leaves together
+    const int e = d.e0 + blockIdx.x * epb + env_in_blk;
+    if (e >= d.e1) return;  // whole env (all its warps) leaves together
 
     // ---- shared memory: [per warp: dirty list | scratch | stage] ... [per env: reward staging]
     const size_t wbytes = feature_warp_smem_bytes(SP);

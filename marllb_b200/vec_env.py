@@ -216,17 +216,31 @@ class VecLoadBalanceEnv:
         self._last_action = a  # keep alive until the kernel has consumed it
         return self.obs, self.reward, self.done
 
-    def step_host(self, action: np.ndarray):
-        """End-to-end step with HOST buffers: pinned H2D of the actions, kernel, pinned D2H of
-        obs / reward / done, then a stream synchronise.  Returns numpy views of the pinned buffers."""
+    def pinned_actions(self) -> "torch.Tensor":
+        """A pinned (E, S) host tensor of the action dtype; fill it and pass it to step_host to
+        skip the staging copy."""
+        return torch.empty((self.num_envs, self.total_servers), dtype=self._adtype, pin_memory=True)
+
+    def step_host(self, action):
+        """End-to-end step with HOST buffers: H2D of the actions from pinned memory, the two
+        kernels, pinned D2H of obs / reward / done, then a stream synchronise.  With many envs the
+        library pipelines this in chunks of envs (copy of chunk c overlaps the kernels of chunk
+        c+1).  `action`: numpy array (staged through a pinned buffer) or a pinned torch tensor from
+        pinned_actions() (used in place).  Returns numpy views of the pinned output buffers."""
         E, S = self.num_envs, self.total_servers
-        if self._h_action is None:
-            self._h_action = torch.empty((E, S), dtype=self._adtype, pin_memory=True)
+        if self._h_obs is None:
             self._h_obs = torch.empty((E, S, 11), dtype=torch.float32, pin_memory=True)
             self._h_reward = torch.empty((E,), dtype=torch.float64, pin_memory=True)
             self._h_done = torch.empty((E,), dtype=torch.uint8, pin_memory=True)
-        self._h_action.numpy()[...] = np.asarray(action).reshape(E, S)
-        check(self._L.mlb_step(self._h, _dptr(self._h_action), _lib.HOST, _dptr(self._h_obs),
+        if isinstance(action, torch.Tensor) and action.is_pinned() and action.dtype == self._adtype \
+                and action.is_contiguous() and action.numel() == E * S:
+            src = action
+        else:
+            if self._h_action is None:
+                self._h_action = self.pinned_actions()
+            self._h_action.numpy()[...] = np.asarray(action).reshape(E, S)
+            src = self._h_action
+        check(self._L.mlb_step(self._h, _dptr(src), _lib.HOST, _dptr(self._h_obs),
                                _dptr(self._h_reward), _dptr(self._h_done), _lib.HOST, self._stream()), self._h)
         torch.cuda.current_stream().synchronize()
         return self._h_obs.numpy(), self._h_reward.numpy(), self._h_done.numpy()
@@ -244,6 +258,16 @@ class VecLoadBalanceEnv:
     @property
     def launch_count(self) -> int:
         return int(self._L.mlb_launch_count(self._h))
+
+    def profile_begin(self, max_steps: int):
+        """Record CUDA events around the two kernels of the next `max_steps` step() calls."""
+        check(self._L.mlb_profile_begin(self._h, int(max_steps)), self._h)
+
+    def profile_end(self):
+        """-> (event_kernel_ms, feature_kernel_ms, steps) summed over the profiled steps."""
+        ev, ft, n = C.c_double(), C.c_double(), C.c_int32()
+        check(self._L.mlb_profile_end(self._h, C.byref(ev), C.byref(ft), C.byref(n)), self._h)
+        return ev.value, ft.value, n.value
 
     # ------------------------------------------------------------ state dumps
     def get_state(self, field: str) -> np.ndarray:
