@@ -23,6 +23,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ["NCCL_DEBUG"] = os.environ.get("MLB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {

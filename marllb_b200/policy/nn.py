@@ -31,6 +31,9 @@ class Params:
         return t
 
     def zero_grad(self):
+        if getattr(self, "_flat_g", None) is not None:   # sole owner of a FlatBucket: one launch
+            self._flat_g.zero_()
+            return
         for g in self.g.values():
             g.zero_()
 
@@ -51,19 +54,87 @@ class Params:
         return list(self.g.values())
 
 
-class Adam:
-    """torch.optim.Adam (default betas / eps, no weight decay) over a list of (param, grad)."""
+class FlatBucket:
+    """All parameters of ONE optimiser in one flat float32 buffer and all their gradients in
+    another ("one flattened gradient bucket per optimiser step").
 
-    def __init__(self, params, grads, lr):
-        self.params, self.grads, self.lr = params, grads, lr
-        self.m = [torch.zeros_like(p) for p in params]
-        self.v = [torch.zeros_like(p) for p in params]
+    The tensors of the given `Params` sets are re-bound to views of the flat buffers (16-byte
+    aligned, padding stays zero), so that per step the optimiser is ONE Adam launch, gradient
+    clipping ONE norm + ONE scale launch, and the data-parallel reduction ONE all-reduce.
+    """
+
+    def __init__(self, param_sets, extra=()):
+        """param_sets: list of Params; extra: list of (param, grad) tensor pairs (e.g. log_alpha)."""
+        items = []
+        for P in param_sets:
+            for name in P.p:
+                items.append((P, name, P.p[name], P.g[name]))
+        for pt, gt in extra:
+            items.append((None, None, pt, gt))
+        dev = items[0][2].device
+        offs, total = [], 0
+        for _, _, t, _ in items:
+            offs.append(total)
+            total += (t.numel() + 3) // 4 * 4
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params, self.grads, self._slices = [], [], []
+        for (P, name, t, g), o in zip(items, offs):
+            pv = self.flat_p[o:o + t.numel()].view(t.shape)
+            gv = self.flat_g[o:o + t.numel()].view(t.shape)
+            pv.copy_(t)
+            gv.copy_(g)
+            if P is not None:
+                P.p[name], P.g[name] = pv, gv
+            self.params.append(pv)
+            self.grads.append(gv)
+            self._slices.append((o, t.numel(), tuple(t.shape)))
+        if len(param_sets) == 1 and not extra:
+            param_sets[0]._flat_g = self.flat_g
+
+    def views(self, flat):
+        return [flat[o:o + n].view(shape) for o, n, shape in self._slices]
+
+
+def allreduce_mean_(flat_g, group=None):
+    """Data-parallel gradient reduction over one flat bucket: NCCL (or gloo) all-reduce SUM, then
+    divide by the world size so the loss keeps its mean-over-the-global-batch meaning
+    (F.mse_loss / .mean(), sac_agent.py:197-198,216).  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat_g
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat_g
+    dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=group)
+    if flat_g.is_cuda:
+        ops.axpby(0.0, flat_g, 1.0 / world, flat_g)
+    else:
+        flat_g.mul_(1.0 / world)
+    return flat_g
+
+
+class Adam:
+    """torch.optim.Adam (default betas / eps, no weight decay) over one FlatBucket."""
+
+    def __init__(self, bucket: FlatBucket, lr, data_parallel=True, max_grad_norm=None):
+        self.bucket, self.lr = bucket, lr
+        self.params, self.grads = bucket.params, bucket.grads
+        self._m = torch.zeros_like(bucket.flat_p)
+        self._v = torch.zeros_like(bucket.flat_p)
+        self.m, self.v = bucket.views(self._m), bucket.views(self._v)   # per-tensor views (checkpoints)
         self.t = 0
+        self.data_parallel, self.max_grad_norm = data_parallel, max_grad_norm
 
     def step(self):
+        """[all-reduce] -> [clip by the GLOBAL norm] -> Adam, each over the whole bucket."""
+        b = self.bucket
+        if self.data_parallel:
+            allreduce_mean_(b.flat_g)
+        if self.max_grad_norm is not None:
+            ops.clip_grad_norm_([b.flat_g], self.max_grad_norm)
         self.t += 1
-        for p, g, m, v in zip(self.params, self.grads, self.m, self.v):
-            ops.adam_step(p, g, m, v, self.lr, self.t)
+        ops.adam_step(b.flat_p, b.flat_g, self._m, self._v, self.lr, self.t)
 
     def state_dict(self):
         return {"step": self.t, "exp_avg": [m.clone() for m in self.m], "exp_avg_sq": [v.clone() for v in self.v],

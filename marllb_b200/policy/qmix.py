@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .nn import Adam, GRUCellSeq, Params, linear_backward
+from .nn import Adam, FlatBucket, GRUCellSeq, Params, linear_backward
 
 
 def _device(device):
@@ -305,12 +305,11 @@ class QMIXAgent:
             self.mixer = QMixingNetwork(num_agents, state_dim, mixing_embed_dim, hypernet_embed_dim, self.device)
             self.mixer_target = QMixingNetwork(num_agents, state_dim, mixing_embed_dim, hypernet_embed_dim, self.device)
             self.mixer_target.load_state_dict(self.mixer.state_dict())
-        params, grads = [], []
-        for net in self.agent_networks + [self.mixer]:                                 # one optimiser, :108-113
-            params += net.P.tensors()
-            grads += net.P.grads()
-        self._params, self._grads = params, grads
-        self.optimizer = Adam(params, grads, lr)
+        # one optimiser over all agent nets + mixer (:108-113) = one flat bucket; gradient clipping
+        # (:284) uses the global norm AFTER the data-parallel all-reduce
+        self._bucket = FlatBucket([net.P for net in self.agent_networks + [self.mixer]])
+        self._params, self._grads = self._bucket.params, self._bucket.grads
+        self.optimizer = Adam(self._bucket, lr, max_grad_norm=10.0)
         self.episode_buffer = EpisodeBuffer(capacity=buffer_capacity, num_agents=num_agents)
         self.total_updates = 0
         self.training_stats = {'loss': [], 'q_tot': [], 'target_q_tot': []}
@@ -403,8 +402,7 @@ class QMIXAgent:
         rsum = ops.linear(rewards.reshape(B * T, A).contiguous(), ones).reshape(B, T).contiguous()
         targets, dq_tot, stats = ops.qmix_td_loss(q_tot, target_q_tot, rsum, dones, seq_len, self.gamma)
         # backward (:280-285)
-        for net in self.agent_networks + [self.mixer]:
-            net.P.zero_grad()
+        self._bucket.flat_g.zero_()
         dchosen = self.mixer.backward(dq_tot.reshape(B * T)).reshape(B, T, A)
         dq_all = torch.zeros((B, T, A * K) if self.strict_reference else (B, T, A, K), dtype=f32, device=dev)
         if self.strict_reference:
@@ -415,8 +413,7 @@ class QMIXAgent:
         dq_tb = dq_all.permute(2, 1, 0, 3).contiguous()                               # [A,T,B,K]
         for a in range(A):
             self.agent_networks[a].backward_seq(dq_tb[a])
-        ops.clip_grad_norm_(self._grads, 10.0)                                        # :284
-        self.optimizer.step()
+        self.optimizer.step()                                                         # all-reduce, clip 10 (:284), Adam
         self.total_updates += 1
         if self.total_updates % self.target_update_interval == 0:                     # :288-294
             for i in range(A):

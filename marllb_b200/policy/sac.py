@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .nn import Adam, GRUCellSeq, Params, linear_backward
+from .nn import Adam, FlatBucket, GRUCellSeq, Params, linear_backward
 from .qmix import _device
 
 
@@ -242,15 +242,19 @@ class SAC_GRU_Agent:
         self.q2_target = QNetwork(state_dim, action_dim, hidden_dim, gru_dim, self.device)
         hard_update(self.q1, self.q1_target)
         hard_update(self.q2, self.q2_target)
-        self.policy_optimizer = Adam(self.policy.P.tensors(), self.policy.P.grads(), lr_policy)
-        self.q1_optimizer = Adam(self.q1.P.tensors(), self.q1.P.grads(), lr_q)
-        self.q2_optimizer = Adam(self.q2.P.tensors(), self.q2.P.grads(), lr_q)
+        # four optimisers like the reference (sac_agent.py:93-106), each over one flat bucket that is
+        # all-reduced once per step in the reference's step order
+        self.policy_optimizer = Adam(FlatBucket([self.policy.P]), lr_policy)
+        self.q1_optimizer = Adam(FlatBucket([self.q1.P]), lr_q)
+        self.q2_optimizer = Adam(FlatBucket([self.q2.P]), lr_q)
         if auto_entropy_tuning:
             self.target_entropy = -action_dim if target_entropy is None else target_entropy   # sac_agent.py:99-102
             self.log_alpha = torch.zeros(1, dtype=torch.float32, device=self.device)
             self._log_alpha_grad = torch.zeros_like(self.log_alpha)
             self.alpha = ops.exp_scalar(self.log_alpha)
-            self.alpha_optimizer = Adam([self.log_alpha], [self._log_alpha_grad], lr_alpha)
+            ab = FlatBucket([], extra=[(self.log_alpha, self._log_alpha_grad)])
+            self.log_alpha, self._log_alpha_grad = ab.params[0], ab.grads[0]
+            self.alpha_optimizer = Adam(ab, lr_alpha)
         else:
             self.alpha = torch.tensor([alpha], dtype=torch.float32, device=self.device)
             self.target_entropy = None

@@ -64,3 +64,53 @@ def test_shard_range_properties():
         assert seen == total
     with pytest.raises(ValueError):
         shard_range(8, 8, 8)
+
+
+# ---- policy update: one flat gradient bucket per optimiser, all-reduced and divided by the world size
+def _grad_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from marllb_b200.policy.nn import FlatBucket, Params, allreduce_mean_
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    W = torch.randn(6, 10, generator=g)
+    b = torch.randn(6, generator=g)
+    X = torch.randn(8, 10, generator=g)        # the GLOBAL batch; each rank owns half of it
+    Y = torch.randn(8, 6, generator=g)
+    P = Params("cpu")
+    P.add("fc.weight", W)
+    P.add("fc.bias", b)
+    bucket = FlatBucket([P])
+    assert P.p["fc.weight"].data_ptr() == bucket.flat_p.data_ptr()       # tensors are views of the bucket
+    assert bucket.flat_p.numel() == 60 + 8                               # bias padded to a 16-byte multiple
+
+    def grads(x, y):   # mean-squared-error gradient of y_hat = x W^T + b over the rows given
+        d = 2.0 * (x @ W.T + b - y) / y.numel()
+        return d.T @ x, d.sum(0)
+
+    lo, hi = rank * 4, rank * 4 + 4
+    gw, gb = grads(X[lo:hi], Y[lo:hi])
+    P.g["fc.weight"].copy_(gw)
+    P.g["fc.bias"].copy_(gb)
+    allreduce_mean_(bucket.flat_g)
+    gw_all, gb_all = grads(X, Y)
+    ok = torch.allclose(P.g["fc.weight"], gw_all, rtol=1e-5, atol=1e-7) and \
+        torch.allclose(P.g["fc.bias"], gb_all, rtol=1e-5, atol=1e-7) and float(bucket.flat_g[66:].abs().sum()) == 0.0
+    q.put((rank, bool(ok), np.asarray(bucket.flat_g).tobytes()))
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_equals_global_batch_gradient():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][1] and out[1][1]
+    assert out[0][2] == out[1][2]          # both ranks hold bit-identical reduced gradients
