@@ -37,6 +37,17 @@ int mlb_gemm(const float *A, int64_t a_bs, int64_t a_rs, int64_t a_cs,
              float *C, int64_t c_bs, int64_t ldc, const float *bias, int64_t bias_bs,
              int32_t M, int32_t N, int32_t K, int32_t batch, float beta, int32_t act, void *stream);
 
+/*
+ * nn.Linear forward on the tensor cores (tcgen05, 3xTF32 with fp32 accumulation in tensor memory):
+ *   C[m][n] = act( sum_k X[m*lda + k] * W[n*ldw + k] + bias[n] ),  X [M][K], W [N][K] (nn.Linear layout).
+ * lda and ldw must be multiples of 4 and X, W 16-byte aligned (TMA); any M, N, K >= 1.
+ * Same results as mlb_gemm within fp32 rounding (error ~1e-6 relative); used for the large-M
+ * (rollout batch) calls of AgentQNetwork / PolicyNetwork / QNetwork forward.
+ */
+int mlb_linear_tc_supported(int32_t M, int32_t N, int32_t K, int64_t lda, int64_t ldw, int64_t ldc);
+int mlb_linear_tc(const float *X, int64_t lda, const float *W, int64_t ldw, const float *bias,
+                  float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
+
 /* nn.GRU single step, gate part (torch gate order r,z,n):
  *   gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (computed by mlb_gemm), both [M][3H];
  *   r = sigmoid(gi_r+gh_r), z = sigmoid(gi_z+gh_z), n = tanh(gi_n + r*gh_n), h' = (1-z)*n + z*h.

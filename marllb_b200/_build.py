@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmarllb_b200.so")
-SOURCES = ["mlb_api.cu", "mlb_ops.cu", "mlb_policy.cu"]
+SOURCES = ["mlb_api.cu", "mlb_ops.cu", "mlb_policy.cu", "mlb_linear_tc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -26,6 +26,7 @@ def _stale() -> bool:
     t = os.path.getmtime(LIB_PATH)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(os.path.dirname(_HERE), "include", "marllb_b200.h"))
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "marllb_b200_policy.h"))
     return any(os.path.getmtime(p) > t for p in deps)
 
 

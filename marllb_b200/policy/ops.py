@@ -22,6 +22,8 @@ def _L():
         vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
         sig = {
             "mlb_gemm": [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, vp, i64, i32, i32, i32, i32, f32, i32, vp],
+            "mlb_linear_tc_supported": [i32, i32, i32, i64, i64, i64],
+            "mlb_linear_tc": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp],
             "mlb_gru_gates_forward": [vp, vp, vp, vp, vp, i32, i32, vp],
             "mlb_gru_gates_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
             "mlb_relu_backward": [vp, vp, vp, i64, vp],
@@ -52,7 +54,7 @@ def _L():
     return L
 
 
-POLICY_EXPORTS = ["mlb_gemm", "mlb_gru_gates_forward", "mlb_gru_gates_backward", "mlb_relu_backward",
+POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_gru_gates_forward", "mlb_gru_gates_backward", "mlb_relu_backward",
                   "mlb_abs_backward", "mlb_colsum", "mlb_axpby", "mlb_sumsq", "mlb_scale", "mlb_adam",
                   "mlb_egreedy_select", "mlb_row_max", "mlb_mixer_forward", "mlb_mixer_backward",
                   "mlb_tanh_gaussian_forward", "mlb_tanh_gaussian_backward", "mlb_abs_forward",
@@ -73,8 +75,29 @@ def _chk(t):
     return t
 
 
+TC_MIN_M = 512   # below this the tile launch overhead beats the FFMA kernel's
+
+
+def linear_tc(x, W, b=None, act=ACT_NONE, out=None):
+    """y = act(x W^T + b) on the tensor cores (tcgen05, 3xTF32).  x [M,K] with unit inner stride
+    (rows may be strided, e.g. one agent's slice of [E, A, obs]); W [N,K] contiguous."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    _chk(W)
+    M, K = x.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(_L().mlb_linear_tc(_p(x), x.stride(0), _p(W), K, _p(b), _p(out), out.stride(0), M, N, K, act, _st()))
+    return out
+
+
 def linear(x, W, b=None, act=ACT_NONE, out=None):
-    """y = act(x W^T + b).  x [M,K] or [G,M,K]; W [N,K] or [G,N,K]; b [N] / [G,N] (nn.Linear layout)."""
+    """y = act(x W^T + b).  x [M,K] or [G,M,K]; W [N,K] or [G,N,K]; b [N] / [G,N] (nn.Linear layout).
+    Large-M 2-D calls go to the tensor-core kernel, the rest to the FFMA GEMM."""
+    if (x.dim() == 2 and W.dim() == 2 and x.shape[0] >= TC_MIN_M and x.stride(1) == 1 and x.stride(0) % 4 == 0
+            and W.is_contiguous() and x.shape[1] % 4 == 0 and x.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0
+            and (b is None or b.dim() == 1) and (out is None or out.stride(1) == 1)):
+        return linear_tc(x, W, b, act, out)
     _chk(x), _chk(W)
     batched = x.dim() == 3
     G = x.shape[0] if batched else 1
