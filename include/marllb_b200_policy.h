@@ -73,6 +73,10 @@ int mlb_adam(float *p, const float *g, float *m, float *v, int64_t n, float lr, 
  * rnd [M] int32 pre-drawn random actions; action = u < epsilon ? rnd : argmax (first max). */
 int mlb_egreedy_select(const float *q, const float *u, const int32_t *rnd, float epsilon,
                        int32_t *action, float *q_sel, int32_t M, int32_t K, void *stream);
+/* QMIX actions -> per-server env action (rl_controller.py:314-321 puts the weight on the chosen
+ * server of each agent): out[m][j] = (action[m*stride] == j) ? hot : cold, m < M agents, j < Sa. */
+int mlb_onehot_action(const int32_t *action, int32_t M, int32_t Sa, int32_t stride, uint8_t hot,
+                      uint8_t cold, uint8_t *out, void *stream);
 /* row max (target Q: qmix_agent.py:253) and gather q[m][idx[m]] */
 int mlb_row_max(const float *q, float *out, int32_t *argmax, int32_t M, int32_t K, void *stream);
 

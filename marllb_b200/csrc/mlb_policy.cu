@@ -213,6 +213,16 @@ __global__ void egreedy_kernel(const float* __restrict__ q, const float* __restr
     if (q_sel) q_sel[m] = qm[a];
 }
 
+// QMIX action (one server index per agent, rl_controller.py:314-321: weight on the chosen server) ->
+// the env's per-server discrete action: `hot` at the chosen server of each agent, `cold` elsewhere
+__global__ void onehot_action_kernel(const int32_t* __restrict__ action, int M, int Sa, int stride, uint8_t hot, uint8_t cold,
+                                     uint8_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * Sa) return;
+    const int m = (int)(i / Sa), j = (int)(i - (int64_t)m * Sa);
+    out[i] = action[(int64_t)m * stride] == j ? hot : cold;
+}
+
 __global__ void row_max_kernel(const float* __restrict__ q, float* __restrict__ out, int32_t* __restrict__ arg, int M, int K) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
@@ -520,6 +530,14 @@ int mlb_egreedy_select(const float* q, const float* u, const int32_t* rnd, float
     if (!q || !action || (u && !rnd) || K < 1) return MLB_EINVAL;
     if (M == 0) return MLB_OK;
     egreedy_kernel<<<nblk(M, 128), 128, 0, (cudaStream_t)stream>>>(q, u, rnd, epsilon, action, q_sel, M, K);
+    return ok();
+}
+
+int mlb_onehot_action(const int32_t* action, int32_t M, int32_t Sa, int32_t stride, uint8_t hot, uint8_t cold,
+                      uint8_t* out, void* stream) {
+    if (!action || !out || Sa < 1) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    onehot_action_kernel<<<nblk((int64_t)M * Sa, 256), 256, 0, (cudaStream_t)stream>>>(action, M, Sa, stride, hot, cold, out);
     return ok();
 }
 

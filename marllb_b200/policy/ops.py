@@ -35,6 +35,7 @@ def _L():
             "mlb_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp],
             "mlb_egreedy_select": [vp, vp, vp, f32, vp, vp, i32, i32, vp],
             "mlb_row_max": [vp, vp, vp, i32, i32, vp],
+            "mlb_onehot_action": [vp, i32, i32, i32, C.c_uint8, C.c_uint8, vp, vp],
             "mlb_mixer_forward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
             "mlb_mixer_backward": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
             "mlb_tanh_gaussian_forward": [vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, i32, i32, vp],
@@ -56,7 +57,7 @@ def _L():
 
 POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_gru_gates_forward", "mlb_gru_gates_backward", "mlb_relu_backward",
                   "mlb_abs_backward", "mlb_colsum", "mlb_axpby", "mlb_sumsq", "mlb_scale", "mlb_adam",
-                  "mlb_egreedy_select", "mlb_row_max", "mlb_mixer_forward", "mlb_mixer_backward",
+                  "mlb_egreedy_select", "mlb_onehot_action", "mlb_row_max", "mlb_mixer_forward", "mlb_mixer_backward",
                   "mlb_tanh_gaussian_forward", "mlb_tanh_gaussian_backward", "mlb_abs_forward",
                   "mlb_qmix_td_loss", "mlb_sac_q_target", "mlb_mse_loss", "mlb_sac_policy_loss",
                   "mlb_sac_alpha_loss", "mlb_exp_scalar"]
@@ -209,6 +210,16 @@ def egreedy_select(q, epsilon=0.0, u=None, rnd=None):
     qsel = torch.empty(M, dtype=torch.float32, device=q.device)
     check(_L().mlb_egreedy_select(_p(_chk(q)), _p(u), _p(rnd), float(epsilon), _p(act), _p(qsel), M, K, _st()))
     return act, qsel
+
+
+def onehot_action(action, servers_per_agent, hot=2, cold=0, out=None):
+    """QMIX actions [E, A] int32 (one server index per agent) -> env action [E, A*Sa] uint8."""
+    assert action.is_cuda and action.dtype == torch.int32 and action.is_contiguous()
+    M = action.numel()
+    if out is None:
+        out = torch.empty((action.shape[0], action.shape[1] * servers_per_agent), dtype=torch.uint8, device=action.device)
+    check(_L().mlb_onehot_action(_p(action), M, servers_per_agent, 1, hot, cold, _p(out), _st()))
+    return out
 
 
 def row_max(q):

@@ -60,7 +60,9 @@ class AgentQNetwork:
     def forward(self, obs, hidden):
         """obs [B, obs_dim], hidden [1, B, gru] -> (q [B, action_dim], hidden_new [1, B, gru])."""
         P = self.P.p
-        obs = obs.to(self.device, torch.float32).contiguous()
+        obs = obs.to(self.device, torch.float32)
+        if not (obs.dim() == 2 and obs.shape[0] >= ops.TC_MIN_M and obs.stride(1) == 1):
+            obs = obs.contiguous()      # large strided batches (one agent's rows of [E, A, obs]) go to TMA as they are
         h = hidden.to(self.device, torch.float32).reshape(-1, self.gru_dim).contiguous()
         h_new = self.gru.step(obs, h)
         x = ops.linear(h_new, P["fc1.weight"], P["fc1.bias"], ops.ACT_RELU)
@@ -343,7 +345,7 @@ class QMIXAgent:
         E = observations.shape[0]
         acts, hs, qs = [], [], []
         for a in range(self.num_agents):
-            obs = observations[:, a].contiguous()
+            obs = observations[:, a]
             h = self.agent_networks[a].init_hidden(E) if hiddens is None else hiddens[a].unsqueeze(0)
             q, hn = self.agent_networks[a](obs, h)
             ua = u[:, a].contiguous() if u is not None else None
