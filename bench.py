@@ -31,6 +31,9 @@ WORKLOADS = {
     "c5": dict(envs=131072, agents=1, servers=64, rate=128.0, K=128),
     "c2": dict(envs=4096, agents=1, servers=16, rate=32.0, K=128),
     "c3env": dict(envs=16384, agents=2, servers=32, rate=128.0, K=128),
+    # config C3: QMIX action selection for every (env, agent) fused with the env step (marllb_b200/rollout.py);
+    # network sizes as wired by the reference driver (training_pipeline.py:171-185), clean obs layout (Sa*11)
+    "c3": dict(envs=16384, agents=2, servers=32, rate=128.0, K=128, policy="qmix"),
 }
 RHO = 0.8
 DT = 0.25
@@ -190,8 +193,9 @@ def run_reference(args):
 
 
 def workload_config(args, wl):
+    pol = "QMIX epsilon-greedy action selection (eps=0.05) fused with the env step" if wl.get("policy") else "random policy"
     return {"workload": f"{args.workload}: {wl['envs']} envs/GPU x {wl['agents']} LB agent x {wl['servers']} servers, "
-                        f"K={wl['K']}-slot reservoirs, Poisson {wl['rate']:.0f} flows/s/agent, rho={RHO}, random policy, SED",
+                        f"K={wl['K']}-slot reservoirs, Poisson {wl['rate']:.0f} flows/s/agent, rho={RHO}, {pol}, SED",
             "envs_per_gpu": wl["envs"], "agents": wl["agents"], "servers_per_agent": wl["servers"],
             "reservoir_k": wl["K"], "flows_per_s_per_agent": wl["rate"], "dt_s": DT,
             "burnin_steps": args.burnin,
@@ -215,7 +219,7 @@ def run_ours(args):
         wl["envs"] = args.envs
     E, A, S, K = wl["envs"], wl["agents"], wl["servers"], wl["K"]
     e2e_steps = min(args.steps, args.e2e_steps)
-    total_steps = args.burnin + args.warmup + args.steps + 3 + e2e_steps
+    total_steps = args.burnin + args.warmup + args.steps + 20 + e2e_steps
     env = VecLoadBalanceEnv(E, num_servers=S, num_agents=A, reservoir_capacity=K, max_steps=10 ** 9,
                             action_dtype="uint8", env_id_base=rank * E, device=local,
                             feature_cache=not args.no_feature_cache)
@@ -227,17 +231,51 @@ def run_ours(args):
     g = torch.Generator(device="cuda")
     g.manual_seed(99 + rank)
     pool = [torch.randint(0, 3, (E, S * A), generator=g, device="cuda", dtype=torch.uint8) for _ in range(8)]
+    rollout = None
+    if wl.get("policy") == "qmix":
+        from marllb_b200.policy import QMIXAgent, ops as pops
+        from marllb_b200.rollout import QMIXRollout
+        torch.manual_seed(7)   # random-init weights of the reference architecture
+        agent = QMIXAgent(num_agents=A, state_dim=4 * A * S + 10, obs_dim=S * 11, action_dim=S, hidden_dim=64, gru_dim=64,
+                          mixing_embed_dim=32, hypernet_embed_dim=64, device=torch.device("cuda", local))
+        rollout = QMIXRollout(env, agent)
+        upool = [torch.rand((E, A), generator=g, device="cuda") for _ in range(8)]
+        rpool = [torch.randint(0, S, (E, A), generator=g, device="cuda", dtype=torch.int32) for _ in range(8)]
+
+    graphed = False
+
+    def do_step(k):
+        if rollout is None:
+            env.step(pool[k % 8])
+        elif graphed:
+            rollout.graph_u.copy_(upool[k % 8])
+            rollout.graph_rnd.copy_(rpool[k % 8])
+            rollout.step_graph()
+        else:
+            rollout.step(0.05, upool[k % 8], rpool[k % 8])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.burnin + args.warmup):
-        env.step(pool[k % 8])
+    for k in range(args.burnin):
+        do_step(k)
+    prof_eager = None
+    if rollout is not None and not args.no_graph:
+        # per-kernel times of the env kernels from a short eager pass (event records are not captured),
+        # then the whole rollout step as ONE CUDA-graph launch for the timed region
+        env.profile_begin(10)
+        for k in range(10):
+            do_step(k)
+        prof_eager = env.profile_end()
+        rollout.capture(0.05)
+        graphed = True
+    for k in range(args.warmup):
+        do_step(k)
     env.check_status()
     cur0 = env.get_state("arr_cursor").astype(np.int64).sum()
-    l0 = env.launch_count
+    l0 = env.launch_count + (pops.LAUNCHES if rollout is not None else 0)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -246,13 +284,17 @@ def run_ours(args):
     barrier()
     ev0.record()
     for k in range(args.steps):
-        env.step(pool[k % 8])
+        do_step(k)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     ev_ms, ft_ms, prof_steps = env.profile_end()
+    if prof_eager is not None:
+        ev_ms, ft_ms, prof_steps = prof_eager
     clk = clocks.stop() if rank == 0 else None
-    launches = env.launch_count - l0
+    launches = env.launch_count + (pops.LAUNCHES if rollout is not None else 0) - l0
+    if graphed:
+        launches = rollout.graph_launches * args.steps
     flows = env.get_state("arr_cursor").astype(np.int64).sum() - cur0
     env.check_status()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -264,23 +306,52 @@ def run_ours(args):
     value = world * E * A * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the public API with HOST buffers (pinned H2D actions, D2H obs/reward/done)
-    h_act = []
-    for p_ in pool[:2]:
-        t_ = env.pinned_actions()
-        t_.copy_(p_.view_as(t_))
-        h_act.append(t_)
-    torch.cuda.synchronize()
-    env.step_host(h_act[0])  # allocates pinned output buffers, untimed
+    if rollout is None:
+        h_act = []
+        for p_ in pool[:2]:
+            t_ = env.pinned_actions()
+            t_.copy_(p_.view_as(t_))
+            h_act.append(t_)
+        torch.cuda.synchronize()
+        env.step_host(h_act[0])  # allocates pinned output buffers, untimed
+        e2e_step = lambda k: env.step_host(h_act[k % 2])
+        h2d, d2h = env.e2e_bytes
+    else:
+        # what a trainer exchanges with the rollout per step: exploration draws in (pinned H2D),
+        # rewards / dones / chosen actions out (pinned D2H); observations stay on the device
+        h_u = [torch.empty((E, A), dtype=torch.float32, pin_memory=True).copy_(upool[i]) for i in range(2)]
+        h_r = [torch.empty((E, A), dtype=torch.int32, pin_memory=True).copy_(rpool[i]) for i in range(2)]
+        d_u, d_r = torch.empty_like(upool[0]), torch.empty_like(rpool[0])
+        o_rew = torch.empty((E,), dtype=torch.float64, pin_memory=True)
+        o_done = torch.empty((E,), dtype=torch.uint8, pin_memory=True)
+        o_act = torch.empty((E, A), dtype=torch.int32, pin_memory=True)
+
+        def e2e_step(k):
+            if not graphed:
+                d_u.copy_(h_u[k % 2], non_blocking=True)
+                d_r.copy_(h_r[k % 2], non_blocking=True)
+            if graphed:
+                rollout.graph_u.copy_(h_u[k % 2], non_blocking=True)
+                rollout.graph_rnd.copy_(h_r[k % 2], non_blocking=True)
+                _, r_, dn_, a_ = rollout.step_graph()
+            else:
+                _, r_, dn_, a_ = rollout.step(0.05, d_u, d_r)
+            o_rew.copy_(r_, non_blocking=True)
+            o_done.copy_(dn_, non_blocking=True)
+            o_act.copy_(a_, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = E * A * 8, E * 8 + E + E * A * 4
+        torch.cuda.synchronize()
+        e2e_step(0)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        env.step_host(h_act[k % 2])
+        e2e_step(k)
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * A * e2e_steps / float(te.item())
-    h2d, d2h = env.e2e_bytes
 
     if rank == 0:
         F = float(fl.item()) / (world * E * A * args.steps)
@@ -313,12 +384,14 @@ def run_ours(args):
                                             "achieved": b_event * E * A / ev_avg_s / 1e9 if ev_avg_s > 0 else None}],
                          "step": {"algorithmic_bytes_per_agent_step": bytes_as, "achieved": step_achieved,
                                   "frac": step_achieved / peak},
-                         "flows_per_agent_step": F},
+                         "flows_per_agent_step": F,
+                         "policy_ms_per_step": (ms / args.steps - (ev_ms + ft_ms) / max(prof_steps, 1)) if rollout is not None else None,
+                         "cuda_graph": graphed},
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clk,
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and rollout is None:
             del env
             torch.cuda.empty_cache()
             v, steps, cores = cpu_oracle_rate(wl, n_envs=0 or max(4 * (os.cpu_count() or 1), 32),
@@ -344,6 +417,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-feature-cache", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="c3: launch the rollout step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

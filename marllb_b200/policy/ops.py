@@ -67,7 +67,12 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+LAUNCHES = 0   # kernels launched through this module (every op fetches the stream once per launch)
+
+
 def _st():
+    global LAUNCHES
+    LAUNCHES += 1
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -76,7 +81,8 @@ def _chk(t):
     return t
 
 
-TC_MIN_M = 512   # below this the tile launch overhead beats the FFMA kernel's
+import os as _os
+TC_MIN_M = int(_os.environ.get("MLB_TC_MIN_M", "512"))   # below this the tile launch overhead beats the FFMA kernel's
 
 
 def linear_tc(x, W, b=None, act=ACT_NONE, out=None):

@@ -36,6 +36,46 @@ class QMIXRollout:
         self.hidden = None
         return self.env.reset()
 
+    # ---- CUDA graph: the ~17 launches of a rollout step replayed as one graph launch
+    def capture(self, epsilon: float = 0.0, warmup: int = 2):
+        """Capture step(epsilon, u, rnd) into a CUDA graph.  The exploration draws are read from the
+        static buffers `graph_u` [E, A] float32 / `graph_rnd` [E, A] int32 (fill them before each
+        replay; with epsilon == 0 they are unused) and the GRU hidden state lives in a static
+        buffer.  Note: the `warmup` + 1 steps run here advance the envs."""
+        dev = self.env.device
+        self.graph_u = torch.zeros((self.E, self.A), dtype=torch.float32, device=dev)
+        self.graph_rnd = torch.zeros((self.E, self.A), dtype=torch.int32, device=dev)
+        if self.hidden is None:
+            self.hidden = torch.zeros((self.A, self.E, self.agent.agent_networks[0].gru_dim), dtype=torch.float32, device=dev)
+        self._h_static = self.hidden.clone()
+
+        def body():
+            self.hidden = self._h_static
+            out = self.step(epsilon, self.graph_u, self.graph_rnd)
+            self._h_static.copy_(self.hidden)
+            self.hidden = self._h_static
+            return out
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from .policy import ops as _ops
+        n0 = self.env.launch_count + _ops.LAUNCHES
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = body()
+        self.graph_launches = self.env.launch_count + _ops.LAUNCHES - n0 + 1   # + the hidden-state copy
+        return self
+
+    def step_graph(self):
+        """Replay the captured step (inputs: graph_u / graph_rnd).  Returns (obs, reward, done, actions)."""
+        self._graph.replay()
+        return self._graph_out
+
     def step(self, epsilon: float = 0.0, u=None, rnd=None):
         """One rollout step for every env.  u [E, A] uniforms / rnd [E, A] int32 random actions
         pre-drawn by the caller (None = greedy).  Returns (obs, reward, done, actions [E, A])."""
