@@ -34,6 +34,9 @@ WORKLOADS = {
     # config C3: QMIX action selection for every (env, agent) fused with the env step (marllb_b200/rollout.py);
     # network sizes as wired by the reference driver (training_pipeline.py:171-185), clean obs layout (Sa*11)
     "c3": dict(envs=16384, agents=2, servers=32, rate=128.0, K=128, policy="qmix"),
+    # config C4 (per-GPU slice): one SAC-GRU learner over 1024 envs x 256 servers, actor inference + env step +
+    # one SAC update (batch 256, device replay) per step; with N > 1 the gradient buckets are all-reduced over NCCL
+    "c4": dict(envs=1024, agents=1, servers=256, rate=512.0, K=128, policy="sac"),
 }
 RHO = 0.8
 DT = 0.25
@@ -193,7 +196,9 @@ def run_reference(args):
 
 
 def workload_config(args, wl):
-    pol = "QMIX epsilon-greedy action selection (eps=0.05) fused with the env step" if wl.get("policy") else "random policy"
+    pol = {"qmix": "QMIX epsilon-greedy action selection (eps=0.05) fused with the env step",
+           "sac": "SAC-GRU actor sampling + env step + one SAC update (batch 256) per step",
+           None: "random policy"}[wl.get("policy")]
     return {"workload": f"{args.workload}: {wl['envs']} envs/GPU x {wl['agents']} LB agent x {wl['servers']} servers, "
                         f"K={wl['K']}-slot reservoirs, Poisson {wl['rate']:.0f} flows/s/agent, rho={RHO}, {pol}, SED",
             "envs_per_gpu": wl["envs"], "agents": wl["agents"], "servers_per_agent": wl["servers"],
@@ -221,6 +226,7 @@ def run_ours(args):
     e2e_steps = min(args.steps, args.e2e_steps)
     total_steps = args.burnin + args.warmup + args.steps + 20 + e2e_steps
     env = VecLoadBalanceEnv(E, num_servers=S, num_agents=A, reservoir_capacity=K, max_steps=10 ** 9,
+                            action_type="continuous" if wl.get("policy") == "sac" else "discrete",
                             action_dtype="uint8", env_id_base=rank * E, device=local,
                             feature_cache=not args.no_feature_cache)
     speeds = np.where(np.arange(S * A) % 2 == 0, 1.0, 2.0).astype(np.float32)
@@ -242,10 +248,23 @@ def run_ours(args):
         upool = [torch.rand((E, A), generator=g, device="cuda") for _ in range(8)]
         rpool = [torch.randint(0, S, (E, A), generator=g, device="cuda", dtype=torch.int32) for _ in range(8)]
 
+    sac = None
+    if wl.get("policy") == "sac":
+        from marllb_b200.policy import SAC_GRU_Agent, ops as pops
+        from marllb_b200.rollout import SACRollout
+        torch.manual_seed(7)   # same initial weights on every rank
+        sac_agent = SAC_GRU_Agent(state_dim=S * 11, action_dim=S, hidden_dim=256, gru_dim=128, batch_size=256,
+                                  device=torch.device("cuda", local))
+        sac = SACRollout(env, sac_agent)
+        sac_gen = torch.Generator(device="cuda")
+        sac_gen.manual_seed(5 + rank)
     graphed = False
 
     def do_step(k):
-        if rollout is None:
+        if sac is not None:
+            sac.step()
+            sac.update(1, sac_gen)
+        elif rollout is None:
             env.step(pool[k % 8])
         elif graphed:
             rollout.graph_u.copy_(upool[k % 8])
@@ -275,7 +294,7 @@ def run_ours(args):
         do_step(k)
     env.check_status()
     cur0 = env.get_state("arr_cursor").astype(np.int64).sum()
-    l0 = env.launch_count + (pops.LAUNCHES if rollout is not None else 0)
+    l0 = env.launch_count + (pops.LAUNCHES if (rollout is not None or sac is not None) else 0)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -292,7 +311,7 @@ def run_ours(args):
     if prof_eager is not None:
         ev_ms, ft_ms, prof_steps = prof_eager
     clk = clocks.stop() if rank == 0 else None
-    launches = env.launch_count + (pops.LAUNCHES if rollout is not None else 0) - l0
+    launches = env.launch_count + (pops.LAUNCHES if (rollout is not None or sac is not None) else 0) - l0
     if graphed:
         launches = rollout.graph_launches * args.steps
     flows = env.get_state("arr_cursor").astype(np.int64).sum() - cur0
@@ -306,7 +325,23 @@ def run_ours(args):
     value = world * E * A * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the public API with HOST buffers (pinned H2D actions, D2H obs/reward/done)
-    if rollout is None:
+    if sac is not None:
+        # per step a trainer needs the rewards / dones back; the Gaussian draws go in from pinned memory
+        h_eps = [torch.randn((E, S), dtype=torch.float32).pin_memory() for _ in range(2)]
+        d_eps = torch.empty((E, S), dtype=torch.float32, device="cuda")
+        o_rew = torch.empty((E,), dtype=torch.float64, pin_memory=True)
+        o_done = torch.empty((E,), dtype=torch.uint8, pin_memory=True)
+
+        def e2e_step(k):
+            d_eps.copy_(h_eps[k % 2], non_blocking=True)
+            _, r_, dn_, _ = sac.step(eps=d_eps)
+            sac.update(1, sac_gen)
+            o_rew.copy_(r_, non_blocking=True)
+            o_done.copy_(dn_, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = E * S * 4, E * 8 + E
+        e2e_step(0)
+    elif rollout is None:
         h_act = []
         for p_ in pool[:2]:
             t_ = env.pinned_actions()
@@ -385,13 +420,13 @@ def run_ours(args):
                          "step": {"algorithmic_bytes_per_agent_step": bytes_as, "achieved": step_achieved,
                                   "frac": step_achieved / peak},
                          "flows_per_agent_step": F,
-                         "policy_ms_per_step": (ms / args.steps - (ev_ms + ft_ms) / max(prof_steps, 1)) if rollout is not None else None,
+                         "policy_ms_per_step": (ms / args.steps - (ev_ms + ft_ms) / max(prof_steps, 1)) if (rollout is not None or sac is not None) else None,
                          "cuda_graph": graphed},
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clk,
         }
-        if world == 1 and not args.no_cpu and rollout is None:
+        if world == 1 and not args.no_cpu and rollout is None and sac is None:
             del env
             torch.cuda.empty_cache()
             v, steps, cores = cpu_oracle_rate(wl, n_envs=0 or max(4 * (os.cpu_count() or 1), 32),

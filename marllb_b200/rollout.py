@@ -84,3 +84,86 @@ class QMIXRollout:
         ops.onehot_action(act, self.Sa, self.hot, self.cold, out=self._env_action)
         o, r, d = self.env.step(self._env_action)
         return o, r, d, act
+
+
+class DeviceReplay:
+    """Replay ring held on the GPU for the batched rollout (the reference's ReplayBuffer,
+    problem-04-sac-gru/src/replay_buffer.py:35-94, stores one transition per Python call in a host
+    deque; at thousands of transitions per step that would be the bottleneck).  Same content per
+    transition -- (state, action, reward, next_state, done, policy hidden state) -- and uniform
+    sampling with replacement-free semantics left to the caller-supplied indices."""
+
+    def __init__(self, capacity, state_dim, action_dim, gru_dim, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.capacity, self.size, self.pos = capacity, 0, 0
+        self.state = torch.empty((capacity, state_dim), **f)
+        self.next_state = torch.empty((capacity, state_dim), **f)
+        self.action = torch.empty((capacity, action_dim), **f)
+        self.reward = torch.empty((capacity, 1), **f)
+        self.done = torch.empty((capacity, 1), **f)
+        self.hidden = torch.empty((capacity, gru_dim), **f)
+
+    def push_batch(self, state, action, reward, next_state, done, hidden):
+        n = state.shape[0]
+        if n > self.capacity:
+            raise ValueError("batch larger than the replay capacity")
+        first = min(n, self.capacity - self.pos)
+        for dst, src in ((self.state, state), (self.action, action), (self.reward, reward.reshape(n, 1).float()),
+                         (self.next_state, next_state), (self.done, done.reshape(n, 1).float()), (self.hidden, hidden)):
+            dst[self.pos:self.pos + first].copy_(src[:first])
+            if first < n:
+                dst[:n - first].copy_(src[first:])
+        self.pos = (self.pos + n) % self.capacity
+        self.size = min(self.size + n, self.capacity)
+
+    def __len__(self):
+        return self.size
+
+    def sample(self, batch_size, generator=None):
+        """-> the tuple SAC_GRU_Agent.update_parameters(batch=...) takes (hidden as [1, B, gru])."""
+        idx = torch.randint(0, self.size, (batch_size,), device=self.state.device, generator=generator)
+        g = lambda t: t.index_select(0, idx)
+        return (g(self.state), g(self.action), g(self.reward), g(self.next_state), g(self.done),
+                g(self.hidden).unsqueeze(0))
+
+
+class SACRollout:
+    """Config C4 of BASELINE.json: one SAC-GRU learner over E envs of S servers (the reference's SAC
+    is single-agent: state = the flattened (S, 11) observation, one continuous weight per server,
+    problem-04-sac-gru/src/trainer.py:96-133).  step(): actor forward + tanh-Gaussian sample for all
+    envs -> env step -> transition into the device replay; update(): SAC_GRU_Agent.update_parameters
+    on a device-sampled batch (its flat gradient buckets are all-reduced when a process group exists)."""
+
+    def __init__(self, env: VecLoadBalanceEnv, agent, replay_capacity: int = 65536):
+        if env.num_agents != 1 or env.action_type != "continuous":
+            raise ValueError("SACRollout needs a single-agent env with continuous actions")
+        self.env, self.agent = env, agent
+        self.E, self.S = env.num_envs, env.total_servers
+        if agent.state_dim != self.S * 11 or agent.action_dim != self.S:
+            raise ValueError("agent dims must be (servers*11, servers)")
+        self.hidden = agent.policy.init_hidden(self.E)
+        self.replay = DeviceReplay(replay_capacity, agent.state_dim, agent.action_dim, agent.policy.gru_dim, env.device)
+        self._state = torch.empty((self.E, self.S * 11), dtype=torch.float32, device=env.device)
+
+    def reset(self):
+        self.hidden = self.agent.policy.init_hidden(self.E)
+        return self.env.reset()
+
+    def step(self, eps=None, evaluate=False, store=True):
+        """eps [E, S] standard-normal draws (None: drawn on the device).  Returns (obs, reward, done, action)."""
+        self._state.copy_(self.env.obs.view(self.E, self.S * 11))      # obs is overwritten by the env step
+        action, h_new = self.agent.select_action_batch(self._state, self.hidden, evaluate=evaluate, eps=eps)
+        action = action.contiguous()
+        obs, rew, done = self.env.step(action)
+        if store:
+            self.replay.push_batch(self._state, action, rew, obs.view(self.E, self.S * 11), done, self.hidden[0])
+        self.hidden = h_new
+        return obs, rew, done, action
+
+    def update(self, updates=1, generator=None):
+        if len(self.replay) < self.agent.batch_size:
+            return None
+        out = None
+        for _ in range(updates):
+            out = self.agent.update_parameters(1, batch=self.replay.sample(self.agent.batch_size, generator))
+        return out

@@ -67,3 +67,41 @@ def test_qmix_rollout_matches_float64_policy_and_plain_env(E):
         o2, r2, d2 = env2.step(env_action)
         assert torch.equal(o, o2) and torch.equal(r, r2) and torch.equal(d, d2)
     env.check_status()
+
+
+def test_sac_rollout_device_replay_and_update():
+    from marllb_b200 import VecLoadBalanceEnv
+    from marllb_b200.policy import SAC_GRU_Agent
+    from marllb_b200.rollout import SACRollout
+    E, S = 48, 16
+
+    def mk():
+        env = VecLoadBalanceEnv(E, num_servers=S, action_type="continuous", max_steps=10 ** 6)
+        env.set_speeds(np.where(np.arange(S) % 2 == 0, 1.0, 2.0).astype(np.float32))
+        env.gen_poisson(64.0, 0.8 * 1.5 * S / 64.0, 10.0, seed=5)
+        env.reset()
+        return env
+    env, env2 = mk(), mk()
+    torch.manual_seed(11)
+    agent = SAC_GRU_Agent(state_dim=S * 11, action_dim=S, hidden_dim=64, gru_dim=32, batch_size=64)
+    ro = SACRollout(env, agent, replay_capacity=100)      # wraps around: 48 per step into 100 slots
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for k in range(6):
+        state_before = env.obs.clone().view(E, S * 11)
+        h_before = ro.hidden[0].clone()
+        eps = torch.randn(E, S, device="cuda", generator=g)
+        o, r, d, a = ro.step(eps=eps)
+        assert bool((a.abs() <= 1).all())                                        # tanh-squashed (networks.py:136)
+        o2, r2, d2 = env2.step(a)
+        assert torch.equal(o, o2) and torch.equal(r, r2)
+        # the newest transitions sit right behind the write position
+        pos = (ro.replay.pos - E) % 100
+        idx = (torch.arange(E, device="cuda") + pos) % 100
+        assert torch.equal(ro.replay.state[idx], state_before) and torch.equal(ro.replay.action[idx], a)
+        assert torch.equal(ro.replay.next_state[idx], o.view(E, S * 11)) and torch.equal(ro.replay.hidden[idx], h_before)
+        assert torch.equal(ro.replay.reward[idx, 0], r.float())
+    assert len(ro.replay) == 100
+    p0 = agent.policy.state_dict()["fc1.weight"].clone()
+    out = ro.update(2, g)
+    assert set(out) == {"q1", "q2", "policy", "alpha"} and all(np.isfinite(list(out.values())))
+    assert not torch.equal(p0, agent.policy.state_dict()["fc1.weight"])
