@@ -109,6 +109,7 @@ struct TcParams {
     const float* bias;
     int64_t ldc;
     int M, N, K, act;
+    int tma_store;   // C goes out through shared memory + TMA (coalesced, clipped at the matrix edge)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -119,7 +120,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 template <int NT, int RAW_STAGES>
 __global__ void __launch_bounds__(THREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_c, const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment for the swizzled tiles
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -279,25 +281,54 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         drain((nkb - 1) / DRAIN_KB);
         // epilogue from registers: thread = half of one output row
         const int row = m0 + q * 32 + lane;
-        if (row < p.M) {
-            const int c0 = half * NC;
-            const int n_valid = min(NT, p.N - n0);
-            float* crow = p.C + (int64_t)row * p.ldc + n0;
-            const bool vec = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+        const int c0 = half * NC;
+        const int n_valid = min(NT, p.N - n0);
+        if (p.tma_store) {
+            // A thread owning a row would store with a 4*ldc-byte stride between lanes (one 32-byte
+            // sector per lane and instruction: measured 12 us for a 128 x 192 tile).  Instead the tile is
+            // staged in shared memory -- the operand rings are free now -- as NT/32 sub-tiles of
+            // [128 rows x 128 bytes] in the 128-byte swizzle (conflict-free float4 writes) and written
+            // by TMA, which also clips at the matrix edge.
+            const int r = q * 32 + lane;
+            const bool bias4 = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
 #pragma unroll
             for (int c = 0; c < NC; c += 4) {
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    o[j] = apply_act(tot[c + j] + ((p.bias && c0 + c + j < n_valid) ? __ldg(p.bias + n0 + c0 + c + j) : 0.f), p.act);
-                if (vec && c0 + c + 4 <= n_valid) {
-                    *reinterpret_cast<float4*>(crow + c0 + c) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (c0 + c + j < n_valid) crow[c0 + c + j] = o[j];
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias4 && c0 + c + 4 <= n_valid) {
+                    bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + c));
+                } else if (p.bias) {
+                    if (c0 + c + 0 < n_valid) bv.x = __ldg(p.bias + n0 + c0 + c + 0);
+                    if (c0 + c + 1 < n_valid) bv.y = __ldg(p.bias + n0 + c0 + c + 1);
+                    if (c0 + c + 2 < n_valid) bv.z = __ldg(p.bias + n0 + c0 + c + 2);
+                    if (c0 + c + 3 < n_valid) bv.w = __ldg(p.bias + n0 + c0 + c + 3);
                 }
+                float4 o;
+                o.x = apply_act(tot[c + 0] + bv.x, p.act);
+                o.y = apply_act(tot[c + 1] + bv.y, p.act);
+                o.z = apply_act(tot[c + 2] + bv.z, p.act);
+                o.w = apply_act(tot[c + 3] + bv.w, p.act);
+                const int col = c0 + c, sub = col >> 5, chunk = (col & 31) >> 2;
+                *reinterpret_cast<float4*>(smem + (size_t)sub * (TILE_M * 128) + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(SPLIT_THREADS) : "memory");
+            if (threadIdx.x == 64) {
+#pragma unroll
+                for (int sub = 0; sub < NT / 32; sub++) {
+                    if (n0 + sub * 32 < p.N)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&map_c), "r"(smem_u32(smem + (size_t)sub * (TILE_M * 128))), "r"(n0 + sub * 32), "r"(m0)
+                                     : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
+            }
+        } else if (row < p.M) {
+            float* crow = p.C + (int64_t)row * p.ldc + n0;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+                if (c0 + c < n_valid)
+                    crow[c0 + c] = apply_act(tot[c] + (p.bias ? __ldg(p.bias + n0 + c0 + c) : 0.f), p.act);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -360,12 +391,14 @@ int mlb_linear_tc(const float* X, int64_t lda, const float* W, int64_t ldw, cons
     const int n_tiles = (N + NT - 1) / NT;
     CUtensorMap mx, mw;
     if (!make_map(&mx, X, M, K, lda, TILE_M) || !make_map(&mw, W, N, K, ldw, NT)) return MLB_ECUDA;
-    TcParams p{C, bias, ldc, M, N, K, act};
+    CUtensorMap mc = mx;   // placeholder when the TMA store cannot be used
+    const int tma_store = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && make_map(&mc, C, M, N, ldc, TILE_M);
+    TcParams p{C, bias, ldc, M, N, K, act, tma_store};
     const size_t smem = (size_t)(raw + LO_STAGES) * (TILE_M * TILE_K * 4 + (size_t)NT * TILE_K * 4) +
                         8 * (2 * raw + 2 * LO_STAGES + 6) + 1024;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MLB_ECUDA;
     dim3 grid(n_tiles, (M + TILE_M - 1) / TILE_M);
-    void* args[] = {&mx, &mw, &p};
+    void* args[] = {&mx, &mw, &mc, &p};
     if (cudaLaunchKernel(fn, grid, dim3(THREADS), args, smem, (cudaStream_t)stream) != cudaSuccess) return MLB_ECUDA;
     return cudaGetLastError() == cudaSuccess ? MLB_OK : MLB_ECUDA;
 }
