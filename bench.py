@@ -262,8 +262,11 @@ def run_ours(args):
 
     def do_step(k):
         if sac is not None:
-            sac.step()
-            sac.update(1, sac_gen)
+            if graphed:
+                sac.step_graph()
+            else:
+                sac.step()
+                sac.update(1, sac_gen)
         elif rollout is None:
             env.step(pool[k % 8])
         elif graphed:
@@ -290,6 +293,15 @@ def run_ours(args):
         prof_eager = env.profile_end()
         rollout.capture(0.05)
         graphed = True
+    if sac is not None and not args.no_graph and world == 1:
+        while len(sac.replay) < sac.replay.capacity:      # the graph samples from a full ring
+            do_step(0)
+        env.profile_begin(10)
+        for k in range(10):
+            do_step(k)
+        prof_eager = env.profile_end()
+        sac.capture(1)
+        graphed = True
     for k in range(args.warmup):
         do_step(k)
     env.check_status()
@@ -313,7 +325,7 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     launches = env.launch_count + (pops.LAUNCHES if (rollout is not None or sac is not None) else 0) - l0
     if graphed:
-        launches = rollout.graph_launches * args.steps
+        launches = (rollout if rollout is not None else sac).graph_launches * args.steps
     flows = env.get_state("arr_cursor").astype(np.int64).sum() - cur0
     env.check_status()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -334,8 +346,11 @@ def run_ours(args):
 
         def e2e_step(k):
             d_eps.copy_(h_eps[k % 2], non_blocking=True)
-            _, r_, dn_, _ = sac.step(eps=d_eps)
-            sac.update(1, sac_gen)
+            if graphed:
+                (_, r_, dn_, _), _ = sac.step_graph()   # (Gaussian draws come from the device generator here)
+            else:
+                _, r_, dn_, _ = sac.step(eps=d_eps)
+                sac.update(1, sac_gen)
             o_rew.copy_(r_, non_blocking=True)
             o_done.copy_(dn_, non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -69,6 +69,12 @@ int mlb_scale(float *x, int64_t n, const double *norm_sq, float max_norm, void *
 int mlb_adam(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1,
              float beta2, float eps, int32_t step, void *stream);
 
+/* The same with the step counter in device memory (step_dev[0] = steps taken so far; advanced by
+ * the call) and a 2-float scratch coef_dev: no host value changes from step to step, so an
+ * optimiser step can be captured in a CUDA graph. */
+int mlb_adam_dev(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1,
+                 float beta2, float eps, int32_t *step_dev, float *coef_dev, void *stream);
+
 /* QMIX epsilon-greedy selection (qmix_agent.py:159-164): q [M][K]; u [M] uniform draws,
  * rnd [M] int32 pre-drawn random actions; action = u < epsilon ? rnd : argmax (first max). */
 int mlb_egreedy_select(const float *q, const float *u, const int32_t *rnd, float epsilon,

@@ -198,6 +198,31 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] -= step_size * (mi / denom);
 }
 
+// Adam with the step counter on the device, so that an optimiser step can be replayed from a CUDA graph:
+// the prologue advances the counter and derives the two bias-correction coefficients from it.
+__global__ void adam_prep_kernel(int32_t* __restrict__ step, float lr, float beta1, float beta2, float* __restrict__ coef) {
+    const int t = step[0] + 1;
+    step[0] = t;
+    const double bc1 = 1.0 - pow((double)beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    coef[0] = (float)((double)lr / bc1);
+    coef[1] = (float)sqrt(bc2);
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float beta1, float beta2, float eps,
+                                const float* __restrict__ coef) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float step_size = coef[0], bc2_sqrt = coef[1];
+    const float gi = g[i];
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+}
+
 __global__ void egreedy_kernel(const float* __restrict__ q, const float* __restrict__ u, const int32_t* __restrict__ rnd,
                                float epsilon, int32_t* __restrict__ action, float* __restrict__ q_sel, int M, int K) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,6 +547,15 @@ int mlb_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps,
                                                                 (float)((double)lr / bc1), (float)sqrt(bc2));
+    return ok();
+}
+
+int mlb_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int32_t* step_dev, float* coef_dev, void* stream) {
+    if (!p || !g || !m || !v || !step_dev || !coef_dev) return MLB_EINVAL;
+    adam_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr, beta1, beta2, coef_dev);
+    if (n > 0)
+        adam_dev_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, coef_dev);
     return ok();
 }
 

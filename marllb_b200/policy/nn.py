@@ -124,6 +124,10 @@ class Adam:
         self._v = torch.zeros_like(bucket.flat_p)
         self.m, self.v = bucket.views(self._m), bucket.views(self._v)   # per-tensor views (checkpoints)
         self.t = 0
+        # the step counter the kernel uses lives on the device (a step replayed from a CUDA graph must not
+        # depend on a host value that changes); self.t mirrors it for checkpoints
+        self._t_dev = torch.zeros(1, dtype=torch.int32, device=bucket.flat_p.device)
+        self._coef_dev = torch.zeros(2, dtype=torch.float32, device=bucket.flat_p.device)
         self.data_parallel, self.max_grad_norm = data_parallel, max_grad_norm
 
     def step(self):
@@ -134,7 +138,10 @@ class Adam:
         if self.max_grad_norm is not None:
             ops.clip_grad_norm_([b.flat_g], self.max_grad_norm)
         self.t += 1
-        ops.adam_step(b.flat_p, b.flat_g, self._m, self._v, self.lr, self.t)
+        if b.flat_p.is_cuda:
+            ops.adam_step_dev(b.flat_p, b.flat_g, self._m, self._v, self.lr, self._t_dev, self._coef_dev)
+        else:
+            ops.adam_step(b.flat_p, b.flat_g, self._m, self._v, self.lr, self.t)
 
     def state_dict(self):
         return {"step": self.t, "exp_avg": [m.clone() for m in self.m], "exp_avg_sq": [v.clone() for v in self.v],
@@ -142,6 +149,7 @@ class Adam:
 
     def load_state_dict(self, sd):
         self.t = int(sd["step"])
+        self._t_dev.fill_(self.t)
         for m, s in zip(self.m, sd["exp_avg"]):
             m.copy_(s)
         for v, s in zip(self.v, sd["exp_avg_sq"]):

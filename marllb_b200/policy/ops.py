@@ -33,6 +33,7 @@ def _L():
             "mlb_sumsq": [vp, i64, vp, vp],
             "mlb_scale": [vp, i64, vp, f32, vp],
             "mlb_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp],
+            "mlb_adam_dev": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp, vp],
             "mlb_egreedy_select": [vp, vp, vp, f32, vp, vp, i32, i32, vp],
             "mlb_row_max": [vp, vp, vp, i32, i32, vp],
             "mlb_onehot_action": [vp, i32, i32, i32, C.c_uint8, C.c_uint8, vp, vp],
@@ -56,7 +57,7 @@ def _L():
 
 
 POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_gru_gates_forward", "mlb_gru_gates_backward", "mlb_relu_backward",
-                  "mlb_abs_backward", "mlb_colsum", "mlb_axpby", "mlb_sumsq", "mlb_scale", "mlb_adam",
+                  "mlb_abs_backward", "mlb_colsum", "mlb_axpby", "mlb_sumsq", "mlb_scale", "mlb_adam", "mlb_adam_dev",
                   "mlb_egreedy_select", "mlb_onehot_action", "mlb_row_max", "mlb_mixer_forward", "mlb_mixer_backward",
                   "mlb_tanh_gaussian_forward", "mlb_tanh_gaussian_backward", "mlb_abs_forward",
                   "mlb_qmix_td_loss", "mlb_sac_q_target", "mlb_mse_loss", "mlb_sac_policy_loss",
@@ -207,6 +208,12 @@ def clip_grad_norm_(grads, max_norm):
 
 def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_L().mlb_adam(_p(_chk(p)), _p(_chk(g)), _p(_chk(m)), _p(_chk(v)), p.numel(), lr, beta1, beta2, eps, step, _st()))
+
+
+def adam_step_dev(p, g, m, v, lr, step_dev, coef_dev, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Adam step whose step counter lives on the device (int32 [1], advanced here): graph-capturable."""
+    check(_L().mlb_adam_dev(_p(_chk(p)), _p(_chk(g)), _p(_chk(m)), _p(_chk(v)), p.numel(), lr, beta1, beta2, eps,
+                            _p(step_dev), _p(coef_dev), _st()))
 
 
 def egreedy_select(q, epsilon=0.0, u=None, rnd=None):

@@ -279,8 +279,10 @@ class SAC_GRU_Agent:
         action, _, mean_action, hidden_new = self.policy.sample(states, hiddens, eps=eps)
         return (mean_action if evaluate else action), hidden_new
 
-    def update_parameters(self, updates=1, batch=None, eps_next=None, eps_new=None):
-        """sac_agent.py:151-255.  `batch`, `eps_next`, `eps_new` may be supplied for parity tests."""
+    def update_parameters(self, updates=1, batch=None, eps_next=None, eps_new=None, sync_stats=True):
+        """sac_agent.py:151-255.  `batch`, `eps_next`, `eps_new` may be supplied for parity tests.
+        sync_stats=False keeps the losses on the device (no host synchronisation: the whole update can
+        then be captured in a CUDA graph) and returns them as 0-d tensors."""
         if batch is None and not self.replay_buffer.is_ready(self.batch_size):
             return None
         losses = {'q1': 0, 'q2': 0, 'policy': 0, 'alpha': 0}
@@ -328,14 +330,17 @@ class SAC_GRU_Agent:
             # ---- targets, :234-235
             soft_update(self.q1, self.q1_target, self.tau)
             soft_update(self.q2, self.q2_target, self.tau)
-            losses['q1'] += float(q_losses[0].item())
-            losses['q2'] += float(q_losses[1].item())
-            losses['policy'] += float(p_loss.item())
+            conv = (lambda t: float(t.item())) if sync_stats else (lambda t: t.reshape(()).detach())
+            losses['q1'] = losses['q1'] + conv(q_losses[0])
+            losses['q2'] = losses['q2'] + conv(q_losses[1])
+            losses['policy'] = losses['policy'] + conv(p_loss)
             if a_loss is not None:
-                losses['alpha'] += float(a_loss.item())
+                losses['alpha'] = losses['alpha'] + conv(a_loss)
             self.total_steps += 1
         for k in losses:
-            losses[k] /= updates
+            losses[k] = losses[k] / updates
+        if not sync_stats:
+            return losses
         self.training_stats['q1_loss'].append(losses['q1'])
         self.training_stats['q2_loss'].append(losses['q2'])
         self.training_stats['policy_loss'].append(losses['policy'])

@@ -96,6 +96,7 @@ class DeviceReplay:
     def __init__(self, capacity, state_dim, action_dim, gru_dim, device):
         f = dict(dtype=torch.float32, device=device)
         self.capacity, self.size, self.pos = capacity, 0, 0
+        self._pos_dev = torch.zeros(1, dtype=torch.int64, device=device)   # write position, device copy (graph replays)
         self.state = torch.empty((capacity, state_dim), **f)
         self.next_state = torch.empty((capacity, state_dim), **f)
         self.action = torch.empty((capacity, action_dim), **f)
@@ -107,13 +108,14 @@ class DeviceReplay:
         n = state.shape[0]
         if n > self.capacity:
             raise ValueError("batch larger than the replay capacity")
-        first = min(n, self.capacity - self.pos)
+        # the slot indices come from the device-side position so that a captured push lands in the
+        # right place on every replay
+        idx = (self._pos_dev + torch.arange(n, device=self.state.device)) % self.capacity
         for dst, src in ((self.state, state), (self.action, action), (self.reward, reward.reshape(n, 1).float()),
                          (self.next_state, next_state), (self.done, done.reshape(n, 1).float()), (self.hidden, hidden)):
-            dst[self.pos:self.pos + first].copy_(src[:first])
-            if first < n:
-                dst[:n - first].copy_(src[first:])
-        self.pos = (self.pos + n) % self.capacity
+            dst.index_copy_(0, idx, src)
+        self._pos_dev.add_(n).remainder_(self.capacity)
+        self.pos = (self.pos + n) % self.capacity      # host mirror (not advanced by graph replays)
         self.size = min(self.size + n, self.capacity)
 
     def __len__(self):
@@ -160,10 +162,59 @@ class SACRollout:
         self.hidden = h_new
         return obs, rew, done, action
 
-    def update(self, updates=1, generator=None):
+    def update(self, updates=1, generator=None, sync_stats=True):
         if len(self.replay) < self.agent.batch_size:
             return None
         out = None
         for _ in range(updates):
-            out = self.agent.update_parameters(1, batch=self.replay.sample(self.agent.batch_size, generator))
+            out = self.agent.update_parameters(1, batch=self.replay.sample(self.agent.batch_size, generator),
+                                               sync_stats=sync_stats)
         return out
+
+    # ---- CUDA graph: actor sampling + env step + replay push + one SAC update = one graph launch
+    def capture(self, updates=1, warmup=2):
+        """Capture `step(); update(updates)` into a CUDA graph (single process: an NCCL all-reduce in
+        the optimiser steps is not captured here).  Needs a FULL replay ring (the sampling range is
+        fixed at capture) -- run at least capacity / num_envs eager steps first.  Gaussian and index
+        draws come from torch's default CUDA generator, which is graph-safe."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise RuntimeError("SACRollout.capture is single-process; run data-parallel training eagerly")
+        if len(self.replay) < self.replay.capacity:
+            raise RuntimeError("fill the replay ring before capturing (sampling range is fixed in the graph)")
+        dev = self.env.device
+        self._h_static = self.hidden.clone()
+
+        def body():
+            self.hidden = self._h_static
+            out = self.step()
+            self._h_static.copy_(self.hidden)
+            self.hidden = self._h_static
+            losses = self.update(updates, sync_stats=False)
+            return out, losses
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from .policy import ops as _ops
+        n0 = self.env.launch_count + _ops.LAUNCHES
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = body()
+        self.graph_launches = self.env.launch_count + _ops.LAUNCHES - n0
+        self._graph_updates = updates
+        return self
+
+    def step_graph(self):
+        """Replay the captured rollout step + update.  Returns ((obs, reward, done, action), losses)."""
+        self._graph.replay()
+        for opt in (self.agent.q1_optimizer, self.agent.q2_optimizer, self.agent.policy_optimizer):
+            opt.t += self._graph_updates            # host mirrors of the device-side step counters
+        if self.agent.auto_entropy_tuning:
+            self.agent.alpha_optimizer.t += self._graph_updates
+        self.agent.total_steps += self._graph_updates
+        return self._graph_out
