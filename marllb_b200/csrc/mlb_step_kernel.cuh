@@ -542,7 +542,7 @@ feature_kernel(const __grid_constant__ DevState d) {
             const unsigned bal = __ballot_sync(MLB_FULL, dirty);
             if (dirty) {
                 const uint32_t n = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
-                const bool inc = staged && chg_nold(chg) > 0 && n > 64 && nchg >= 1 && nchg <= 3;
+                const bool inc = staged && chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
                 dlist[nd + __popc(bal & ((1u << lane) - 1u))] =
                     make_uint2(chg, (uint32_t)(j * 2 + m) | (n << 9) | ((inc ? 1u : 0u) << 17));
             }

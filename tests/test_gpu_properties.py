@@ -33,12 +33,13 @@ def test_flow_conservation_and_feature_cache_idempotence():
         outs = [env.step(act) for env in envs]
         obs, rew, done = outs[0]
         for o2, r2, d2 in outs[1:]:
-            # order statistics, counts, rewards: bit-identical.  mean_decay (cols 4, 9) divides by the
-            # weight total taken from the rank-ordered scan, so equal values ranked in a different
-            # (equally valid) order can move it by one ulp.
-            exact = [0, 1, 2, 3, 5, 6, 7, 8, 10]
+            # counts and order statistics (p90, p90_decay: elements / exact lerps of the reservoir) and the
+            # reward, which reads column 10: bit-identical.  mean, std, mean_decay are float32 sums whose
+            # reduction tree depends on the path (mode 1 keeps 4 slots per lane for every fill level, the
+            # re-sorting modes use 1 / 2 / 4): equal within a few ulp.
+            exact = [0, 2, 5, 7, 10]
             assert torch.equal(obs[..., exact], o2[..., exact]) and torch.equal(rew, r2) and torch.equal(done, d2)
-            assert torch.allclose(obs[..., [4, 9]], o2[..., [4, 9]], rtol=3e-7, atol=0)
+            assert torch.allclose(obs[..., [1, 3, 4, 6, 8, 9]], o2[..., [1, 3, 4, 6, 8, 9]], rtol=2e-6, atol=1e-9)
         active_sum += obs[..., 0].double()
         assert bool((obs >= 0).all()) and bool(torch.isfinite(obs).all())
         assert bool(((rew >= 1.0 / S - 1e-12) & (rew <= 1.0 + 1e-12) | (rew == 0)).all())    # Jain in [1/n, 1]
