@@ -2,6 +2,7 @@
 //
 // Reference modules: problem-05-qmix/src/{agent_network,mixing_network,qmix_agent}.py and
 // problem-04-sac-gru/src/{networks,sac_agent}.py (paths under simulation-mode/).
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -18,10 +19,14 @@ __global__ void __launch_bounds__(256)
 gemm_kernel(const float* __restrict__ A, int64_t a_bs, int64_t a_rs, int64_t a_cs,
             const float* __restrict__ B, int64_t b_bs, int64_t b_rs, int64_t b_cs,
             float* __restrict__ C, int64_t c_bs, int64_t ldc, const float* __restrict__ bias,
-            int64_t bias_bs, int M, int N, int K, float beta, int act) {
+            int64_t bias_bs, int M, int N, int K, float beta, int act, int splits, float* __restrict__ ws) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
-    const int b = blockIdx.z;
+    // split-K (small outputs with a long reduction, e.g. M = 256 rows x K = 3000): z = batch * splits + split,
+    // raw partial sums go to the workspace and splitk_reduce_kernel applies beta / bias / activation
+    const int b = blockIdx.z / splits, sp = blockIdx.z - b * splits;
+    const int kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+    const int k_lo = sp * kchunk, k_hi = min(K, k_lo + kchunk);
     A += (int64_t)b * a_bs;
     B += (int64_t)b * b_bs;
     C += (int64_t)b * c_bs;
@@ -35,14 +40,14 @@ gemm_kernel(const float* __restrict__ A, int64_t a_bs, int64_t a_rs, int64_t a_c
         for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
     const bool a_kfast = (a_cs == 1);  // k contiguous in A -> walk k fastest when loading
     const bool b_nfast = (b_cs == 1);  // n contiguous in B
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
 #pragma unroll
         for (int i = 0; i < (BM * BK) / 256; i++) {
             const int t = tid + i * 256;
             const int ml = a_kfast ? t / BK : t % BM;
             const int kl = a_kfast ? t % BK : t / BM;
             const int m = m0 + ml, k = k0 + kl;
-            As[kl][ml] = (m < M && k < K) ? A[(int64_t)m * a_rs + (int64_t)k * a_cs] : 0.f;
+            As[kl][ml] = (m < M && k < k_hi) ? A[(int64_t)m * a_rs + (int64_t)k * a_cs] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < (BN * BK) / 256; i++) {
@@ -50,7 +55,7 @@ gemm_kernel(const float* __restrict__ A, int64_t a_bs, int64_t a_rs, int64_t a_c
             const int nl = b_nfast ? t % BN : t / BK;
             const int kl = b_nfast ? t / BN : t % BK;
             const int n = n0 + nl, k = k0 + kl;
-            Bs[kl][nl] = (n < N && k < K) ? B[(int64_t)k * b_rs + (int64_t)n * b_cs] : 0.f;
+            Bs[kl][nl] = (n < N && k < k_hi) ? B[(int64_t)k * b_rs + (int64_t)n * b_cs] : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -77,6 +82,10 @@ gemm_kernel(const float* __restrict__ A, int64_t a_bs, int64_t a_rs, int64_t a_c
             const int n = n0 + tx * TN + j;
             if (n >= N) continue;
             float v = acc[i][j];
+            if (splits > 1) {
+                ws[(((int64_t)sp * (gridDim.z / splits) + b) * M + m) * N + n] = v;
+                continue;
+            }
             if (bias) v += bias[n];
             if (beta != 0.f) v += beta * C[(int64_t)m * ldc + n];
             if (act == MLB_ACT_RELU) v = fmaxf(v, 0.f);
@@ -84,6 +93,26 @@ gemm_kernel(const float* __restrict__ A, int64_t a_bs, int64_t a_rs, int64_t a_c
             C[(int64_t)m * ldc + n] = v;
         }
     }
+}
+
+// C = act(beta*C + sum_s ws[s] + bias), partial sums added in split order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int batch, float* __restrict__ C,
+                                     int64_t c_bs, int64_t ldc, const float* __restrict__ bias, int64_t bias_bs,
+                                     int M, int N, float beta, int act) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)M * N;
+    if (i >= per * batch) return;
+    const int b = (int)(i / per);
+    const int64_t r = i - (int64_t)b * per;
+    const int m = (int)(r / N), n = (int)(r - (int64_t)m * N);
+    float v = 0.f;
+    for (int s = 0; s < splits; s++) v += ws[((int64_t)s * batch + b) * per + r];
+    if (bias) v += bias[(int64_t)b * bias_bs + n];
+    float* c = C + (int64_t)b * c_bs + (int64_t)m * ldc + n;
+    if (beta != 0.f) v += beta * *c;
+    if (act == MLB_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == MLB_ACT_ABS) v = fabsf(v);
+    *c = v;
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -474,8 +503,41 @@ int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const flo
     if (!A || !B || !C || M < 0 || N < 0 || K < 0 || batch < 1) return MLB_EINVAL;
     if (M == 0 || N == 0) return MLB_OK;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
+    // few output tiles and a long reduction: split K over more thread blocks (workspace per device, grown
+    // outside stream capture only)
+    int splits = 1;
+    const int64_t tiles = (int64_t)grid.x * grid.y * batch;
+    if (tiles < 64 && K >= 256) {
+        splits = (int)std::min<int64_t>(std::min<int64_t>(16, 160 / tiles), K / 128);
+        if (splits < 2) splits = 1;
+    }
+    float* ws = nullptr;
+    if (splits > 1) {
+        static float* ws_ptr[64] = {nullptr};
+        static size_t ws_cap[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const size_t need = (size_t)splits * batch * M * N * sizeof(float);
+        if (dev < 64 && need > ws_cap[dev]) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+            if (cs == cudaStreamCaptureStatusNone) {
+                const size_t cap = std::max<size_t>(need, (size_t)32 << 20);
+                float* q = nullptr;
+                if (cudaMalloc(&q, cap) == cudaSuccess) {   // the old buffer may still be in use by queued work: keep it
+                    ws_ptr[dev] = q;
+                    ws_cap[dev] = cap;
+                }
+            }
+        }
+        if (dev < 64 && need <= ws_cap[dev]) ws = ws_ptr[dev]; else splits = 1;
+    }
+    grid.z = batch * splits;
     gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, a_bs, a_rs, a_cs, B, b_bs, b_rs, b_cs, C, c_bs, ldc,
-                                                        bias, bias_bs, M, N, K, beta, act);
+                                                        bias, bias_bs, M, N, K, beta, act, splits, ws);
+    if (splits > 1)
+        splitk_reduce_kernel<<<nblk((int64_t)M * N * batch, 256), 256, 0, (cudaStream_t)stream>>>(
+            ws, splits, batch, C, c_bs, ldc, bias, bias_bs, M, N, beta, act);
     return ok();
 }
 
