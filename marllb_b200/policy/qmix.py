@@ -313,6 +313,8 @@ class QMIXAgent:
         self._params, self._grads = self._bucket.params, self._bucket.grads
         self.optimizer = Adam(self._bucket, lr, max_grad_norm=10.0)
         self.episode_buffer = EpisodeBuffer(capacity=buffer_capacity, num_agents=num_agents)
+        self.graph_updates = False      # True: replay the device part of update() as a CUDA graph
+        self._graphs = {}
         self.total_updates = 0
         self.training_stats = {'loss': [], 'q_tot': [], 'target_q_tot': []}
 
@@ -376,6 +378,58 @@ class QMIXAgent:
         states = torch.as_tensor(batch['states'], dtype=f32).to(dev)                  # [B,T,S]
         dones = torch.as_tensor(batch['dones'], dtype=f32).to(dev).contiguous()       # [B,T]
         seq_len = torch.as_tensor(np.asarray(batch['seq_lengths'], dtype=np.int32)).to(dev)
+        key = (tuple(obs.shape), tuple(actions.shape), tuple(states.shape))
+        if self.graph_updates and not self._dp_active():
+            stats = self._update_graphed(key, obs, actions, rewards, states, dones, seq_len)
+        else:
+            stats = self._update_device(obs, actions, rewards, states, dones, seq_len)
+        return self._finish_update(stats)
+
+    @staticmethod
+    def _dp_active():
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _update_graphed(self, key, *inputs):
+        """Replay the whole device part of update() (~900 launches at C3 sizes) as one CUDA graph; one
+        graph per batch shape, static input buffers.  Not used under data parallelism (the NCCL
+        all-reduce of the gradient bucket stays eager)."""
+        g = self._graphs.get(key)
+        if g is None:
+            static = [t.clone() for t in inputs]
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            snap = self._snapshot()
+            with torch.cuda.stream(side):
+                self._update_device(*static)            # warm-up (allocations, lazy inits); undone below
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self._restore(snap)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._update_device(*static)
+            self._restore(snap)                          # capture does not execute, but keep the host mirrors honest
+            g = self._graphs[key] = (graph, static, out)
+        graph, static, out = g
+        for dst, src in zip(static, inputs):
+            dst.copy_(src)
+        graph.replay()
+        self.optimizer.t += 1
+        return out
+
+    def _snapshot(self):
+        o = self.optimizer
+        return (self._bucket.flat_p.clone(), o._m.clone(), o._v.clone(), o._t_dev.clone(), o.t)
+
+    def _restore(self, snap):
+        o = self.optimizer
+        self._bucket.flat_p.copy_(snap[0]); o._m.copy_(snap[1]); o._v.copy_(snap[2]); o._t_dev.copy_(snap[3])
+        o.t = snap[4]
+
+    def _update_device(self, obs, actions, rewards, states, dones, seq_len):
+        """Everything of update() that runs on the GPU: forward, TD loss, backward, optimiser step.
+        No host synchronisation; returns the float64[3] stats tensor (loss, mean q_tot, mean target)."""
+        dev, f32 = self.device, torch.float32
         B, T, A, _ = obs.shape
         K = self.action_dim
         obs_tb = obs.permute(2, 1, 0, 3).contiguous()                                 # [A,T,B,obs] time-major per agent
@@ -416,6 +470,10 @@ class QMIXAgent:
         for a in range(A):
             self.agent_networks[a].backward_seq(dq_tb[a])
         self.optimizer.step()                                                         # all-reduce, clip 10 (:284), Adam
+        return stats
+
+    def _finish_update(self, stats):
+        A = self.num_agents
         self.total_updates += 1
         if self.total_updates % self.target_update_interval == 0:                     # :288-294
             for i in range(A):

@@ -96,10 +96,12 @@ class TrainingPipeline:
         S, A = self.num_servers, self.num_agents
         if self.agent_type == 'qmix':
             Sa = S // A
-            return QMIXAgent(num_agents=A, state_dim=4 * S + 10, obs_dim=Sa * 11, action_dim=Sa, hidden_dim=64,
-                             mixing_embed_dim=32, lr=self.config.get('learning_rate', 0.0005),
-                             gamma=self.config.get('gamma', 0.99), batch_size=self.config.get('batch_size', 32),
-                             max_seq_len=self.config.get('max_seq_len', 50), device=self.device)
+            agent = QMIXAgent(num_agents=A, state_dim=4 * S + 10, obs_dim=Sa * 11, action_dim=Sa, hidden_dim=64,
+                              mixing_embed_dim=32, lr=self.config.get('learning_rate', 0.0005),
+                              gamma=self.config.get('gamma', 0.99), batch_size=self.config.get('batch_size', 32),
+                              max_seq_len=self.config.get('max_seq_len', 50), device=self.device)
+            agent.graph_updates = bool(self.config.get('graph_updates', True))   # update() replayed as one CUDA graph
+            return agent
         lr = self.config.get('learning_rate', 0.0003)
         return SAC_GRU_Agent(state_dim=S * 11, action_dim=S, hidden_dim=256, lr_policy=lr, lr_q=lr, lr_alpha=lr,
                              gamma=self.config.get('gamma', 0.99), batch_size=self.config.get('batch_size', 256),

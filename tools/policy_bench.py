@@ -23,6 +23,9 @@ batch = {'observations': rng.randn(B, T, A, Sa * 11), 'actions': rng.randint(0, 
          'seq_lengths': np.full(B, T, np.int32)}
 ms, l = timeit(lambda: agent.update(batch=batch))
 print("QMIX update  B=32 T=50 A=2 obs=352: %.2f ms, %d kernel launches" % (ms, l), flush=True)
+agent.graph_updates = True
+ms, l = timeit(lambda: agent.update(batch=batch))
+print("QMIX update  (CUDA graph)          : %.2f ms" % ms, flush=True)
 
 S = 256
 sac = SAC_GRU_Agent(state_dim=S * 11, action_dim=S, hidden_dim=256, gru_dim=128, batch_size=256)
