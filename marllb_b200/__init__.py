@@ -7,6 +7,11 @@ Public surface (reference API names kept):
     ReservoirSampler, MultiMetricReservoir, PerServerFeatures
                                           problem-01-reservoir-sampling/src/{reservoir,features}.py
     VecLoadBalanceEnv, BatchedReservoirs  batched forms (new)
+    policy.{QMIXAgent, AgentQNetwork, QMixingNetwork, EpisodeBuffer, SAC_GRU_Agent, PolicyNetwork, QNetwork, ...}
+                                          problem-05-qmix/src, problem-04-sac-gru/src
+    QMIXRollout, SACRollout, DeviceReplay env step fused with batched policy inference (CUDA graph)
+    training_pipeline.TrainingPipeline    problem-06-vpp-integration/src/training_pipeline.py
+    wire                                  problem-02-shared-memory-ipc/src/shm_layout.py (msg_out / msg_in)
 All compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
 include/marllb_b200.h; there is no CPU fallback.
 """
@@ -14,7 +19,7 @@ from ._build import build  # noqa: F401
 
 __all__ = ["build", "LoadBalanceEnv", "LoadBalanceEnvGym", "MultiAgentLoadBalanceEnv",
            "VecLoadBalanceEnv", "RewardFunction", "ReservoirSampler", "MultiMetricReservoir",
-           "PerServerFeatures", "BatchedReservoirs"]
+           "PerServerFeatures", "BatchedReservoirs", "QMIXRollout", "SACRollout", "DeviceReplay"]
 
 _LAZY = {
     "LoadBalanceEnv": "env", "LoadBalanceEnvGym": "env",
@@ -22,6 +27,7 @@ _LAZY = {
     "RewardFunction": "rewards", "ReservoirSampler": "reservoir",
     "MultiMetricReservoir": "reservoir", "PerServerFeatures": "reservoir",
     "BatchedReservoirs": "reservoir",
+    "QMIXRollout": "rollout", "SACRollout": "rollout", "DeviceReplay": "rollout",
 }
 
 

@@ -559,7 +559,11 @@ feature_kernel(const __grid_constant__ DevState d) {
         const float4* const val4 = reinterpret_cast<const float4*>(d.res_val);
         const float4* const ts4 = reinterpret_cast<const float4*>(d.res_ts);
         uint32_t* const rank4 = reinterpret_cast<uint32_t*>(d.res_rank);
-        const uint32_t off0 = (uint32_t)(sbase * 2 * 32) + (uint32_t)lane;
+        uint32_t off0 = (uint32_t)(sbase * 2 * 32) + (uint32_t)lane;
+        uint32_t obs0 = (uint32_t)(sbase * MLB_OBS_COLS) + 1u;      // column 1 of this warp's first server
+        // opaque to the optimiser: otherwise both are re-derived from (env, agent) with 64-bit multiplies
+        // inside the loop instead of living in two registers
+        asm volatile("" : "+r"(off0), "+r"(obs0));
         const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + lane * 16;
         const float4* stage_v = reinterpret_cast<const float4*>(stage) + lane;
         if (nd > 0) {
@@ -597,7 +601,7 @@ feature_kernel(const __grid_constant__ DevState d) {
                                                (int)chg_nold(ent.x), ent.x, (int)chg_count(ent.x), t1, d.decay,
                                                d.log2_decay, scratch, f);
                 if (ok && lane == 0) {
-                    float* o = warp_obs + (id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u;
+                    float* o = d.obs + (obs0 + (id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u);
 #pragma unroll
                     for (int q = 0; q < 5; q++) o[q] = f[q];
                 }
