@@ -34,7 +34,8 @@ struct mlb_env {
     void* d_action = nullptr;
     size_t action_bytes = 0;
     uint8_t* d_mask = nullptr;
-    size_t ev_smem = 0, ft_smem = 0;   // dynamic shared memory of the event / feature kernel
+    size_t ev_smem = 0, ft_smem = 0, pr_smem = 0;   // dynamic shared memory of the event / feature / pair kernel
+    bool use_pair = false;             // pair_kernel applies (128-slot reservoirs, feature cache on)
     int ev_threads = 128;              // event kernel: independent warps
     int epb = 1, ft_threads = 32;      // feature kernel: epb envs x A agent warps per block
     cudaStream_t copy_stream = nullptr;   // device->host copies of the chunked host-buffer step
@@ -205,6 +206,15 @@ static const void* feature_fn(int Sa) {
     }
 }
 
+static const void* pair_fn(int Sa) {
+    switch (lanes_r(Sa)) {
+    case 1: return (const void*)pair_kernel<1>;
+    case 2: return (const void*)pair_kernel<2>;
+    case 4: return (const void*)pair_kernel<4>;
+    default: return (const void*)pair_kernel<8>;
+    }
+}
+
 // dynamic shared memory + carve-out sized for `warps_wanted` resident warps (the rest stays L1)
 static cudaError_t set_smem(const void* fn, size_t block_bytes, int threads, int warps_wanted) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_bytes);
@@ -234,6 +244,10 @@ static int launch_cfg(mlb_env* h) {
                     h->ft_smem > h->ev_smem ? h->ft_smem : h->ev_smem);
     cudaError_t e = set_smem(event_fn(c.policy, c.servers_per_agent), h->ev_smem, h->ev_threads, 4 * MLB_EV_MINBLOCKS);
     if (e == cudaSuccess) e = set_smem(feature_fn(c.servers_per_agent), h->ft_smem, h->ft_threads, 32);
+    h->use_pair = h->d.KP == 128 && h->d.K == 128 && c.feature_cache == 1 && !getenv("MLB_NO_PAIR");
+    h->d.use_pair = h->use_pair ? 1 : 0;
+    h->pr_smem = (size_t)4 * pair_warp_smem_bytes(SP);
+    if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent), h->pr_smem, 128, 32);
     if (e != cudaSuccess) return fail(h, MLB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return MLB_OK;
 }
@@ -622,6 +636,11 @@ static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_
     CK(h, cudaLaunchKernel(event_fn(dv.policy, dv.Sa), dim3(ev_blocks), dim3(h->ev_threads), ev_args, h->ev_smem, st));
     if (pe) CK(h, cudaEventRecord(pe[1], st));
     void* ft_args[] = {&dv};
+    if (h->use_pair) {
+        const int pr_blocks = (int)(((int64_t)(e1 - e0) * dv.A + 3) / 4);
+        CK(h, cudaLaunchKernel(pair_fn(dv.Sa), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
+        h->launches += 1;
+    }
     const int ft_blocks = (e1 - e0 + h->epb - 1) / h->epb;
     CK(h, cudaLaunchKernel(feature_fn(dv.Sa), dim3(ft_blocks), dim3(h->ft_threads), ft_args, h->ft_smem, st));
     if (pe) CK(h, cudaEventRecord(pe[2], st));

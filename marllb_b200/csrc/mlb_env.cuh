@@ -16,6 +16,7 @@ struct DevState {
     int reward_metric, reward_field, max_steps;
     int L;                 // words per MT19937 replay row
     int feature_cache, record_assign;
+    int use_pair;          // pair_kernel evaluates the "fast" reservoirs before feature_kernel
     float dw[8];
     float min_w, max_w, dt;
     float log2_decay;

@@ -532,6 +532,140 @@ __device__ __forceinline__ void features_sorted_epl(const float* __restrict__ va
         features_ranked<EPL, false>(v, t, rk, n, now, decay, log2_decay, sc, out);
 }
 
+// ---------------------------------------------------------------------------
+// Half-warp forms for the steady state (FULL 128-slot reservoir, ONE replaced slot): the reservoir
+// lies on 16 lanes x 8 consecutive slots, so every warp instruction serves TWO reservoirs (one per
+// half-warp).  All warp-uniform work -- list decoding, addresses, reductions, scans, broadcasts -- is
+// thereby halved per reservoir; the per-element work is unchanged.  hl = lane & 15, half = lane >> 4.
+// Every collective keeps the FULL member mask so that the warp stays converged (half masks would let the
+// two halves drift apart and be issued separately): shuffles are segmented by width 16, integer REDUX sums
+// carry the two halves in separate 16-bit fields, REDUX min / max run once per half with the identity
+// contributed by the other half.
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(MLB_FULL, v, o, 16);
+    return v;
+}
+__device__ __forceinline__ uint32_t half_reduce_add_u16(uint32_t x, int half) {   // x < 2^16 / 16 per lane
+    const uint32_t both = __reduce_add_sync(MLB_FULL, half ? (x << 16) : x);
+    return half ? (both >> 16) : (both & 0xffffu);
+}
+__device__ __forceinline__ uint32_t half_reduce_max(uint32_t x, int half) {
+    const uint32_t m0 = __reduce_max_sync(MLB_FULL, half ? 0u : x);
+    const uint32_t m1 = __reduce_max_sync(MLB_FULL, half ? x : 0u);
+    return half ? m1 : m0;
+}
+__device__ __forceinline__ uint32_t half_reduce_min(uint32_t x, int half) {
+    const uint32_t m0 = __reduce_min_sync(MLB_FULL, half ? 0xffffffffu : x);
+    const uint32_t m1 = __reduce_min_sync(MLB_FULL, half ? x : 0xffffffffu);
+    return half ? m1 : m0;
+}
+
+template <typename T>
+__device__ __forceinline__ T pick8(const T (&x)[8], int sub) {
+    const T a = (sub & 1) ? x[1] : x[0], b = (sub & 1) ? x[3] : x[2];
+    const T c = (sub & 1) ? x[5] : x[4], d = (sub & 1) ? x[7] : x[6];
+    const T lo = (sub & 2) ? b : a, hi = (sub & 2) ? d : c;
+    return (sub & 4) ? hi : lo;
+}
+
+// rank_replace_one_packed on 8 slots per lane (ranks packed in two words)
+__device__ __forceinline__ void rank_replace_one_h16(const float (&v)[8], uint32_t (&rkp)[2], int c, int hl,
+                                                     int half) {
+    const int sub = c & 7, lc = c >> 3;
+    const float x = __shfl_sync(MLB_FULL, pick8(v, sub), lc, 16) + 0.0f;   // -0 -> +0
+    const uint32_t wsel = (sub & 4) ? rkp[1] : rkp[0];
+    const uint32_t r_old = (__shfl_sync(MLB_FULL, wsel, lc, 16) >> (8 * (sub & 3))) & 255u;
+    const uint32_t xb = __float_as_uint(x);
+    const float xup = __uint_as_float((xb >> 31) ? xb - 1u : xb + 1u);
+    const int dl = c - hl * 8;  // slots r < dl of this lane lie before c
+    uint32_t bef0 = 0, bef1 = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        bef0 |= v[r] < (r < dl ? xup : x) ? (1u << (8 * r)) : 0u;
+        bef1 |= v[r + 4] < (r + 4 < dl ? xup : x) ? (1u << (8 * r)) : 0u;
+    }
+    const uint32_t r_new = half_reduce_add_u16((uint32_t)(__popc(bef0) + __popc(bef1)), half);
+    const uint32_t rep = (r_old + 1u) * 0x01010101u;
+    rkp[0] = rkp[0] - ((((rkp[0] | 0x80808080u) - rep) >> 7) & 0x01010101u) + (bef0 ^ 0x01010101u);
+    rkp[1] = rkp[1] - ((((rkp[1] | 0x80808080u) - rep) >> 7) & 0x01010101u) + (bef1 ^ 0x01010101u);
+    if (hl == lc) {
+        const int sh = 8 * (sub & 3);
+        if (sub & 4) rkp[1] = (rkp[1] & ~(255u << sh)) | (r_new << sh);
+        else rkp[0] = (rkp[0] & ~(255u << sh)) | (r_new << sh);
+    }
+}
+
+// features_ranked<4, true, DEFER> on 8 slots per lane; vw = this half's 128-entry scratch.
+// Returns false when the float32 weighted-percentile decision is not trusted (caller defers).
+__device__ __forceinline__ bool features_full_h16(const float (&v)[8], const float (&t)[8], const uint32_t (&rkp)[2],
+                                                  float log2_decay, float2* vw, int hl, int half,
+                                                  float (&out)[5]) {
+    const float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    const float tm = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])));
+    const float mean = half_sum(s) * (1.0f / 128.0f);
+    const float tmax = f32_from_orderable(half_reduce_max(f32_orderable(tm), half));
+    float s2 = 0.f, svw = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const float dv = v[r] - mean;
+        s2 += dv * dv;
+        const float w = fast_exp2(log2_decay * (tmax - t[r]));
+        svw += v[r] * w;
+        // rank p lives at index (p & 7) * 16 + (p >> 3): lane hl then reads its eight consecutive ranks
+        // 8 * hl + r at index r * 16 + hl -- consecutive lanes, consecutive words, no bank conflicts
+        const uint32_t pos = (rkp[r >> 2] >> (8 * (r & 3))) & 255u;
+        vw[((pos & 7u) << 4) | (pos >> 3)] = make_float2(v[r], w);
+    }
+    const float sd = fast_sqrt(half_sum(s2) * (1.0f / 128.0f));
+    svw = half_sum(svw);
+    __syncwarp();
+    float cum[8];
+    float sw = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        sw += vw[r * 16 + hl].y;
+        cum[r] = sw;
+    }
+    float incl = sw;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const float y = __shfl_up_sync(MLB_FULL, incl, o, 16);
+        if (hl >= o) incl += y;
+    }
+    const float W = __shfl_sync(MLB_FULL, incl, 15, 16);
+    const float mean_decay = svw * fast_rcp(W);
+    const float rel = 0.9f * W - (incl - sw);
+    int below = 0;
+    float dmin = MLB_INF;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        below += cum[r] < rel ? 1 : 0;
+        dmin = fminf(dmin, fabsf(cum[r] - rel));
+    }
+    int idx = (int)half_reduce_add_u16((uint32_t)below, half);
+    const uint32_t dmin_bits = half_reduce_min(__float_as_uint(dmin), half);
+    const bool ok = !(__uint_as_float(dmin_bits) < MLB_WP_MARGIN * W);
+    idx = idx > 127 ? 127 : idx;
+    // p90 = np.percentile(values, 90) for n = 128: float32 'linear' rule of numpy >= 2 (same ops as features_ranked)
+    const float vidx = 127.0f * (90.0f / 100.0f);
+    const float fl = floorf(vidx);
+    const int lo = (int)fl, hi = lo + 1;
+    const float gamma = vidx - fl;
+    const float a = vw[((lo & 7) << 4) | (lo >> 3)].x, b = vw[((hi & 7) << 4) | (hi >> 3)].x;
+    const float p90_decay = vw[((idx & 7) << 4) | (idx >> 3)].x;
+    const float diff = __fsub_rn(b, a);
+    float p90 = __fadd_rn(a, __fmul_rn(diff, gamma));
+    if (gamma >= 0.5f) p90 = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+    __syncwarp();  // scratch is reused by the next reservoir
+    out[0] = mean;
+    out[1] = p90;
+    out[2] = sd;
+    out[3] = mean_decay;
+    out[4] = p90_decay;
+    return ok;
+}
+
 // lane q < 5 keeps feature q (the lane that stores it)
 __device__ __forceinline__ float feature_of_lane(const float (&f)[5], int lane) {
     float mine = f[0];

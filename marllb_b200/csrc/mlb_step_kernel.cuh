@@ -482,6 +482,114 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
 }
 
 // ---------------------------------------------------------------------------
+// pair_kernel: the steady state of the statistics -- FULL 128-slot reservoirs in which Algorithm R replaced
+// exactly one slot -- two reservoirs per warp instruction (one per half-warp, 8 slots per lane; see
+// mlb_features.cuh).  One warp per (env, agent), warps independent.  A separate kernel so that its loop
+// (~420 instructions per pair) has the instruction cache to itself: inside feature_kernel the two hot
+// paths evicted each other (ncu: 29 % of the stalls were instruction fetches).
+__host__ __device__ inline size_t pair_warp_smem_bytes(int SP) {
+    return (size_t)2 * SP * 8 + 2 * MLB_SCRATCH_BYTES + 2 * MLB_STAGE_BYTES;
+}
+
+template <int R>
+__global__ void __launch_bounds__(128, 8)
+pair_kernel(const __grid_constant__ DevState d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SP = 32 * R;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int A = d.A, Sa = d.Sa, S = d.S;
+    const int ea = d.e0 * A + blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ea >= d.e1 * A) return;
+    const int e = ea / A;
+    const int agent = ea - e * A;
+    unsigned char* wbase = smem_raw + (size_t)warp * pair_warp_smem_bytes(SP);
+    uint2* dlist = reinterpret_cast<uint2*>(wbase);
+    float2* const vw = reinterpret_cast<float2*>(wbase + (size_t)2 * SP * 8);
+    unsigned char* stage = wbase + (size_t)2 * SP * 8 + 2 * MLB_SCRATCH_BYTES;
+    const size_t sbase = (size_t)e * S + (size_t)agent * Sa;
+    const int seed0 = agent * Sa;
+
+    int nfast = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = lane + 32 * r;
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            uint32_t chg = 0, cnt = 0;
+            if (j < Sa) {
+                const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
+                chg = __ldg(d.res_chg + c);
+                cnt = __ldg(d.res_count + c);
+            }
+            const bool fast = j < Sa && chg_count(chg) == 1 && chg_nold(chg) == 128 && cnt >= 128u;
+            const unsigned bal = __ballot_sync(MLB_FULL, fast);
+            if (fast) dlist[nfast + __popc(bal & ((1u << lane) - 1u))] = make_uint2(chg, (uint32_t)(j * 2 + m));
+            nfast += __popc(bal);
+        }
+    }
+    __syncwarp();
+    if (nfast == 0) return;
+    const float4* const val4 = reinterpret_cast<const float4*>(d.res_val);
+    const float4* const ts4 = reinterpret_cast<const float4*>(d.res_ts);
+    uint32_t* const rank4 = reinterpret_cast<uint32_t*>(d.res_rank);
+    uint32_t off0 = (uint32_t)(sbase * 2 * 32) + (uint32_t)lane;
+    uint32_t obs0 = (uint32_t)(sbase * MLB_OBS_COLS) + 1u;
+    uint32_t chg0 = (uint32_t)((size_t)e * 2 * S + seed0);
+    asm volatile("" : "+r"(off0), "+r"(obs0), "+r"(chg0));   // keep them in registers (see feature_kernel)
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + lane * 16;
+    const int half = lane >> 4, hl = lane & 15;
+    float2* const vw_half = vw + half * 128;
+    auto stage_in = [&](uint32_t id, int slot) {
+        const uint32_t off = off0 + id * 32u;
+        const uint32_t dst = stage_s + (uint32_t)slot * MLB_STAGE_BYTES;
+        cp_async16(dst, val4 + off);
+        cp_async16(dst + 512, ts4 + off);
+        cp_async4(dst + 1024 - lane * 12, rank4 + off);
+    };
+    stage_in(dlist[0].y, 0);
+    if (nfast > 1) stage_in(dlist[1].y, 1);
+    cp_async_commit();
+#pragma unroll 1
+    for (int i = 0; i < nfast; i += 2) {
+        const bool valid = i + half < nfast;              // an odd list ends with half 1 idle
+        const uint2 ent = dlist[valid ? i + half : i];
+        const uint32_t id = ent.y;
+        cp_async_wait_all();
+        __syncwarp();
+        const unsigned char* rec = stage + half * MLB_STAGE_BYTES;
+        const float4 v0 = reinterpret_cast<const float4*>(rec)[hl * 2], v1 = reinterpret_cast<const float4*>(rec)[hl * 2 + 1];
+        const float4 t0 = reinterpret_cast<const float4*>(rec + 512)[hl * 2], t1q = reinterpret_cast<const float4*>(rec + 512)[hl * 2 + 1];
+        const uint2 rq = reinterpret_cast<const uint2*>(rec + 1024)[hl];
+        __syncwarp();
+        if (i + 2 < nfast) {
+            stage_in(dlist[i + 2].y, 0);
+            if (i + 3 < nfast) stage_in(dlist[i + 3].y, 1);
+            cp_async_commit();
+        }
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1q.x, t1q.y, t1q.z, t1q.w};
+        uint32_t rkp[2] = {valid ? rq.x : 0u, valid ? rq.y : 0u};   // idle half: every scatter position 0
+        rank_replace_one_h16(v, rkp, (int)(ent.x & 127u), hl, half);
+        if (valid) reinterpret_cast<uint2*>(rank4 + (off0 - lane + id * 32u))[hl] = make_uint2(rkp[0], rkp[1]);
+        if (!valid) { rkp[0] = 0u; rkp[1] = 0u; }
+        float f[5];
+        const bool ok = features_full_h16(v, t, rkp, d.log2_decay, vw_half, hl, half, f);
+        if (valid && hl == 0) {
+            if (ok) {
+                float* o = d.obs + (obs0 + (id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u);
+#pragma unroll
+                for (int q = 0; q < 5; q++) o[q] = f[q];
+            } else {
+                // float32 decision not trusted: hand the reservoir to feature_kernel's re-sort path by
+                // saturating its change count ([E][2][S] layout: metric-major)
+                d.res_chg[chg0 + (id & 1u) * (uint32_t)S + (id >> 1)] = ent.x | (7u << 21);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // feature_kernel: block = epb envs x A agent warps (the reward needs all agents of an env).
 template <int R>
 __global__ void __launch_bounds__(1024, 1)
@@ -525,6 +633,9 @@ feature_kernel(const __grid_constant__ DevState d) {
     const bool all = d.feature_cache == 0;  // mode 0: recompute every reservoir
     const int KP = d.KP;
     const bool staged = KP == 128 && d.feature_cache == 1;
+    // "Fast" entries (full reservoir, exactly one replaced slot: the steady state) were already evaluated by
+    // pair_kernel, two per warp instruction; an entry it could not settle comes back with its change count
+    // saturated (-> re-sorted here).  This kernel takes everything else.
     int nd = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -534,18 +645,18 @@ feature_kernel(const __grid_constant__ DevState d) {
             uint32_t chg = 0, cnt = 0;
             if (j < Sa) {
                 const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
-                chg = __ldcs(d.res_chg + c);
-                cnt = __ldcs(d.res_count + c);
+                chg = __ldg(d.res_chg + c);
+                cnt = __ldg(d.res_count + c);
             }
             const uint32_t nchg = chg_count(chg);
-            const bool dirty = j < Sa && (all || nchg > 0);
-            const unsigned bal = __ballot_sync(MLB_FULL, dirty);
-            if (dirty) {
-                const uint32_t n = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
-                const bool inc = staged && chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
+            const uint32_t n = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
+            const bool inc = staged && chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
+            const bool fast = d.use_pair && inc && nchg == 1 && chg_nold(chg) == 128 && n == 128;
+            const bool take = j < Sa && (all || nchg > 0) && !fast;
+            const unsigned bal = __ballot_sync(MLB_FULL, take);
+            if (take)
                 dlist[nd + __popc(bal & ((1u << lane) - 1u))] =
                     make_uint2(chg, (uint32_t)(j * 2 + m) | (n << 9) | ((inc ? 1u : 0u) << 17));
-            }
             nd += __popc(bal);
         }
     }
@@ -566,13 +677,14 @@ feature_kernel(const __grid_constant__ DevState d) {
         asm volatile("" : "+r"(off0), "+r"(obs0));
         const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + lane * 16;
         const float4* stage_v = reinterpret_cast<const float4*>(stage) + lane;
-        if (nd > 0) {
-            const uint32_t off = off0 + (dlist[0].y & 511u) * 32u;
+        auto stage_in = [&](uint32_t id) {
+            const uint32_t off = off0 + id * 32u;
             cp_async16(stage_s, val4 + off);
             cp_async16(stage_s + 512, ts4 + off);
             cp_async4(stage_s + 1024 - lane * 12, rank4 + off);
             cp_async_commit();
-        }
+        };
+        if (nd > 0) stage_in(dlist[0].y & 511u);
 #pragma unroll 1
         for (int i = 0; i < nd; i++) {
             const uint2 ent = dlist[i];
@@ -582,13 +694,7 @@ feature_kernel(const __grid_constant__ DevState d) {
             const float4 qt = stage_v[32];
             const uint32_t rkp = reinterpret_cast<const uint32_t*>(stage_v - lane + 64)[lane];
             __syncwarp();
-            if (i + 1 < nd) {
-                const uint32_t off = off0 + (dlist[i + 1].y & 511u) * 32u;
-                cp_async16(stage_s, val4 + off);
-                cp_async16(stage_s + 512, ts4 + off);
-                cp_async4(stage_s + 1024 - lane * 12, rank4 + off);
-                cp_async_commit();
-            }
+            if (i + 1 < nd) stage_in(dlist[i + 1].y & 511u);
             // anything that is not "a few replaced slots, trusted float32 decision" is deferred to
             // the cold loop below (entries re-packed at the front of the list): no calls in here
             bool ok = false;
