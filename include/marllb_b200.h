@@ -177,9 +177,13 @@ int64_t mlb_launch_count(const mlb_env *h);
 /* Per-kernel timing of mlb_step (measurement only; no reference counterpart). After
  * mlb_profile_begin the next max_steps calls of mlb_step record CUDA events around their two
  * kernels on the step's stream; mlb_profile_end synchronises those events and returns the
- * summed durations (ms) of the event kernel and the feature kernel and the steps covered. */
+ * summed durations (ms) of the event kernel and of the statistics pass (pair_kernel +
+ * feature_kernel) and the steps covered. */
 int mlb_profile_begin(mlb_env *h, int max_steps);
 int mlb_profile_end(mlb_env *h, double *event_ms, double *feature_ms, int *steps);
+/* Of the feature_ms of the last mlb_profile_end (the statistics pass = pair_kernel + feature_kernel),
+ * the part spent in pair_kernel. */
+double mlb_profile_pair_ms(const mlb_env *h);
 
 /* ---- stand-alone pieces (P01 reservoir, P03 rewards) ------------------------ */
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "mlb_abi_version", "mlb_config_default", "mlb_create", "mlb_destroy", "mlb_last_error",
     "mlb_set_speeds", "mlb_load_arrivals", "mlb_gen_poisson", "mlb_get_arrivals", "mlb_reset",
     "mlb_step", "mlb_get_assignments", "mlb_device_ptr", "mlb_get_state", "mlb_status",
-    "mlb_launch_count", "mlb_profile_begin", "mlb_profile_end", "mlb_mt19937_fill", "mlb_reservoir_add", "mlb_reservoir_features",
+    "mlb_launch_count", "mlb_profile_begin", "mlb_profile_end", "mlb_profile_pair_ms", "mlb_mt19937_fill", "mlb_reservoir_add", "mlb_reservoir_features",
     "mlb_reward_metric", "mlb_legacy_seed", "mlb_legacy_obs",
 ]
 
@@ -86,6 +86,7 @@ def load():
         "mlb_launch_count": (i64, [vp]),
         "mlb_profile_begin": (C.c_int, [vp, i32]),
         "mlb_profile_end": (C.c_int, [vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(i32)]),
+        "mlb_profile_pair_ms": (f64, [vp]),
         "mlb_mt19937_fill": (C.c_int, [C.c_uint32, vp, i64]),
         "mlb_reservoir_add": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
         "mlb_reservoir_features": (C.c_int, [vp, vp, vp, i32, i32, f64, vp, vp, vp]),

@@ -42,7 +42,8 @@ struct mlb_env {
     cudaEvent_t copy_done = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
     int host_chunks = 8;
-    std::vector<cudaEvent_t> prof_ev;  // 3 events per profiled step
+    std::vector<cudaEvent_t> prof_ev;  // 4 events per profiled step: | event | pair | feature |
+    double prof_pair_ms = 0.0;         // pair_kernel share of the last mlb_profile_end
     int prof_cap = 0, prof_n = 0;
     size_t state_bytes[MLB_F_COUNT_] = {0};
     void* state_ptr[MLB_F_COUNT_] = {nullptr};
@@ -296,7 +297,7 @@ int64_t mlb_launch_count(const mlb_env* h) { return h ? h->launches : 0; }
 int mlb_profile_begin(mlb_env* h, int max_steps) {
     if (!h || max_steps < 0) return MLB_EINVAL;
     CK(h, cudaSetDevice(h->device));
-    while ((int)h->prof_ev.size() < 3 * max_steps) {
+    while ((int)h->prof_ev.size() < 4 * max_steps) {
         cudaEvent_t e;
         CK(h, cudaEventCreate(&e));
         h->prof_ev.push_back(e);
@@ -309,17 +310,20 @@ int mlb_profile_begin(mlb_env* h, int max_steps) {
 int mlb_profile_end(mlb_env* h, double* event_ms, double* feature_ms, int* steps) {
     if (!h) return MLB_EINVAL;
     CK(h, cudaSetDevice(h->device));
-    double ev = 0.0, ft = 0.0;
+    double ev = 0.0, ft = 0.0, pair = 0.0;
     for (int i = 0; i < h->prof_n; i++) {
-        float a = 0.f, b = 0.f;
-        CK(h, cudaEventSynchronize(h->prof_ev[(size_t)3 * i + 2]));
-        CK(h, cudaEventElapsedTime(&a, h->prof_ev[(size_t)3 * i], h->prof_ev[(size_t)3 * i + 1]));
-        CK(h, cudaEventElapsedTime(&b, h->prof_ev[(size_t)3 * i + 1], h->prof_ev[(size_t)3 * i + 2]));
+        float a = 0.f, b = 0.f, c = 0.f;
+        CK(h, cudaEventSynchronize(h->prof_ev[(size_t)4 * i + 3]));
+        CK(h, cudaEventElapsedTime(&a, h->prof_ev[(size_t)4 * i], h->prof_ev[(size_t)4 * i + 1]));
+        CK(h, cudaEventElapsedTime(&c, h->prof_ev[(size_t)4 * i + 1], h->prof_ev[(size_t)4 * i + 2]));
+        CK(h, cudaEventElapsedTime(&b, h->prof_ev[(size_t)4 * i + 1], h->prof_ev[(size_t)4 * i + 3]));
+        pair += c;
         ev += a;
         ft += b;
     }
     if (event_ms) *event_ms = ev;
-    if (feature_ms) *feature_ms = ft;
+    if (feature_ms) *feature_ms = ft;       // statistics pass = pair_kernel + feature_kernel
+    h->prof_pair_ms = pair;
     if (steps) *steps = h->prof_n;
     h->prof_cap = 0;
     h->prof_n = 0;
@@ -641,9 +645,10 @@ static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_
         CK(h, cudaLaunchKernel(pair_fn(dv.Sa), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
         h->launches += 1;
     }
+    if (pe) CK(h, cudaEventRecord(pe[2], st));
     const int ft_blocks = (e1 - e0 + h->epb - 1) / h->epb;
     CK(h, cudaLaunchKernel(feature_fn(dv.Sa), dim3(ft_blocks), dim3(h->ft_threads), ft_args, h->ft_smem, st));
-    if (pe) CK(h, cudaEventRecord(pe[2], st));
+    if (pe) CK(h, cudaEventRecord(pe[3], st));
     h->launches += 2;
     return MLB_OK;
 }
@@ -701,7 +706,7 @@ int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, dou
     }
     const bool prof = h->prof_n < h->prof_cap;
     {
-        const int rc = launch_step(h, dact, 0, d.E, st, prof ? &h->prof_ev[(size_t)3 * h->prof_n] : nullptr);
+        const int rc = launch_step(h, dact, 0, d.E, st, prof ? &h->prof_ev[(size_t)4 * h->prof_n] : nullptr);
         if (rc != MLB_OK) return rc;
         if (prof) h->prof_n++;
     }
@@ -713,6 +718,8 @@ int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, dou
     if (out_done) CK(h, cudaMemcpyAsync(out_done, d.done, (size_t)d.E, kind, st));
     return MLB_OK;
 }
+
+double mlb_profile_pair_ms(const mlb_env* h) { return h ? h->prof_pair_ms : 0.0; }
 
 int mlb_get_assignments(mlb_env* h, int32_t* dst, int64_t n, int loc, void* stream) {
     if (!h || !dst) return MLB_EINVAL;

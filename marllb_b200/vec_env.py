@@ -267,6 +267,7 @@ class VecLoadBalanceEnv:
         """-> (event_kernel_ms, feature_kernel_ms, steps) summed over the profiled steps."""
         ev, ft, n = C.c_double(), C.c_double(), C.c_int32()
         check(self._L.mlb_profile_end(self._h, C.byref(ev), C.byref(ft), C.byref(n)), self._h)
+        self.last_pair_ms = float(self._L.mlb_profile_pair_ms(self._h))   # pair_kernel part of the statistics pass
         return ev.value, ft.value, n.value
 
     # ------------------------------------------------------------ state dumps
