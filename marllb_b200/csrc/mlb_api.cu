@@ -207,12 +207,12 @@ static const void* feature_fn(int Sa) {
     }
 }
 
-static const void* pair_fn(int Sa) {
+static const void* pair_fn(int Sa, int cls) {
     switch (lanes_r(Sa)) {
-    case 1: return (const void*)pair_kernel<1>;
-    case 2: return (const void*)pair_kernel<2>;
-    case 4: return (const void*)pair_kernel<4>;
-    default: return (const void*)pair_kernel<8>;
+    case 1: return cls ? (const void*)pair_kernel<1, 1> : (const void*)pair_kernel<1, 0>;
+    case 2: return cls ? (const void*)pair_kernel<2, 1> : (const void*)pair_kernel<2, 0>;
+    case 4: return cls ? (const void*)pair_kernel<4, 1> : (const void*)pair_kernel<4, 0>;
+    default: return cls ? (const void*)pair_kernel<8, 1> : (const void*)pair_kernel<8, 0>;
     }
 }
 
@@ -248,7 +248,8 @@ static int launch_cfg(mlb_env* h) {
     h->use_pair = h->d.KP == 128 && h->d.K == 128 && c.feature_cache == 1 && !getenv("MLB_NO_PAIR");
     h->d.use_pair = h->use_pair ? 1 : 0;
     h->pr_smem = (size_t)4 * pair_warp_smem_bytes(SP);
-    if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent), h->pr_smem, 128, 32);
+    if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent, 0), h->pr_smem, 128, 32);
+    if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent, 1), h->pr_smem, 128, 32);
     if (e != cudaSuccess) return fail(h, MLB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return MLB_OK;
 }
@@ -642,8 +643,9 @@ static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_
     void* ft_args[] = {&dv};
     if (h->use_pair) {
         const int pr_blocks = (int)(((int64_t)(e1 - e0) * dv.A + 3) / 4);
-        CK(h, cudaLaunchKernel(pair_fn(dv.Sa), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
-        h->launches += 1;
+        CK(h, cudaLaunchKernel(pair_fn(dv.Sa, 0), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
+        CK(h, cudaLaunchKernel(pair_fn(dv.Sa, 1), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
+        h->launches += 2;
     }
     if (pe) CK(h, cudaEventRecord(pe[2], st));
     const int ft_blocks = (e1 - e0 + h->epb - 1) / h->epb;

@@ -666,6 +666,145 @@ __device__ __forceinline__ bool features_full_h16(const float (&v)[8], const flo
     return ok;
 }
 
+// General incremental rank update on 8 slots per lane (packed ranks, SWAR): up to three written slots
+// (7-bit ids in `list`), slots >= n_old are appends of the fill phase.  pm0 / pm1 carry one 0x01 per PRESENT
+// slot; first every replaced slot's old rank is taken out, then the new values are inserted one at a time.
+// The two halves of the warp may have different nchg: the loops run to the larger one with the shorter
+// half predicated off, so that every collective is executed by the whole warp.
+__device__ __forceinline__ void rank_update_h16(const float (&v)[8], uint32_t (&rkp)[2], uint32_t list, int nchg,
+                                                int n_old, int hl, int half) {
+    const int s0 = hl * 8;
+    uint32_t pm0 = 0, pm1 = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        pm0 |= (s0 + r < n_old) ? (1u << (8 * r)) : 0u;
+        pm1 |= (s0 + 4 + r < n_old) ? (1u << (8 * r)) : 0u;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        const int c = (list >> (7 * k)) & 127;
+        const bool rem = k < nchg && c < n_old;
+        if (!__any_sync(MLB_FULL, rem)) continue;
+        const int sub = c & 7, lc = c >> 3;
+        const uint32_t wsel = (sub & 4) ? rkp[1] : rkp[0];
+        const uint32_t r_old = (__shfl_sync(MLB_FULL, wsel, lc, 16) >> (8 * (sub & 3))) & 255u;
+        const uint32_t rep = ((r_old & 127u) + 1u) * 0x01010101u;
+        const uint32_t g0 = ((((rkp[0] | 0x80808080u) - rep) >> 7) & pm0);
+        const uint32_t g1 = ((((rkp[1] | 0x80808080u) - rep) >> 7) & pm1);
+        if (rem) {
+            rkp[0] -= g0;
+            rkp[1] -= g1;
+            if (hl == lc) {
+                if (sub & 4) pm1 &= ~(1u << (8 * (sub & 3))); else pm0 &= ~(1u << (8 * (sub & 3)));
+            }
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        const bool ins = k < nchg;
+        if (!__any_sync(MLB_FULL, ins)) break;
+        const int c = (list >> (7 * k)) & 127;
+        const int sub = c & 7, lc = c >> 3;
+        const float x = __shfl_sync(MLB_FULL, pick8(v, sub), lc, 16) + 0.0f;
+        const uint32_t xb = __float_as_uint(x);
+        const float xup = __uint_as_float((xb >> 31) ? xb - 1u : xb + 1u);
+        const int dl = c - s0;
+        uint32_t bef0 = 0, bef1 = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            bef0 |= v[r] < (r < dl ? xup : x) ? (1u << (8 * r)) : 0u;
+            bef1 |= v[r + 4] < (r + 4 < dl ? xup : x) ? (1u << (8 * r)) : 0u;
+        }
+        const uint32_t r_new = half_reduce_add_u16((uint32_t)(__popc(bef0 & pm0) + __popc(bef1 & pm1)), half);
+        if (ins) {
+            rkp[0] += ~bef0 & pm0;
+            rkp[1] += ~bef1 & pm1;
+            if (hl == lc) {
+                const int sh = 8 * (sub & 3);
+                if (sub & 4) { rkp[1] = (rkp[1] & ~(255u << sh)) | (r_new << sh); pm1 |= 1u << sh; }
+                else { rkp[0] = (rkp[0] & ~(255u << sh)) | (r_new << sh); pm0 |= 1u << sh; }
+            }
+        }
+    }
+}
+
+// features_ranked<4, false, DEFER> on 8 slots per lane: n valid slots (1..128), possibly different in the two halves
+__device__ __forceinline__ bool features_any_h16(const float (&v)[8], const float (&t)[8], const uint32_t (&rkp)[2],
+                                                 int n, float log2_decay, float2* vw, int hl, int half,
+                                                 float (&out)[5]) {
+    const int s0 = hl * 8;
+    float s = 0.f, tm = -MLB_INF;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const bool valid = s0 + r < n;
+        s += valid ? v[r] : 0.f;
+        tm = valid ? fmaxf(tm, t[r]) : tm;
+    }
+    const float nf = (float)n;
+    const float mean = half_sum(s) / nf;
+    const float tmax = f32_from_orderable(half_reduce_max(f32_orderable(tm), half));
+    float s2 = 0.f, svw = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const bool valid = s0 + r < n;
+        const float dv = v[r] - mean;
+        s2 += valid ? dv * dv : 0.f;
+        const float w = valid ? fast_exp2(log2_decay * (tmax - t[r])) : 0.f;
+        svw += valid ? v[r] * w : 0.f;
+        const uint32_t pos = valid ? ((rkp[r >> 2] >> (8 * (r & 3))) & 127u) : (uint32_t)(s0 + r);
+        vw[((pos & 7u) << 4) | (pos >> 3)] = make_float2(v[r], w);
+    }
+    const float sd = fast_sqrt(half_sum(s2) / nf);
+    svw = half_sum(svw);
+    __syncwarp();
+    float cum[8];
+    float sw = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        sw += vw[r * 16 + hl].y;
+        cum[r] = sw;
+    }
+    float incl = sw;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const float y = __shfl_up_sync(MLB_FULL, incl, o, 16);
+        if (hl >= o) incl += y;
+    }
+    const float W = __shfl_sync(MLB_FULL, incl, 15, 16);
+    const float mean_decay = svw * fast_rcp(W);
+    const float rel = 0.9f * W - (incl - sw);
+    int below = 0;
+    float dmin = MLB_INF;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const bool valid = s0 + r < n;  // here s0 + r is a POSITION in rank order
+        below += (valid && cum[r] < rel) ? 1 : 0;
+        dmin = valid ? fminf(dmin, fabsf(cum[r] - rel)) : dmin;
+    }
+    int idx = (int)half_reduce_add_u16((uint32_t)below, half);
+    const uint32_t dmin_bits = half_reduce_min(__float_as_uint(dmin), half);
+    const bool ok = !(__uint_as_float(dmin_bits) < MLB_WP_MARGIN * W);
+    idx = idx > n - 1 ? n - 1 : idx;
+    const float vidx = (float)(n - 1) * (90.0f / 100.0f);
+    const float fl = floorf(vidx);
+    int lo = (int)fl, hi = lo + 1;
+    if (vidx >= (float)(n - 1)) { lo = n - 1; hi = n - 1; }
+    hi = hi > n - 1 ? n - 1 : hi;
+    const float gamma = vidx - fl;
+    const float a = vw[((lo & 7) << 4) | (lo >> 3)].x, b = vw[((hi & 7) << 4) | (hi >> 3)].x;
+    const float p90_decay = vw[((idx & 7) << 4) | (idx >> 3)].x;
+    const float diff = __fsub_rn(b, a);
+    float p90 = __fadd_rn(a, __fmul_rn(diff, gamma));
+    if (gamma >= 0.5f) p90 = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+    __syncwarp();
+    out[0] = mean;
+    out[1] = p90;
+    out[2] = sd;
+    out[3] = mean_decay;
+    out[4] = p90_decay;
+    return ok;
+}
+
 // lane q < 5 keeps feature q (the lane that stores it)
 __device__ __forceinline__ float feature_of_lane(const float (&f)[5], int lane) {
     float mine = f[0];

@@ -491,7 +491,9 @@ __host__ __device__ inline size_t pair_warp_smem_bytes(int SP) {
     return (size_t)2 * SP * 8 + 2 * MLB_SCRATCH_BYTES + 2 * MLB_STAGE_BYTES;
 }
 
-template <int R>
+// CLS 0: full reservoirs with ONE replaced slot (constants folded, one-slot SWAR update);
+// CLS 1: every other incrementally updatable reservoir (2-3 written slots, fill-phase appends, any n).
+template <int R, int CLS>
 __global__ void __launch_bounds__(128, 8)
 pair_kernel(const __grid_constant__ DevState d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -522,9 +524,13 @@ pair_kernel(const __grid_constant__ DevState d) {
                 chg = __ldg(d.res_chg + c);
                 cnt = __ldg(d.res_count + c);
             }
-            const bool fast = j < Sa && chg_count(chg) == 1 && chg_nold(chg) == 128 && cnt >= 128u;
+            const uint32_t nchg = chg_count(chg);
+            const uint32_t n = cnt < 128u ? cnt : 128u;
+            const bool one = nchg == 1 && chg_nold(chg) == 128 && n == 128;
+            const bool inc = chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
+            const bool fast = j < Sa && (CLS == 0 ? one : (inc && !one));
             const unsigned bal = __ballot_sync(MLB_FULL, fast);
-            if (fast) dlist[nfast + __popc(bal & ((1u << lane) - 1u))] = make_uint2(chg, (uint32_t)(j * 2 + m));
+            if (fast) dlist[nfast + __popc(bal & ((1u << lane) - 1u))] = make_uint2(chg, (uint32_t)(j * 2 + m) | (n << 9));
             nfast += __popc(bal);
         }
     }
@@ -547,14 +553,14 @@ pair_kernel(const __grid_constant__ DevState d) {
         cp_async16(dst + 512, ts4 + off);
         cp_async4(dst + 1024 - lane * 12, rank4 + off);
     };
-    stage_in(dlist[0].y, 0);
-    if (nfast > 1) stage_in(dlist[1].y, 1);
+    stage_in(dlist[0].y & 511u, 0);
+    if (nfast > 1) stage_in(dlist[1].y & 511u, 1);
     cp_async_commit();
 #pragma unroll 1
     for (int i = 0; i < nfast; i += 2) {
         const bool valid = i + half < nfast;              // an odd list ends with half 1 idle
         const uint2 ent = dlist[valid ? i + half : i];
-        const uint32_t id = ent.y;
+        const uint32_t id = ent.y & 511u;
         cp_async_wait_all();
         __syncwarp();
         const unsigned char* rec = stage + half * MLB_STAGE_BYTES;
@@ -563,18 +569,27 @@ pair_kernel(const __grid_constant__ DevState d) {
         const uint2 rq = reinterpret_cast<const uint2*>(rec + 1024)[hl];
         __syncwarp();
         if (i + 2 < nfast) {
-            stage_in(dlist[i + 2].y, 0);
-            if (i + 3 < nfast) stage_in(dlist[i + 3].y, 1);
+            stage_in(dlist[i + 2].y & 511u, 0);
+            if (i + 3 < nfast) stage_in(dlist[i + 3].y & 511u, 1);
             cp_async_commit();
         }
         const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1q.x, t1q.y, t1q.z, t1q.w};
         uint32_t rkp[2] = {valid ? rq.x : 0u, valid ? rq.y : 0u};   // idle half: every scatter position 0
-        rank_replace_one_h16(v, rkp, (int)(ent.x & 127u), hl, half);
-        if (valid) reinterpret_cast<uint2*>(rank4 + (off0 - lane + id * 32u))[hl] = make_uint2(rkp[0], rkp[1]);
-        if (!valid) { rkp[0] = 0u; rkp[1] = 0u; }
         float f[5];
-        const bool ok = features_full_h16(v, t, rkp, d.log2_decay, vw_half, hl, half, f);
+        bool ok;
+        if (CLS == 0) {
+            rank_replace_one_h16(v, rkp, (int)(ent.x & 127u), hl, half);
+            if (valid) reinterpret_cast<uint2*>(rank4 + (off0 - lane + id * 32u))[hl] = make_uint2(rkp[0], rkp[1]);
+            if (!valid) { rkp[0] = 0u; rkp[1] = 0u; }
+            ok = features_full_h16(v, t, rkp, d.log2_decay, vw_half, hl, half, f);
+        } else {
+            const int n = valid ? (int)((ent.y >> 9) & 255u) : 1;
+            rank_update_h16(v, rkp, ent.x, valid ? (int)chg_count(ent.x) : 0, valid ? (int)chg_nold(ent.x) : 1, hl, half);
+            if (valid) reinterpret_cast<uint2*>(rank4 + (off0 - lane + id * 32u))[hl] = make_uint2(rkp[0], rkp[1]);
+            if (!valid) { rkp[0] = 0u; rkp[1] = 0u; }
+            ok = features_any_h16(v, t, rkp, n, d.log2_decay, vw_half, hl, half, f);
+        }
         if (valid && hl == 0) {
             if (ok) {
                 float* o = d.obs + (obs0 + (id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u);
@@ -651,7 +666,7 @@ feature_kernel(const __grid_constant__ DevState d) {
             const uint32_t nchg = chg_count(chg);
             const uint32_t n = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
             const bool inc = staged && chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
-            const bool fast = d.use_pair && inc && nchg == 1 && chg_nold(chg) == 128 && n == 128;
+            const bool fast = d.use_pair && inc;   // pair_kernel<.,0> / <.,1> took these
             const bool take = j < Sa && (all || nchg > 0) && !fast;
             const unsigned bal = __ballot_sync(MLB_FULL, take);
             if (take)
