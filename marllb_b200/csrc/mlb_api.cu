@@ -198,12 +198,12 @@ static const void* event_fn(int policy, int Sa) {
     default: return event_fn_r<MLB_POLICY_ALIAS>(R);
     }
 }
-static const void* feature_fn(int Sa) {
+static const void* feature_fn(int Sa, bool small) {
     switch (lanes_r(Sa)) {
-    case 1: return (const void*)feature_kernel<1>;
-    case 2: return (const void*)feature_kernel<2>;
-    case 4: return (const void*)feature_kernel<4>;
-    default: return (const void*)feature_kernel<8>;
+    case 1: return small ? (const void*)feature_kernel<1, true> : (const void*)feature_kernel<1, false>;
+    case 2: return small ? (const void*)feature_kernel<2, true> : (const void*)feature_kernel<2, false>;
+    case 4: return small ? (const void*)feature_kernel<4, true> : (const void*)feature_kernel<4, false>;
+    default: return small ? (const void*)feature_kernel<8, true> : (const void*)feature_kernel<8, false>;
     }
 }
 
@@ -244,7 +244,7 @@ static int launch_cfg(mlb_env* h) {
         return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)",
                     h->ft_smem > h->ev_smem ? h->ft_smem : h->ev_smem);
     cudaError_t e = set_smem(event_fn(c.policy, c.servers_per_agent), h->ev_smem, h->ev_threads, 4 * MLB_EV_MINBLOCKS);
-    if (e == cudaSuccess) e = set_smem(feature_fn(c.servers_per_agent), h->ft_smem, h->ft_threads, 32);
+    if (e == cudaSuccess) e = set_smem(feature_fn(c.servers_per_agent, h->ft_threads <= 128 && !getenv("MLB_FT_BIG")), h->ft_smem, h->ft_threads, h->ft_threads <= 128 ? 48 : 32);
     h->use_pair = h->d.KP == 128 && h->d.K == 128 && c.feature_cache == 1 && !getenv("MLB_NO_PAIR");
     h->d.use_pair = h->use_pair ? 1 : 0;
     h->pr_smem = (size_t)4 * pair_warp_smem_bytes(SP);
@@ -649,7 +649,7 @@ static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_
     }
     if (pe) CK(h, cudaEventRecord(pe[2], st));
     const int ft_blocks = (e1 - e0 + h->epb - 1) / h->epb;
-    CK(h, cudaLaunchKernel(feature_fn(dv.Sa), dim3(ft_blocks), dim3(h->ft_threads), ft_args, h->ft_smem, st));
+    CK(h, cudaLaunchKernel(feature_fn(dv.Sa, h->ft_threads <= 128 && !getenv("MLB_FT_BIG")), dim3(ft_blocks), dim3(h->ft_threads), ft_args, h->ft_smem, st));
     if (pe) CK(h, cudaEventRecord(pe[3], st));
     h->launches += 2;
     return MLB_OK;

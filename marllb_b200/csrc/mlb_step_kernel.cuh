@@ -606,8 +606,11 @@ pair_kernel(const __grid_constant__ DevState d) {
 
 // ---------------------------------------------------------------------------
 // feature_kernel: block = epb envs x A agent warps (the reward needs all agents of an env).
-template <int R>
-__global__ void __launch_bounds__(1024, 1)
+// SMALL: blocks of at most 128 threads (A * epb <= 4 warps), compiled for 48 resident warps per SM: what is left
+// for this kernel once pair_kernel took the incremental entries is a latency chain per warp (list loads, the
+// occasional re-sort, obs reads for the reward), hidden by residency rather than by instruction-level parallelism.
+template <int R, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 128 : 1024, SMALL ? 12 : 1)
 feature_kernel(const __grid_constant__ DevState d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SP = 32 * R;
