@@ -254,7 +254,7 @@ __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint
 // ---------------------------------------------------------------------------
 // event_kernel: R = servers per lane (Sa <= 32*R), SP = 32*R.  Warps are independent.
 #ifndef MLB_EV_MINBLOCKS
-#define MLB_EV_MINBLOCKS 10
+#define MLB_EV_MINBLOCKS 12
 #endif
 template <int POLICY, int R>
 __global__ void __launch_bounds__(128, MLB_EV_MINBLOCKS)
