@@ -832,6 +832,23 @@ static __device__ __noinline__ float warp_features_sorted(const float* __restric
     return feature_of_lane(f, lane_id());
 }
 
+// Ranks in global memory are valid (an incremental kernel updated and stored them) but its float32
+// weighted-percentile decision was not trusted: evaluate from the stored ranks with the float64 tiers,
+// no re-sort.  128-slot stride.  Returns feature `lane` in lanes 0..4.
+static __device__ __noinline__ float warp_features_ranked_exact(const float* __restrict__ vals, const float* __restrict__ tss,
+                                                                const uint8_t* __restrict__ ranks, int n, float now,
+                                                                double decay, float log2_decay, float2* scratch) {
+    const WarpScratch sc{scratch};
+    const int lane = lane_id();
+    float v[4], t[4], f[5];
+    int rk[4];
+    load_slots<4>(vals, lane, v);
+    load_slots<4>(tss, lane, t);
+    load_ranks<4>(ranks, lane, rk);
+    features_ranked<4, false, false>(v, t, rk, n, now, decay, log2_decay, sc, f);
+    return feature_of_lane(f, lane);
+}
+
 // Steady state of the env step: a reservoir of 65..128 valid slots whose ranks live in global
 // memory next to it and in which Algorithm R wrote `nchg` <= 3 slots (7-bit ids in `list`;
 // slots >= n_old are appends of the fill phase) since those ranks were stored.

@@ -596,9 +596,9 @@ pair_kernel(const __grid_constant__ DevState d) {
 #pragma unroll
                 for (int q = 0; q < 5; q++) o[q] = f[q];
             } else {
-                // float32 decision not trusted: hand the reservoir to feature_kernel's re-sort path by
-                // saturating its change count ([E][2][S] layout: metric-major)
-                d.res_chg[chg0 + (id & 1u) * (uint32_t)S + (id >> 1)] = ent.x | (7u << 21);
+                // float32 decision not trusted: hand the reservoir to feature_kernel (n_old = 255 marks "ranks are
+                // valid, decide in float64"; [E][2][S] layout: metric-major)
+                d.res_chg[chg0 + (id & 1u) * (uint32_t)S + (id >> 1)] = (ent.x & 0x00ffffffu) | (255u << 24);
             }
         }
     }
@@ -668,13 +668,14 @@ feature_kernel(const __grid_constant__ DevState d) {
             }
             const uint32_t nchg = chg_count(chg);
             const uint32_t n = cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K;
-            const bool inc = staged && chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
-            const bool fast = d.use_pair && inc;   // pair_kernel<.,0> / <.,1> took these
+            const bool redo = chg_nold(chg) == 255u;   // pair_kernel: ranks valid, float64 decision needed
+            const bool inc = staged && !redo && chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
+            const bool fast = d.use_pair && inc;       // pair_kernel<.,0> / <.,1> took these
             const bool take = j < Sa && (all || nchg > 0) && !fast;
             const unsigned bal = __ballot_sync(MLB_FULL, take);
             if (take)
                 dlist[nd + __popc(bal & ((1u << lane) - 1u))] =
-                    make_uint2(chg, (uint32_t)(j * 2 + m) | (n << 9) | ((inc ? 1u : 0u) << 17));
+                    make_uint2(chg, (uint32_t)(j * 2 + m) | (n << 9) | ((inc ? 1u : 0u) << 17) | ((redo ? 1u : 0u) << 18));
             nd += __popc(bal);
         }
     }
@@ -745,8 +746,13 @@ feature_kernel(const __grid_constant__ DevState d) {
         const uint32_t id = ent.y & 511u;
         const int n = (int)((ent.y >> 9) & 255u);
         const int rid = (int)id * KP;
-        const float mine = warp_features_sorted(res_val + rid, res_ts + rid, res_rank + rid, n, t1, d.decay,
-                                                d.log2_decay, scratch.vw);
+        float mine;
+        if ((ent.y >> 18) & 1u)
+            mine = warp_features_ranked_exact(res_val + rid, res_ts + rid, res_rank + rid, n, t1, d.decay,
+                                              d.log2_decay, scratch.vw);
+        else
+            mine = warp_features_sorted(res_val + rid, res_ts + rid, res_rank + rid, n, t1, d.decay,
+                                        d.log2_decay, scratch.vw);
         if (lane < 5) warp_obs[(id >> 1) * MLB_OBS_COLS + (id & 1u) * 5u + lane] = mine;
     }
     __syncwarp();
