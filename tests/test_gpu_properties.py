@@ -97,3 +97,42 @@ def test_determinism_and_episode_replay():
         o, r, _ = env.step(a)
         assert torch.equal(o, o1) and torch.equal(r, r1)
     env.close()
+
+
+def test_c2_full_size_long_episode_modes_agree_and_flows_are_conserved():
+    """BASELINE config C2 at its full size (4096 envs x 16 servers, K = 128, 32 flows/s, 1000 steps): deep in the
+    episode every touched reservoir is full and takes the half-warp pair kernels; their output must keep
+    agreeing with the re-sorting modes (order statistics and rewards exactly, float32 sums to 2e-6), and
+    the flow accounting must close at the end."""
+    import torch
+    from marllb_b200 import VecLoadBalanceEnv
+    E2, S2, T2 = 4096, 16, 1000
+    envs = []
+    for fc in (1, 2):
+        env = VecLoadBalanceEnv(E2, num_servers=S2, max_steps=T2, feature_cache=fc, action_dtype="uint8")
+        env.set_speeds(np.where(np.arange(S2) % 2 == 0, 1.0, 2.0))
+        env.gen_poisson(32.0, 0.8 * 1.5 * S2 / 32.0, T2 * 0.25 + 1.0, seed=21)
+        env.reset()
+        envs.append(env)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(8)
+    exact, approx = [0, 2, 5, 7, 10], [1, 3, 4, 6, 8, 9]
+    active_sum = torch.zeros((E2, S2), dtype=torch.float64, device="cuda")
+    for k in range(T2):
+        act = torch.randint(0, 3, (E2, S2), generator=g, device="cuda", dtype=torch.uint8)
+        (o1, r1, d1), (o2, r2, d2) = [env.step(act) for env in envs]
+        active_sum += o1[..., 0].double()
+        if k % 25 == 24 or k > T2 - 20:
+            assert torch.equal(o1[..., exact], o2[..., exact]) and torch.equal(r1, r2), k
+            assert torch.allclose(o1[..., approx], o2[..., approx], rtol=2e-6, atol=1e-9), k
+    assert bool(d1.all())
+    env = envs[0]
+    env.check_status()
+    cnt = env.get_state("res_count").astype(np.int64)
+    n_on, drp = env.get_state("n_flow_on").astype(np.int64), env.get_state("dropped").astype(np.int64)
+    cur = env.get_state("arr_cursor").astype(np.int64)[:, 0]
+    assert np.array_equal(cur, cnt[:, 0].sum(1) + n_on.sum(1) + drp.sum(1))        # every flow: done, active or dropped
+    assert np.array_equal(cnt[:, 1], active_sum.cpu().numpy().astype(np.int64))      # one duration sample per active flow per step
+    assert (cnt[:, 0] > 128).mean() > 0.9                                            # reservoirs really are in the replacement regime
+    for e in envs:
+        e.close()
