@@ -360,6 +360,8 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     if (!(c.dt > 0.f) || !(c.decay > 0.0)) return fail(nullptr, MLB_EINVAL, "dt and decay must be positive");
     if ((double)c.num_envs * c.num_agents * c.servers_per_agent * 2.0 * (((c.reservoir_k + 31) & ~31) / 4) >= 4294967296.0)
         return fail(nullptr, MLB_EINVAL, "num_envs * servers * 2 * K/4 must stay below 2^32 (32-bit reservoir offsets)");
+    if ((double)c.num_envs * c.num_agents * c.servers_per_agent * (double)c.queue_cap >= 4294967296.0)
+        return fail(nullptr, MLB_EINVAL, "num_envs * servers * queue_cap must stay below 2^32 (32-bit ring offsets)");
 
     mlb_env* h = new (std::nothrow) mlb_env();
     if (!h) return fail(nullptr, MLB_ENOMEM, "host allocation failed");

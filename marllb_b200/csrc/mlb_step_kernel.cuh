@@ -108,11 +108,12 @@ __device__ __forceinline__ int res_draw_slot(uint32_t cnt, uint32_t& cur, const 
 }
 
 // per-warp view of the global arrays (32-bit offsets below these bases)
+// 32-bit element offsets from the array bases in the kernel parameters (which live in the constant bank, not
+// in registers): the event kernel is register-starved at 48 resident warps per SM
 struct WarpGlobals {
-    float* res_val;     // this agent's reservoirs [Sa][2][KP]
-    float* res_ts;
-    float2* ring;       // [Sa][Q] (arrival, finish)
-    const uint32_t* mt; // replay rows of this agent's servers [Sa][L]
+    uint32_t res4;      // this agent's reservoirs [Sa][2][KP], in units of 4 floats (mlb_create checks the range)
+    uint32_t ring;      // [Sa][Q] (arrival, finish) float2 index
+    uint32_t mt;        // replay rows of this agent's servers [Sa][L]
 };
 
 // ReservoirSampler.add by the owning lane of server j, metric m.
@@ -121,13 +122,14 @@ __device__ __forceinline__ void res_add(const DevState& d, uint32_t* sm, const W
                                         float value, float ts) {
     const uint32_t cnt = sm[(F_CNT0 + m) * SP + j];
     uint32_t c = sm[(F_CUR0 + m) * SP + j];
-    const int slot = res_draw_slot(cnt, c, g.mt + (size_t)j * d.L, d.L, d.K, d.status);
+    const int slot = res_draw_slot(cnt, c, d.mt_table + ((size_t)g.mt + (size_t)j * d.L), d.L, d.K, d.status);
     sm[(F_CUR0 + m) * SP + j] = c;
     sm[(F_CNT0 + m) * SP + j] = cnt + 1;
     if (slot >= 0) {
         const int at = (j * 2 + m) * d.KP + slot;
-        g.res_val[at] = value;
-        g.res_ts[at] = ts;
+        const size_t ga = ((size_t)g.res4 << 2) + (size_t)at;
+        d.res_val[ga] = value;
+        d.res_ts[ga] = ts;
         // remember which slot changed (first three distinct ones; more -> ranks are re-sorted)
         uint32_t w = sm[(F_CHG0 + m) * SP + j];
         const uint32_t nc = chg_count(w);
@@ -283,10 +285,9 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
     const size_t sbase = (size_t)e * S + (size_t)agent * Sa;
     const int seed0 = agent * Sa;                         // replay row = server index in env
     WarpGlobals g;
-    g.res_val = d.res_val + sbase * 2 * d.KP;
-    g.res_ts = d.res_ts + sbase * 2 * d.KP;
-    g.ring = d.ring + sbase * d.Q;
-    g.mt = d.mt_table + (size_t)seed0 * d.L;
+    g.res4 = (uint32_t)(sbase * 2 * (d.KP >> 2));
+    g.ring = (uint32_t)(sbase * d.Q);
+    g.mt = (uint32_t)((size_t)seed0 * d.L);
     const int Q = d.Q;
 
     // ---------------- phase 0: load state, action -> weights -----------------
@@ -308,10 +309,10 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
             sm[F_HEAD * SP + j] = h;
             smf[F_SPEED * SP + j] = d.speed[gi];
             if (n > 0) {
-                const float2 hd = g.ring[j * Q + h];
+                const float2 hd = d.ring[g.ring + j * Q + h];
                 ha[r] = hd.x;
                 hf[r] = hd.y;
-                if (n > 1) prefetch_l2(g.ring + j * Q + (h + 1 == (uint32_t)Q ? 0u : h + 1));
+                if (n > 1) prefetch_l2(d.ring + (g.ring + j * Q + (h + 1 == (uint32_t)Q ? 0u : h + 1)));
             }
             uint32_t act;
             if (d.action_kind == MLB_ACTION_CONTINUOUS_F32) {
@@ -386,7 +387,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                         h = (h + 1 == (uint32_t)Q) ? 0u : h + 1;
                         n -= 1;                                             // src/vpp/lb/lbhash.h:120
                         float2 nx = make_float2(0.f, MLB_INF);
-                        if (n > 0) nx = g.ring[j * Q + h];                  // in flight during the add
+                        if (n > 0) nx = d.ring[g.ring + j * Q + h];          // in flight during the add
                         res_add<SP>(d, sm, g, 0, j, __fsub_rn(fin, arr), fin);  // lbhash.h:122-124
                         arr = nx.x;
                         fin = nx.y;
@@ -427,7 +428,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     const float fin = __fadd_rn(start, __fdiv_rn(wk, smf[F_SPEED * SP + k]));
                     uint32_t pos = sm[F_HEAD * SP + k] + (uint32_t)n;
                     if (pos >= (uint32_t)Q) pos -= (uint32_t)Q;
-                    g.ring[k * Q + pos] = make_float2(a, fin);
+                    d.ring[g.ring + k * Q + pos] = make_float2(a, fin);
                     smf[F_LASTFIN * SP + k] = fin;
                     sm[F_NON * SP + k] = (uint32_t)(n + 1);                 // lbhash.h:142,167
                     uint32_t nsc = 0;
@@ -466,7 +467,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
             for (int q = 0; q < n; q++) {  // lbhash.h:131-135, one sample per active flow per step
                 pos = (pos + 1 == (uint32_t)Q) ? 0u : pos + 1;
                 float nx = 0.f;
-                if (q + 1 < n) nx = g.ring[j * Q + pos].x;                  // in flight during the add
+                if (q + 1 < n) nx = d.ring[g.ring + j * Q + pos].x;          // in flight during the add
                 res_add<SP>(d, sm, g, 1, j, __fsub_rn(t1, arr), t1);
                 arr = nx;
             }
