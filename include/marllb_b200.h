@@ -39,7 +39,15 @@ enum {
 enum { MLB_HOST = 0, MLB_DEVICE = 1 };
 
 /* server-assignment rule per new flow: src/vpp/lb/node.c:393-460 */
-enum { MLB_POLICY_SED = 0, MLB_POLICY_LSQ = 1, MLB_POLICY_ALIAS = 2 };
+enum {
+    MLB_POLICY_SED = 0,   /* argmin (n_flow_on+1)/(1e-9+w) over all servers, first minimum   node.c:393-406 */
+    MLB_POLICY_LSQ = 1,   /* argmin n_flow_on                                                 node.c:419-431 */
+    MLB_POLICY_ALIAS = 2, /* alias-table draw from pre-drawn (bucket, u)                      node.c:442-460 */
+    /* power of two choices: candidates c0 = pre-drawn bucket (new_flow_table[hash]) and
+     * c1 = (c0 + 1) mod servers_per_agent (new_flow_table[hash + 1]); c1 wins on a strictly lower score */
+    MLB_POLICY_SED2 = 3,  /* SED score on the two candidates                                  node.c:408-417 */
+    MLB_POLICY_LSQ2 = 4   /* n_flow_on on the two candidates                                  node.c:433-441 */
+};
 
 /* action encodings: problem-03-rl-environment/src/env.py:334-353 */
 enum {
@@ -48,11 +56,20 @@ enum {
     MLB_ACTION_DISCRETE_U8 = 2   /* same as DISCRETE_I32, one byte per server    */
 };
 
-/* reward metrics: problem-03-rl-environment/src/rewards.py:297-307 */
+/* reward metrics 0-8: problem-03-rl-environment/src/rewards.py:297-307;
+ * 9-14: the original testbed's fair_fn table, src/lb/env.py:73-156 ('var' and 'max' of that table
+ * are MLB_REWARD_VARIANCE and MLB_REWARD_MAX) */
 enum {
     MLB_REWARD_JAIN = 0, MLB_REWARD_VARIANCE, MLB_REWARD_STD, MLB_REWARD_CV,
     MLB_REWARD_MAX, MLB_REWARD_MIN, MLB_REWARD_PRODUCT, MLB_REWARD_RANGE,
-    MLB_REWARD_GINI, MLB_REWARD_COUNT_
+    MLB_REWARD_GINI,
+    MLB_REWARD_FAIR_JAIN,     /* (sum x)^2 / (n sum x^2), 1 when sum x == 0, unclipped   src/lb/env.py:73-85   */
+    MLB_REWARD_FAIR_PRODUCT,  /* prod(x / (max x + 1e-6))                                src/lb/env.py:87-96   */
+    MLB_REWARD_VAR_EXP,       /* exp(-10000 var x)                                       src/lb/env.py:108-115 */
+    MLB_REWARD_VAR_LOG,       /* -log(var x)                                             src/lb/env.py:118-125 */
+    MLB_REWARD_MAX_EXP,       /* exp(-10000 max x)                                       src/lb/env.py:142-149 */
+    MLB_REWARD_MAX_LOG,       /* -log(max x)                                             src/lb/env.py:135-139 */
+    MLB_REWARD_COUNT_
 };
 
 /* state fields readable through mlb_get_state (parity dumps) */

@@ -14,10 +14,13 @@ from . import _build
 ABI_VERSION = 1
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ERNG, EACTION = 0, -1, -2, -3, -4, -5, -6
 HOST, DEVICE = 0, 1
-POLICIES = {"sed": 0, "lsq": 1, "alias": 2}
+POLICIES = {"sed": 0, "lsq": 1, "alias": 2, "sed2": 3, "lsq2": 4}    # node.c:393-460
 ACTION_DISCRETE_I32, ACTION_CONTINUOUS_F32, ACTION_DISCRETE_U8 = 0, 1, 2
 METRICS = {"jain": 0, "variance": 1, "std": 2, "cv": 3, "max": 4, "min": 5,
-           "product": 6, "range": 7, "gini": 8}           # rewards.py:297-307
+           "product": 6, "range": 7, "gini": 8,           # rewards.py:297-307
+           # the original testbed's fair_fn table, src/lb/env.py:152-161
+           "fair_jain": 9, "fair_product": 10, "var": 1, "var_exp": 11, "var_log": 12,
+           "max_exp": 13, "max_log": 14}
 FEATURE_NAMES = ['n_flow_on', 'fct_mean', 'fct_p90', 'fct_std', 'fct_mean_decay', 'fct_p90_decay',
                  'flow_duration_mean', 'flow_duration_p90', 'flow_duration_std',
                  'flow_duration_mean_decay', 'flow_duration_avg_decay']   # env.py:377-381

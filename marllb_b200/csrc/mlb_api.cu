@@ -195,6 +195,8 @@ static const void* event_fn(int policy, int Sa) {
     switch (policy) {
     case MLB_POLICY_SED: return event_fn_r<MLB_POLICY_SED>(R);
     case MLB_POLICY_LSQ: return event_fn_r<MLB_POLICY_LSQ>(R);
+    case MLB_POLICY_SED2: return event_fn_r<MLB_POLICY_SED2>(R);
+    case MLB_POLICY_LSQ2: return event_fn_r<MLB_POLICY_LSQ2>(R);
     default: return event_fn_r<MLB_POLICY_ALIAS>(R);
     }
 }
@@ -352,7 +354,7 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     if (c.servers_per_agent < 1 || c.servers_per_agent > 256) return fail(nullptr, MLB_EINVAL, "1 <= servers_per_agent <= 256 required");
     if (c.reservoir_k < 1 || c.reservoir_k > 128) return fail(nullptr, MLB_EINVAL, "1 <= reservoir_k <= 128 required");
     if (c.queue_cap < 1 || c.queue_cap > 65535) return fail(nullptr, MLB_EINVAL, "1 <= queue_cap <= 65535 required");
-    if (c.policy < 0 || c.policy > MLB_POLICY_ALIAS) return fail(nullptr, MLB_EINVAL, "unknown policy %d", c.policy);
+    if (c.policy < 0 || c.policy > MLB_POLICY_LSQ2) return fail(nullptr, MLB_EINVAL, "unknown policy %d", c.policy);
     if (c.action_kind < 0 || c.action_kind > MLB_ACTION_DISCRETE_U8) return fail(nullptr, MLB_EINVAL, "Unknown action_type: %d", c.action_kind);  // env.py:184
     if (c.action_kind != MLB_ACTION_CONTINUOUS_F32 && (c.n_discrete < 1 || c.n_discrete > 8)) return fail(nullptr, MLB_EINVAL, "1 <= n_discrete <= 8 required");
     if (c.reward_metric < 0 || c.reward_metric >= MLB_REWARD_COUNT_) return fail(nullptr, MLB_EINVAL, "Unsupported metric: %d", c.reward_metric);  // rewards.py:321-323
@@ -495,6 +497,11 @@ int mlb_set_speeds(mlb_env* h, const float* speeds, int64_t n, int loc, void* st
     return MLB_OK;
 }
 
+// policies that consume a pre-drawn bucket per flow (alias also consumes u)
+static inline bool needs_bucket(int policy) {
+    return policy == MLB_POLICY_ALIAS || policy == MLB_POLICY_SED2 || policy == MLB_POLICY_LSQ2;
+}
+
 static int alloc_arrivals(mlb_env* h, int64_t total, bool alias) {
     DevState& d = h->d;
     if (total > h->arr_total || (alias && !h->arr_bucket)) {
@@ -527,8 +534,9 @@ int mlb_load_arrivals(mlb_env* h, const float* time, const float* work, const in
     if (!h || !time || !work || !offsets) return fail(h, MLB_EINVAL, "null argument");
     CK(h, cudaSetDevice(h->device));
     DevState& d = h->d;
-    const bool alias = h->cfg.policy == MLB_POLICY_ALIAS;
-    if (alias && (!bucket || !u)) return fail(h, MLB_EINVAL, "alias policy needs pre-drawn bucket/u arrays");
+    const bool alias = needs_bucket(h->cfg.policy);
+    if (h->cfg.policy == MLB_POLICY_ALIAS && (!bucket || !u)) return fail(h, MLB_EINVAL, "alias policy needs pre-drawn bucket/u arrays");
+    if (alias && !bucket) return fail(h, MLB_EINVAL, "power-of-two policies need a pre-drawn bucket array");
     cudaStream_t st = (cudaStream_t)stream;
     const int EA = d.E * d.A;
     std::vector<int64_t> off(EA + 1);
@@ -553,7 +561,11 @@ int mlb_load_arrivals(mlb_env* h, const float* time, const float* work, const in
         CK(h, cudaMemcpyAsync(h->arr_work, work, (size_t)total * 4, kind, st));
         if (alias) {
             CK(h, cudaMemcpyAsync(h->arr_bucket, bucket, (size_t)total * 4, kind, st));
-            CK(h, cudaMemcpyAsync(h->arr_u, u, (size_t)total * 4, kind, st));
+            if (u) {
+                CK(h, cudaMemcpyAsync(h->arr_u, u, (size_t)total * 4, kind, st));
+            } else {
+                CK(h, cudaMemsetAsync(h->arr_u, 0, (size_t)total * 4, st));
+            }
         }
     }
     CK(h, cudaMemcpyAsync(h->arr_off, h->h_off.data(), (size_t)EA * 8, cudaMemcpyHostToDevice, st));
@@ -573,7 +585,7 @@ int mlb_gen_poisson(mlb_env* h, double rate, double mean_work, double horizon, u
     const int EA = d.E * d.A;
     const double mu = rate * horizon;
     const int cap = (int)(mu + 8.0 * std::sqrt(mu) + 64.0);
-    const bool alias = h->cfg.policy == MLB_POLICY_ALIAS;
+    const bool alias = needs_bucket(h->cfg.policy);
     int rc = alloc_arrivals(h, (int64_t)EA * cap, alias);
     if (rc != MLB_OK) return rc;
     h->h_off.resize(EA);

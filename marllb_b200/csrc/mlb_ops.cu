@@ -59,7 +59,7 @@ __global__ void reward_metric_kernel(int metric, const double* __restrict__ valu
     double r;
     if (n[b] == 0) {
         // empty-list conventions of the bare metric functions (rewards.py:49-50,91-92,...)
-        r = metric == MLB_REWARD_JAIN ? 1.0 : 0.0;
+        r = (metric == MLB_REWARD_JAIN || metric == MLB_REWARD_FAIR_JAIN) ? 1.0 : 0.0;
     } else {
         r = reward_staged<double>(metric, values + (size_t)b * stride, nullptr, n[b]);
     }

@@ -8,7 +8,7 @@
 //   phase 0  action -> weights (env.py:334-353); per-server scalars -> shared memory
 //   phase A  per arrival (time order): retire finished flows (n_flow_on--, fct
 //            sample -> Algorithm-R add, reservoir.py:50-85), choose a server
-//            (SED / LSQ / alias, src/vpp/lb/node.c:393-460) with REDUX argmin,
+//            (SED / LSQ / power-of-two SED2, LSQ2 / alias, src/vpp/lb/node.c:393-460) with REDUX argmin,
 //            push on that server's FIFO ring; the window end is one more
 //            (pseudo-)event of the same loop
 //   phase C  one flow_duration sample per still-active flow, state write-back,
@@ -71,7 +71,7 @@ __host__ __device__ inline size_t feature_warp_smem_bytes(int SP) {
 // that arithmetic: sed_table[a * (Q + 2) + n].
 template <int POLICY>
 __device__ __forceinline__ uint32_t server_score(const DevState& d, int n, uint32_t act) {
-    if (POLICY == MLB_POLICY_SED) {
+    if (POLICY == MLB_POLICY_SED || POLICY == MLB_POLICY_SED2) {
         float sc;
         if (d.action_kind == MLB_ACTION_CONTINUOUS_F32) {
             const double s = (double)(n + 1) / (1e-9 + (double)__uint_as_float(act));
@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t server_score(const DevState& d, int n, uint3
         }
         return f32_orderable(sc);
     } else {
-        return f32_orderable((float)n);  // node.c:419-431
+        return f32_orderable((float)n);  // node.c:419-431 (LSQ), :433-441 (LSQ2)
     }
 }
 
@@ -189,7 +189,7 @@ static __device__ __noinline__ void alias_build(double* prob, int32_t* alias, in
 }
 
 // Reward metric over staged reward-field values (one warp).
-// rewards.py:21-287; float64 throughout like the reference.
+// rewards.py:21-287 and the original fair_fn table src/lb/env.py:73-156; float64 throughout like the reference.
 template <typename T>
 __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint32_t* ra, int S) {
     const int lane = lane_id();
@@ -219,7 +219,22 @@ __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint
         const double j = (sum * sum) / (n * sumsq);
         return fmin(fmax(j, 1.0 / n), 1.0);
     }
+    case MLB_REWARD_FAIR_JAIN: {                        // src/lb/env.py:73-85: no clipping, guard is sum != 0
+        if (sum == 0.0) return 1.0;
+        return (sum * sum) / (n * warp_sum(sumsq));
+    }
+    case MLB_REWARD_FAIR_PRODUCT: {                     // src/lb/env.py:87-96
+        const double den = warp_max(mx) + 1e-6;
+        double p = 1.0;
+        for (int i = lane; i < S; i += 32)
+            if (!ra || ra[i]) p *= (double)rv[i] / den;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p *= __shfl_xor_sync(MLB_FULL, p, o);
+        return p;
+    }
     case MLB_REWARD_MAX: return -warp_max(mx);
+    case MLB_REWARD_MAX_EXP: return exp(-10000.0 * warp_max(mx));   // src/lb/env.py:142-149
+    case MLB_REWARD_MAX_LOG: return -log(warp_max(mx));             // src/lb/env.py:135-139
     case MLB_REWARD_MIN: return warp_min(mn);
     case MLB_REWARD_RANGE: return -(warp_max(mx) - warp_min(mn));
     case MLB_REWARD_PRODUCT: return warp_sum(slog);
@@ -248,6 +263,8 @@ __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint
     const double var = warp_sum(ss) / n;
     if (metric == MLB_REWARD_VARIANCE) return -var;
     if (metric == MLB_REWARD_STD) return -sqrt(var);
+    if (metric == MLB_REWARD_VAR_EXP) return exp(-10000.0 * var);   // src/lb/env.py:108-115
+    if (metric == MLB_REWARD_VAR_LOG) return -log(var);             // src/lb/env.py:118-125
     // MLB_REWARD_CV
     if (mean < eps) return 0.0;
     return -(sqrt(var) / (mean + eps));
@@ -264,6 +281,9 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SP = 32 * R;
     constexpr bool kAlias = (POLICY == MLB_POLICY_ALIAS);
+    // power of two choices (node.c:409-417, 433-441): two candidates from a pre-drawn bucket
+    constexpr bool kPo2 = (POLICY == MLB_POLICY_SED2 || POLICY == MLB_POLICY_LSQ2);
+    constexpr bool kArgmin = !kAlias && !kPo2;      // scan over all servers: scores live in registers
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int A = d.A, Sa = d.Sa, S = d.S;
@@ -329,7 +349,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                 act = (uint32_t)a;                                          // env.py:346
             }
             sm[F_ACT * SP + j] = act;
-            if (!kAlias) sc[r] = server_score<POLICY>(d, n, act);
+            if (kArgmin) sc[r] = server_score<POLICY>(d, n, act);
 #pragma unroll
             for (int m = 0; m < 2; m++) {
                 const size_t c = ((size_t)e * 2 + m) * S + seed0 + j;
@@ -365,9 +385,9 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
         const float awk = idx < an ? __ldcs(d.arr_work + aoff + idx) : 0.f;  // issued together with the times
         int abk = 0;
         float au = 0.f;
-        if (kAlias && lane < nv) {
+        if ((kAlias || kPo2) && lane < nv) {
             abk = __ldcs(d.arr_bucket + aoff + idx);
-            au = __ldcs(d.arr_u + aoff + idx);
+            if (kAlias) au = __ldcs(d.arr_u + aoff + idx);
         }
         const int iters = nv + (last ? 1 : 0);  // the window end is the final pseudo-event
         for (int i = 0; i < iters; i++) {
@@ -396,7 +416,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     ha[r] = arr;
                     sm[F_HEAD * SP + j] = h;
                     sm[F_NON * SP + j] = (uint32_t)n;
-                    if (!kAlias) sc[r] = server_score<POLICY>(d, n, sm[F_ACT * SP + j]);
+                    if (kArgmin) sc[r] = server_score<POLICY>(d, n, sm[F_ACT * SP + j]);
                 }
             }
             __syncwarp();
@@ -407,6 +427,15 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                 const int b = __shfl_sync(MLB_FULL, abk, i);
                 const float u = __shfl_sync(MLB_FULL, au, i);
                 kstar = ((double)u < a_prob[b]) ? b : a_alias[b];           // test_integration.py:57-63
+            } else if (kPo2) {
+                // node.c:409-417 / 433-441: candidates = two consecutive flow-table entries; the second one
+                // replaces the first only when its score is strictly lower.  Every lane evaluates both
+                // (broadcast shared-memory reads), so no reduction is needed.
+                const int c0 = __shfl_sync(MLB_FULL, abk, i);
+                const int c1 = (c0 + 1 == Sa) ? 0 : c0 + 1;
+                const uint32_t s0 = server_score<POLICY>(d, (int)sm[F_NON * SP + c0], sm[F_ACT * SP + c0]);
+                const uint32_t s1 = server_score<POLICY>(d, (int)sm[F_NON * SP + c1], sm[F_ACT * SP + c1]);
+                kstar = s1 < s0 ? c1 : c0;
             } else {
                 uint32_t bkey = sc[0];
                 int bj = lane;
@@ -432,7 +461,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     smf[F_LASTFIN * SP + k] = fin;
                     sm[F_NON * SP + k] = (uint32_t)(n + 1);                 // lbhash.h:142,167
                     uint32_t nsc = 0;
-                    if (!kAlias) nsc = server_score<POLICY>(d, n + 1, sm[F_ACT * SP + k]);
+                    if (kArgmin) nsc = server_score<POLICY>(d, n + 1, sm[F_ACT * SP + k]);
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         if ((k >> 5) == r) {

@@ -37,7 +37,7 @@ def reward_metric_batch(metric: str, values: torch.Tensor, n: torch.Tensor) -> t
 def _one(metric: str, values) -> float:
     v = np.asarray(values, dtype=np.float64).reshape(-1)
     if v.size == 0:
-        return 1.0 if metric == "jain" else 0.0          # rewards.py:49-50,91-92
+        return 1.0 if metric in ("jain", "fair_jain") else 0.0          # rewards.py:49-50,91-92
     t = torch.as_tensor(v).to("cuda").reshape(1, -1)
     n = torch.tensor([v.size], dtype=torch.int32, device="cuda")
     return float(reward_metric_batch(metric, t, n).item())
@@ -88,6 +88,62 @@ def gini_coefficient(values) -> float:
     return _one("gini", values)
 
 
+# ---- the original testbed's reward table (src/lb/env.py:73-161), same names ----------------------
+def calcul_fair_jain(values) -> float:
+    """(sum x)^2 / (n sum x^2), 1.0 when sum x == 0, not clipped (src/lb/env.py:73-85)."""
+    return _one("fair_jain", values)
+
+
+def calcul_fair_product(values) -> float:
+    """prod(x / (max x + 1e-6)) (src/lb/env.py:87-96)."""
+    return _one("fair_product", values)
+
+
+def calcul_fair_variance(values) -> float:
+    """-var (src/lb/env.py:98-105)."""
+    return _one("var", values)
+
+
+def calcul_fair_variance_exp(values, k=10000) -> float:
+    """exp(-k var), k = 10000 (src/lb/env.py:108-115)."""
+    if k != 10000:
+        raise ValueError("only the reference's k = 10000 is built into the kernel")
+    return _one("var_exp", values)
+
+
+def calcul_fair_variance_log(values) -> float:
+    """-log(var) (src/lb/env.py:118-125)."""
+    return _one("var_log", values)
+
+
+def calcul_max(values) -> float:
+    """-max = negative makespan (src/lb/env.py:127-132)."""
+    return _one("max", values)
+
+
+def calcul_max_log(values) -> float:
+    """-log(max) (src/lb/env.py:135-139)."""
+    return _one("max_log", values)
+
+
+def calcul_max_exp(values, k=10000) -> float:
+    """exp(-k max), k = 10000 (src/lb/env.py:142-149)."""
+    if k != 10000:
+        raise ValueError("only the reference's k = 10000 is built into the kernel")
+    return _one("max_exp", values)
+
+
+fair_fn = {                                                # src/lb/env.py:152-161
+    'jain': calcul_fair_jain, 'product': calcul_fair_product, 'var': calcul_fair_variance,
+    'var_exp': calcul_fair_variance_exp, 'var_log': calcul_fair_variance_log,
+    'max': calcul_max, 'max_exp': calcul_max_exp, 'max_log': calcul_max_log,
+}
+
+
+def calcul_fair(values, type):                             # src/lb/env.py:158-161
+    return fair_fn[type](values)
+
+
 class RewardFunction:
     """Configurable reward (rewards.py:290-388): same attributes, `compute(obs_dict)` contract."""
 
@@ -95,6 +151,10 @@ class RewardFunction:
         'jain': jain_fairness, 'variance': variance_fairness, 'std': std_fairness,
         'cv': coefficient_of_variation, 'max': max_min_fairness, 'min': min_max_fairness,
         'product': product_fairness, 'range': range_fairness, 'gini': gini_coefficient,
+        # beyond rewards.py:297-307: the original testbed's table (src/lb/env.py:152-161) under distinct names
+        'fair_jain': calcul_fair_jain, 'fair_product': calcul_fair_product, 'var': calcul_fair_variance,
+        'var_exp': calcul_fair_variance_exp, 'var_log': calcul_fair_variance_log,
+        'max_exp': calcul_max_exp, 'max_log': calcul_max_log,
     }
 
     def __init__(self, metric: str = 'jain', reward_field: str = 'flow_duration_avg_decay'):

@@ -147,7 +147,8 @@ class VecLoadBalanceEnv:
 
     def load_arrivals(self, streams):
         """streams: list over (env, agent) -- env-major -- of dicts with float32 arrays
-        'time', 'work' and, for the alias policy, 'bucket' (int32) and 'u' (float32)."""
+        'time', 'work' and, for the alias policy, 'bucket' (int32) and 'u' (float32); the power-of-two
+        policies 'sed2' / 'lsq2' need 'bucket' only."""
         EA = self.num_envs * self.num_agents
         if len(streams) != EA:
             raise ValueError(f"expected {EA} arrival streams (num_envs*num_agents), got {len(streams)}")
@@ -159,6 +160,8 @@ class VecLoadBalanceEnv:
         bucket = u = None
         if self.policy == "alias":
             bucket, u = cat("bucket", np.int32), cat("u", np.float32)
+        elif self.policy in ("sed2", "lsq2"):
+            bucket = cat("bucket", np.int32)
         self.load_arrivals_csr(time, work, off, bucket, u)
 
     def load_arrivals_csr(self, time, work, offsets, bucket=None, u=None):
@@ -166,7 +169,9 @@ class VecLoadBalanceEnv:
         work = np.ascontiguousarray(work, np.float32)
         offsets = np.ascontiguousarray(offsets, np.int64)
         if bucket is not None:
-            bucket, u = np.ascontiguousarray(bucket, np.int32), np.ascontiguousarray(u, np.float32)
+            bucket = np.ascontiguousarray(bucket, np.int32)
+        if u is not None:
+            u = np.ascontiguousarray(u, np.float32)
         check(self._L.mlb_load_arrivals(self._h, _nptr(time), _nptr(work), _nptr(bucket), _nptr(u),
                                         _nptr(offsets), _lib.HOST, self._stream()), self._h)
 
@@ -178,7 +183,7 @@ class VecLoadBalanceEnv:
         n = C.c_int64()
         check(self._L.mlb_get_arrivals(self._h, env, agent, None, None, None, None, 0, C.byref(n)), self._h)
         t, w = np.empty(n.value, np.float32), np.empty(n.value, np.float32)
-        b = np.empty(n.value, np.int32) if self.policy == "alias" else None
+        b = np.empty(n.value, np.int32) if self.policy in ("alias", "sed2", "lsq2") else None
         u = np.empty(n.value, np.float32) if self.policy == "alias" else None
         check(self._L.mlb_get_arrivals(self._h, env, agent, _nptr(t), _nptr(w), _nptr(b), _nptr(u),
                                        n.value, C.byref(n)), self._h)

@@ -343,6 +343,35 @@ double ora_reward_metric(int metric, const double *v, int n) {
             for (int j = 0; j < n; j++) ds += fabs(v[i] - v[j]);
         return -(ds / (2.0 * n * n * mean));
     }
+    /* ---- original testbed rewards, src/lb/env.py:73-156 (fair_fn); Python's builtin sum() is a
+     * strictly sequential float64 sum, np.prod a sequential product, np.var as above ---- */
+    case ORA_FAIR_JAIN: {                                                  /* src/lb/env.py:73-85 */
+        if (n == 0) return 1.0;
+        double s = 0.0, s2 = 0.0;
+        for (int i = 0; i < n; i++) s += v[i];
+        if (s == 0.0) return 1.0;
+        for (int i = 0; i < n; i++) s2 += v[i] * v[i];
+        return (s * s) / ((double)n * s2);
+    }
+    case ORA_FAIR_PRODUCT: {                                               /* src/lb/env.py:87-96 */
+        if (n == 0) return 0.0;
+        double m = v[0], p = 1.0;
+        for (int i = 1; i < n; i++) if (v[i] > m) m = v[i];
+        for (int i = 0; i < n; i++) p *= v[i] / (m + 1e-6);
+        return p;
+    }
+    case ORA_VAR_EXP:                                                      /* src/lb/env.py:108-115, k = 10000 */
+        if (n == 0) return 0.0;
+        return exp(-10000.0 * np_var(v, n));
+    case ORA_VAR_LOG:                                                      /* src/lb/env.py:118-125 */
+        if (n == 0) return 0.0;
+        return -log(np_var(v, n));
+    case ORA_MAX_EXP: case ORA_MAX_LOG: {                                  /* src/lb/env.py:135-149 */
+        if (n == 0) return 0.0;
+        double m = v[0];
+        for (int i = 1; i < n; i++) if (v[i] > m) m = v[i];
+        return metric == ORA_MAX_EXP ? exp(-10000.0 * m) : -log(m);
+    }
     default:
         return NAN;
     }
@@ -561,6 +590,20 @@ int64_t ora_env_step(ora_env *e, const void *action, float *obs, double *reward,
                     float s = (float)e->n_on[j];
                     if (j == lo || s < bs) { best = j; bs = s; }
                 }
+            } else if (c->policy == ORA_SED2 || c->policy == ORA_LSQ2) {   /* node.c:408-417, 433-441: power of two */
+                /* asindex0 = new_flow_table[hash & mask], asindex1 = new_flow_table[(hash+1) & mask]:
+                 * [B] the pre-drawn bucket stands for the hash and the table is the identity mod Sa */
+                const int c0 = e->a_bucket[i][cur];
+                const int c1 = (c0 + 1 == Sa) ? 0 : c0 + 1;
+                float s0, s1;
+                if (c->policy == ORA_SED2) {
+                    s0 = (float)((double)(e->n_on[lo + c0] + 1) / (1e-9 + (double)w[lo + c0]));
+                    s1 = (float)((double)(e->n_on[lo + c1] + 1) / (1e-9 + (double)w[lo + c1]));
+                } else {
+                    s0 = (float)e->n_on[lo + c0];
+                    s1 = (float)e->n_on[lo + c1];
+                }
+                best = lo + (s1 < s0 ? c1 : c0);
             } else {                                                       /* node.c:442-460; rule of test_integration.py:57-63 */
                 int b = e->a_bucket[i][cur];
                 double u = (double)e->a_u[i][cur];

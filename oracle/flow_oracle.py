@@ -14,8 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libflow_oracle.so")
 
-METRICS = ["jain", "variance", "std", "cv", "max", "min", "product", "range", "gini"]
-POLICIES = ["sed", "lsq", "alias"]
+METRICS = ["jain", "variance", "std", "cv", "max", "min", "product", "range", "gini",
+           "fair_jain", "fair_product", "var_exp", "var_log", "max_exp", "max_log"]   # src/lb/env.py:152-161
+POLICIES = ["sed", "lsq", "alias", "sed2", "lsq2"]
 FIELDS = ['n_flow_on', 'fct_mean', 'fct_p90', 'fct_std', 'fct_mean_decay', 'fct_p90_decay',
           'flow_duration_mean', 'flow_duration_p90', 'flow_duration_std',
           'flow_duration_mean_decay', 'flow_duration_avg_decay']   # env.py:377-381

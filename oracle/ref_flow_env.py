@@ -46,7 +46,7 @@ import ref_import
 
 f32 = np.float32
 
-POLICIES = ("sed", "lsq", "alias")
+POLICIES = ("sed", "lsq", "alias", "sed2", "lsq2")
 
 
 def build_alias_table_ref(p):
@@ -147,6 +147,17 @@ class RefFlowEnv:
                     best, best_score = j, score
             return best
         b = int(self.arrivals[agent]["bucket"][k_flow])
+        if self.policy in ("sed2", "lsq2"):
+            # power of two choices [R node.c:408-417, 433-441]: asindex0 = new_flow_table[hash & mask],
+            # asindex1 = new_flow_table[(hash + 1) & mask]; asindex1 wins on a strictly lower score.
+            # [B] the pre-drawn bucket plays the hash, the flow table is the identity modulo Sa.
+            c0, c1 = lo + b, lo + (b + 1) % self.Sa
+            if self.policy == "sed2":
+                s0 = f32((int(n_on[c0]) + 1) / (1e-9 + float(w[c0])))
+                s1 = f32((int(n_on[c1]) + 1) / (1e-9 + float(w[c1])))
+            else:
+                s0, s1 = f32(int(n_on[c0])), f32(int(n_on[c1]))
+            return c1 if s1 < s0 else c0
         u = float(f32(self.arrivals[agent]["u"][k_flow]))
         prob, alias = self._alias[agent][b]
         return lo + (b if u < prob else int(alias))                      # [R test_integration.py:57-63]

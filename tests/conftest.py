@@ -49,7 +49,7 @@ def flow_case(name):
 
 
 FLOW_CASES = ["flow_c1_trace", "flow_sed_a2s3", "flow_lsq_s5", "flow_alias_a2s4", "flow_cont_s4",
-              "flow_drops_q4", "flow_k8_s4", "flow_s40_var", "flow_a4s16_gini"]
+              "flow_drops_q4", "flow_k8_s4", "flow_s40_var", "flow_a4s16_gini", "flow_sed2_a2s5", "flow_lsq2_s36"]
 
 
 def env_kwargs(cfg):

@@ -117,6 +117,41 @@ def gold_rewards():
     save("rewards_cases", values=vals, n=ns, out=out)
 
 
+def gold_fair_fn():
+    """The original testbed's reward table (src/lb/env.py:73-161).  That module cannot be imported here
+    (it needs gym 0.17 and a live /dev/shm region at import), so the `calcul_*` function definitions and
+    the `fair_fn` dict are compiled out of the reference source, unmodified, with ast."""
+    import ast
+    path = os.path.join(ref_import.REF_ROOT, "src", "lb", "env.py")
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body
+            if (isinstance(n, ast.FunctionDef) and n.name.startswith("calcul_"))
+            or (isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "fair_fn")]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    ref_fn = ns["fair_fn"]
+    names = ["jain", "product", "var", "var_exp", "var_log", "max", "max_exp", "max_log"]
+    assert sorted(names) == sorted(ref_fn)
+    rng = np.random.RandomState(11)
+    cases = [np.array(x, np.float64) for x in
+             ([10, 10, 10, 10], [40, 0, 0, 0], [15, 10, 10, 5], [0, 0, 0, 0], [7.5], [1e-4, 2e-4, 1.5e-4])]
+    for i in range(90):
+        n = rng.randint(1, 257)
+        scale = [3.0, 1e-2, 1e-3][i % 3]          # exp(-10000 x) is only non-zero for small x
+        cases.append(rng.exponential(scale, n))
+    L = max(len(c) for c in cases)
+    vals = np.zeros((len(cases), L))
+    nn = np.array([len(c) for c in cases], np.int32)
+    out = np.zeros((len(cases), len(names)))
+    with np.errstate(all="ignore"):
+        for i, c in enumerate(cases):
+            vals[i, :len(c)] = c
+            for m, name in enumerate(names):
+                out[i, m] = float(ref_fn[name](c))
+    assert out[0, 0] == 1.0 and out[1, 0] == 0.25 and out[3, 0] == 1.0
+    save("fair_fn_cases", values=vals, n=nn, out=out, names=np.array(names))
+
+
 def gold_alias():
     rng = np.random.RandomState(2)
     ps, probs, aliases, ns = [], [], [], []
@@ -224,7 +259,8 @@ def synth(rng, A, rate, horizon, mean_work, Sa):
     return arr
 
 
-def gold_flow():
+def gold_flow(only=None):
+    """`only`: optional list of fixture names to (re)generate."""
     # C1: unittest topology, 1 LB x 4 servers, data/trace rate_500, first 60 s (SURVEY 8d)
     steps = 240
     t, n = load_trace(os.path.join(REF, "data/trace/poisson_for_loop/rate_500.csv"), steps * 0.25)
@@ -233,9 +269,12 @@ def gold_flow():
     v0 = rate * float(work.mean()) / (6 * 0.8)              # rho ~= 0.8 over speeds [1,1,2,2]*v0
     speeds = (np.array([1, 1, 2, 2]) * v0).astype(np.float32)
     actions = np.random.RandomState(0).randint(0, 3, (steps, 4)).astype(np.int32)
-    run_flow("flow_c1_trace", 1, 4, steps, [{"time": t.astype(np.float32), "work": work}], speeds, actions)
+    if only is None or "flow_c1_trace" in only:
+        run_flow("flow_c1_trace", 1, 4, steps, [{"time": t.astype(np.float32), "work": work}], speeds, actions)
 
     def case(name, A, Sa, steps, rate, mean_work, speeds, seed, **kw):
+        if only is not None and name not in only:
+            return
         rng = np.random.RandomState(seed)
         arr = synth(rng, A, rate, steps * 0.25 + 1, mean_work, Sa)
         S = A * Sa
@@ -253,15 +292,20 @@ def gold_flow():
     case("flow_k8_s4", 1, 4, 60, 100, 0.03, [1, 1, 2, 2], 6, reservoir_k=8)
     case("flow_s40_var", 1, 40, 30, 160, 0.4, [1, 2] * 20, 8, reward_metric="variance", reward_field="fct_mean")
     case("flow_a4s16_gini", 4, 16, 24, 64, 0.4, [1, 2] * 32, 9, reward_metric="gini")
+    # power of two choices (node.c:408-417, 433-441)
+    case("flow_sed2_a2s5", 2, 5, 40, 70, 0.05, [1, 2, 1, 2, 2] * 2, 10, policy="sed2")
+    case("flow_lsq2_s36", 1, 36, 30, 200, 0.25, [1, 2] * 18, 12, policy="lsq2", reward_metric="max",
+         reward_field="fct_mean")
 
 
 if __name__ == "__main__":
     gold_reservoir()
     gold_features()
     gold_rewards()
+    gold_fair_fn()
     gold_alias()
     gold_legacy()
-    gold_flow()
+    gold_flow(sys.argv[1:] or None)
     meta = {"numpy": np.__version__, "python": sys.version.split()[0],
             "reference": REF, "generator": "tests/golden/make_golden.py"}
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
