@@ -232,6 +232,13 @@ int mlb_reward_metric(int metric, const double *values, const int32_t *n, int32_
 int mlb_legacy_seed(uint32_t *mt_state, const uint32_t *seeds, int32_t E, void *stream);
 int mlb_legacy_obs(uint32_t *mt_state, int32_t E, int32_t S, float *obs, void *stream);
 
+/* Batched _normalize_observation (env.py:450-470): running mean / std update and normalisation of
+ * n = E*S*11 observation entries in float64, the reference's arithmetic operation for operation
+ * (count = obs_count AFTER the increment of env.py:461, >= 1; mean starts at 0, std at 1: env.py:152-153).
+ * mean, std are updated in place; out [n] double = (obs - mean) / (std + 1e-8).  Device pointers. */
+int mlb_normalize_obs(const float *obs, double *mean, double *std, int64_t count, double *out,
+                      int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,36 @@ int mlb_sac_alpha_loss(const float *logp, const float *log_alpha, float target_e
                        float *d_log_alpha, double *loss, int32_t M, void *stream);
 int mlb_exp_scalar(const float *x, float *y, void *stream);                                  /* y[0] = exp(x[0]) */
 
+/* ---- original-paper agents (src/lb/sac_qmix.py:195-460, src/lb/sac_gru_discrete.py:128-359):
+ * multi-head categorical outputs, rows of n <= 64 classes ---- */
+/* F.softmax(x, dim=-1) over rows [rows][n] (sac_qmix.py:250, sac_gru_discrete.py:189) and its backward
+ * dx = y * (dy - sum_k dy_k y_k) */
+int mlb_softmax_forward(const float *x, float *y, int64_t rows, int32_t n, void *stream);
+int mlb_softmax_backward(const float *y, const float *dy, float *dx, int64_t rows, int32_t n, void *stream);
+/* torch.cat([state, one_hot(last_action)], -1) (sac_qmix.py:231-236): out [rows][F + heads*n] */
+int mlb_concat_onehot(const float *x, const int32_t *action, float *out, int64_t rows, int32_t F,
+                      int32_t heads, int32_t n, void *stream);
+/* Categorical(p) over rows: class = given[r] if given, else inverse-CDF of u[r] if u, else argmax (first
+ * maximum, np.argmax).  Nullable outputs: action [rows], logp [rows] = log p[class], psel [rows] = p[class]
+ * (sac_qmix.py:268-274, 431-432; sac_gru_discrete.py:201-209). */
+int mlb_categorical(const float *p, const float *u, const int32_t *given, int32_t *action, float *logp,
+                    float *psel, int64_t rows, int32_t n, void *stream);
+/* d/dlogits of sum_r g[r/group] * log p[r][action[r]]: dlogits[r][k] = g * ((k==a_r) - p[r][k]) */
+int mlb_logprob_backward(const float *p, const int32_t *action, const float *g, float *dlogits,
+                         int64_t rows, int32_t n, int32_t group, void *stream);
+/* backward of the gather of the chosen class: d[r][k] = (k == action[r]) ? g[r] : 0 */
+int mlb_scatter_class(const float *g, const int32_t *action, float *d, int64_t rows, int32_t n, void *stream);
+/* QMix_Trainer._build_td_lambda_targets (sac_qmix.py:449-460) over [B][T]:
+ * ret[:,T-1] = tq[:,T-1]; ret[:,t] = lambda*gamma*ret[:,t+1] + (r[:,t] + (1-lambda)*gamma*tq[:,t+1]) */
+int mlb_td_lambda_targets(const float *reward, const float *target_q, float *ret, float gamma,
+                          float td_lambda, int32_t B, int32_t T, void *stream);
+/* reward normalisation of SAC_Trainer.update (sac_gru_discrete.py:299-300) over [B][T]:
+ * out = scale * (r - mean_b r) / (std_b r + 1e-6), unbiased std over the batch dimension (B >= 2) */
+int mlb_reward_normalize(const float *reward, float *out, float scale, int32_t B, int32_t T, void *stream);
+/* discrete SAC critic target (sac_gru_discrete.py:316-319): y = r + gamma*(min(q1n,q2n) - alpha*logp_next) */
+int mlb_dsac_q_target(const float *reward, const float *q1n, const float *q2n, const float *logp_next,
+                      const float *alpha, float gamma, float *y, int32_t M, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,24 @@ __global__ void reward_metric_kernel(int metric, const double* __restrict__ valu
     if ((threadIdx.x & 31) == 0) out[b] = r;
 }
 
+// env.py:461-468, elementwise in float64.  No fused multiply-adds: numpy rounds every operation.
+__global__ void normalize_obs_kernel(const float* __restrict__ obs, double* __restrict__ mean,
+                                     double* __restrict__ sd, double count, double* __restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = (double)obs[i];
+        const double m0 = mean[i], s0 = sd[i];
+        const double delta = __dsub_rn(x, m0);                                   // :462
+        const double m1 = __dadd_rn(m0, __ddiv_rn(delta, count));                // :463
+        const double delta2 = __dsub_rn(x, m1);                                  // :464
+        const double num = __dadd_rn(__dmul_rn(__dmul_rn(s0, s0), count - 1.0), __dmul_rn(delta, delta2));
+        const double s1 = __dsqrt_rn(fmax(__ddiv_rn(num, count), 1e-8));         // :465
+        mean[i] = m1;
+        sd[i] = s1;
+        out[i] = __ddiv_rn(__dsub_rn(x, m1), __dadd_rn(s1, 1e-8));               // :468
+    }
+}
+
 // ---- device MT19937, state [E][625] (624 words + position) -------------------
 __device__ __forceinline__ uint32_t mt_next(uint32_t* st) {
     uint32_t pos = st[624];
@@ -173,6 +191,18 @@ int mlb_reward_metric(int metric, const double* values, const int32_t* n, int32_
     if (B == 0) return MLB_OK;
     const int wpb = 4;
     reward_metric_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(metric, values, n, B, stride, out);
+    CKL();
+    return MLB_OK;
+}
+
+int mlb_normalize_obs(const float* obs, double* mean, double* std, int64_t count, double* out, int64_t n,
+                      void* stream) {
+    if (!obs || !mean || !std || !out || count < 1 || n < 0) return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    const int threads = 256;
+    const int64_t want = (n + threads - 1) / threads;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);                 // grid-stride, 16 blocks per SM
+    normalize_obs_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(obs, mean, std, (double)count, out, n);
     CKL();
     return MLB_OK;
 }

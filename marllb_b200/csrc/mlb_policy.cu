@@ -494,6 +494,144 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Original-paper agents (src/lb/sac_qmix.py, src/lb/sac_gru_discrete.py): multi-head categorical
+// outputs.  One thread per row of n <= 64 classes (n = discretised weight levels per head).
+__global__ void softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* xr = x + r * n;
+    float mx = xr[0];
+    for (int k = 1; k < n; k++) mx = fmaxf(mx, xr[k]);
+    float s = 0.f;
+    for (int k = 0; k < n; k++) s += expf(xr[k] - mx);
+    const float inv = 1.f / s;
+    for (int k = 0; k < n; k++) y[r * n + k] = expf(xr[k] - mx) * inv;
+}
+
+// dx = y * (dy - sum_k dy_k y_k)
+__global__ void softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx,
+                                   int64_t rows, int n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float dot = 0.f;
+    for (int k = 0; k < n; k++) dot = fmaf(dy[r * n + k], y[r * n + k], dot);
+    for (int k = 0; k < n; k++) dx[r * n + k] = y[r * n + k] * (dy[r * n + k] - dot);
+}
+
+// out[row] = [ x[row][0:F] | one_hot(action[row][h], n) for h < heads ]   (sac_qmix.py:231-236)
+__global__ void concat_onehot_kernel(const float* __restrict__ x, const int32_t* __restrict__ action, float* __restrict__ out,
+                                     int64_t rows, int F, int heads, int n) {
+    const int W = F + heads * n;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * W) return;
+    const int64_t r = i / W;
+    const int c = (int)(i - r * W);
+    float v;
+    if (c < F) {
+        v = x[r * F + c];
+    } else {
+        const int h = (c - F) / n, k = (c - F) - h * n;
+        v = action[r * heads + h] == k ? 1.f : 0.f;
+    }
+    out[i] = v;
+}
+
+// Categorical over rows of probabilities: inverse-CDF draw from a caller-supplied uniform (u nullable: argmax,
+// first maximum like np.argmax), log-probability of the drawn class, gather of a given class.
+__global__ void categorical_kernel(const float* __restrict__ p, const float* __restrict__ u, const int32_t* __restrict__ given,
+                                   int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ psel,
+                                   int64_t rows, int n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* pr = p + r * n;
+    int a;
+    if (given) {
+        a = given[r];
+    } else if (u) {
+        float tot = 0.f;
+        for (int k = 0; k < n; k++) tot += pr[k];
+        const float cut = u[r] * tot;
+        float c = 0.f;
+        a = n - 1;
+        for (int k = 0; k < n; k++) {
+            c += pr[k];
+            if (cut < c) { a = k; break; }
+        }
+    } else {
+        a = 0;
+        for (int k = 1; k < n; k++) if (pr[k] > pr[a]) a = k;
+    }
+    if (action) action[r] = a;
+    if (logp) logp[r] = logf(pr[a]);                       // Categorical.log_prob
+    if (psel) psel[r] = pr[a];                             // torch.gather(agent_outs, -1, action)
+}
+
+// gradient of sum_r g[r/group] * log p[r][a_r] w.r.t. the LOGITS of the softmax that produced p:
+// dlogits[r][k] = g * ((k == a_r) - p[r][k]); `group` consecutive rows (the heads of one sample) share one g
+__global__ void logprob_bwd_kernel(const float* __restrict__ p, const int32_t* __restrict__ action, const float* __restrict__ g,
+                                   float* __restrict__ dlogits, int64_t rows, int n, int group) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * n) return;
+    const int64_t r = i / n;
+    const int k = (int)(i - r * n);
+    dlogits[i] = g[r / group] * ((action[r] == k ? 1.f : 0.f) - p[i]);
+}
+
+// scatter of per-row gradients into the class that was chosen: d[r][k] = (k == a_r) ? g[r] : 0
+__global__ void scatter_class_kernel(const float* __restrict__ g, const int32_t* __restrict__ action, float* __restrict__ d,
+                                     int64_t rows, int n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * n) return;
+    const int64_t r = i / n;
+    d[i] = action[r] == (int)(i - r * n) ? g[r] : 0.f;
+}
+
+// sac_qmix.py:449-460 _build_td_lambda_targets: backward recursion over the sequence, one thread per batch row
+__global__ void td_lambda_kernel(const float* __restrict__ reward, const float* __restrict__ tq, float* __restrict__ ret,
+                                 float gamma, float lam, int B, int T) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* r = reward + (int64_t)b * T;
+    const float* q = tq + (int64_t)b * T;
+    float* o = ret + (int64_t)b * T;
+    float nxt = q[T - 1];
+    o[T - 1] = nxt;
+    for (int t = T - 2; t >= 0; t--) {
+        // torch evaluates td_lambda * gamma (Python floats, double) first, then float32 tensor ops
+        const float v = __fadd_rn(__fmul_rn((float)((double)lam * (double)gamma), nxt),
+                                  __fadd_rn(r[t], __fmul_rn((float)((1.0 - (double)lam) * (double)gamma), q[t + 1])));
+        o[t] = v;
+        nxt = v;
+    }
+}
+
+// sac_gru_discrete.py:299-300: r <- scale * (r - mean_b r) / (std_b r + 1e-6) per sequence position
+// (unbiased std over the batch dimension); one thread per position t
+__global__ void reward_norm_kernel(const float* __restrict__ r, float* __restrict__ out, float scale, int B, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double s = 0.0;
+    for (int b = 0; b < B; b++) s += (double)r[(int64_t)b * T + t];
+    const double mean = s / B;
+    double ss = 0.0;
+    for (int b = 0; b < B; b++) {
+        const double d = (double)r[(int64_t)b * T + t] - mean;
+        ss += d * d;
+    }
+    const float sd = (float)sqrt(ss / (B - 1));
+    const float mf = (float)mean;
+    for (int b = 0; b < B; b++) out[(int64_t)b * T + t] = scale * (r[(int64_t)b * T + t] - mf) / (sd + 1e-6f);
+}
+
+// sac_gru_discrete.py:316-319: y = r + gamma * (min(q1, q2) - alpha * logp_next)   (no done flag in that trainer)
+__global__ void dsac_q_target_kernel(const float* __restrict__ r, const float* __restrict__ q1n, const float* __restrict__ q2n,
+                                     const float* __restrict__ lp, const float* __restrict__ alpha, float gamma,
+                                     float* __restrict__ y, int M) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) y[i] = r[i] + gamma * (fminf(q1n[i], q2n[i]) - alpha[0] * lp[i]);
+}
+
 extern "C" {
 
 int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_bs,
@@ -727,6 +865,72 @@ int mlb_sac_alpha_loss(const float* logp, const float* log_alpha, float target_e
 int mlb_exp_scalar(const float* x, float* y, void* stream) {
     if (!x || !y) return MLB_EINVAL;
     exp_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(x, y);
+    return ok();
+}
+
+int mlb_softmax_forward(const float* x, float* y, int64_t rows, int32_t n, void* stream) {
+    if (!x || !y || n < 1 || n > 64) return MLB_EINVAL;
+    if (rows == 0) return MLB_OK;
+    softmax_fwd_kernel<<<nblk(rows, 128), 128, 0, (cudaStream_t)stream>>>(x, y, rows, n);
+    return ok();
+}
+
+int mlb_softmax_backward(const float* y, const float* dy, float* dx, int64_t rows, int32_t n, void* stream) {
+    if (!y || !dy || !dx || n < 1 || n > 64) return MLB_EINVAL;
+    if (rows == 0) return MLB_OK;
+    softmax_bwd_kernel<<<nblk(rows, 128), 128, 0, (cudaStream_t)stream>>>(y, dy, dx, rows, n);
+    return ok();
+}
+
+int mlb_concat_onehot(const float* x, const int32_t* action, float* out, int64_t rows, int32_t F, int32_t heads,
+                      int32_t n, void* stream) {
+    if (!x || !action || !out || F < 0 || heads < 1 || n < 1) return MLB_EINVAL;
+    if (rows == 0) return MLB_OK;
+    concat_onehot_kernel<<<nblk(rows * (F + heads * n), 256), 256, 0, (cudaStream_t)stream>>>(x, action, out, rows, F, heads, n);
+    return ok();
+}
+
+int mlb_categorical(const float* p, const float* u, const int32_t* given, int32_t* action, float* logp, float* psel,
+                    int64_t rows, int32_t n, void* stream) {
+    if (!p || n < 1) return MLB_EINVAL;
+    if (rows == 0) return MLB_OK;
+    categorical_kernel<<<nblk(rows, 128), 128, 0, (cudaStream_t)stream>>>(p, u, given, action, logp, psel, rows, n);
+    return ok();
+}
+
+int mlb_logprob_backward(const float* p, const int32_t* action, const float* g, float* dlogits, int64_t rows,
+                         int32_t n, int32_t group, void* stream) {
+    if (!p || !action || !g || !dlogits || n < 1 || group < 1) return MLB_EINVAL;
+    if (rows == 0) return MLB_OK;
+    logprob_bwd_kernel<<<nblk(rows * n, 256), 256, 0, (cudaStream_t)stream>>>(p, action, g, dlogits, rows, n, group);
+    return ok();
+}
+
+int mlb_scatter_class(const float* g, const int32_t* action, float* d, int64_t rows, int32_t n, void* stream) {
+    if (!g || !action || !d || n < 1) return MLB_EINVAL;
+    if (rows == 0) return MLB_OK;
+    scatter_class_kernel<<<nblk(rows * n, 256), 256, 0, (cudaStream_t)stream>>>(g, action, d, rows, n);
+    return ok();
+}
+
+int mlb_td_lambda_targets(const float* reward, const float* target_q, float* ret, float gamma, float td_lambda,
+                          int32_t B, int32_t T, void* stream) {
+    if (!reward || !target_q || !ret || B < 1 || T < 1) return MLB_EINVAL;
+    td_lambda_kernel<<<nblk(B, 128), 128, 0, (cudaStream_t)stream>>>(reward, target_q, ret, gamma, td_lambda, B, T);
+    return ok();
+}
+
+int mlb_reward_normalize(const float* reward, float* out, float scale, int32_t B, int32_t T, void* stream) {
+    if (!reward || !out || B < 2 || T < 1) return MLB_EINVAL;
+    reward_norm_kernel<<<nblk(T, 64), 64, 0, (cudaStream_t)stream>>>(reward, out, scale, B, T);
+    return ok();
+}
+
+int mlb_dsac_q_target(const float* reward, const float* q1n, const float* q2n, const float* logp_next,
+                      const float* alpha, float gamma, float* y, int32_t M, void* stream) {
+    if (!reward || !q1n || !q2n || !logp_next || !alpha || !y) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    dsac_q_target_kernel<<<nblk(M, 256), 256, 0, (cudaStream_t)stream>>>(reward, q1n, q2n, logp_next, alpha, gamma, y, M);
     return ok();
 }
 

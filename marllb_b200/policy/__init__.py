@@ -5,3 +5,4 @@ runs in marllb_b200/csrc/mlb_policy.cu through include/marllb_b200_policy.h.
 """
 from .qmix import AgentQNetwork, EpisodeBuffer, QMixingNetwork, QMIXAgent, VDNMixingNetwork  # noqa: F401
 from .sac import PolicyNetwork, QNetwork, ReplayBuffer, SAC_GRU_Agent  # noqa: F401
+from . import paper  # noqa: F401  (original-paper agents: RNNAgent, QMix, QMix_Trainer, discrete SAC)

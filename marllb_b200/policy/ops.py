@@ -48,6 +48,15 @@ def _L():
             "mlb_sac_policy_loss": [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
             "mlb_sac_alpha_loss": [vp, vp, f32, vp, vp, i32, vp],
             "mlb_exp_scalar": [vp, vp, vp],
+            "mlb_softmax_forward": [vp, vp, i64, i32, vp],
+            "mlb_softmax_backward": [vp, vp, vp, i64, i32, vp],
+            "mlb_concat_onehot": [vp, vp, vp, i64, i32, i32, i32, vp],
+            "mlb_categorical": [vp, vp, vp, vp, vp, vp, i64, i32, vp],
+            "mlb_logprob_backward": [vp, vp, vp, vp, i64, i32, i32, vp],
+            "mlb_scatter_class": [vp, vp, vp, i64, i32, vp],
+            "mlb_td_lambda_targets": [vp, vp, vp, f32, f32, i32, i32, vp],
+            "mlb_reward_normalize": [vp, vp, f32, i32, i32, vp],
+            "mlb_dsac_q_target": [vp, vp, vp, vp, vp, f32, vp, i32, vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -61,7 +70,10 @@ POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_g
                   "mlb_egreedy_select", "mlb_onehot_action", "mlb_row_max", "mlb_mixer_forward", "mlb_mixer_backward",
                   "mlb_tanh_gaussian_forward", "mlb_tanh_gaussian_backward", "mlb_abs_forward",
                   "mlb_qmix_td_loss", "mlb_sac_q_target", "mlb_mse_loss", "mlb_sac_policy_loss",
-                  "mlb_sac_alpha_loss", "mlb_exp_scalar"]
+                  "mlb_sac_alpha_loss", "mlb_exp_scalar",
+                  "mlb_softmax_forward", "mlb_softmax_backward", "mlb_concat_onehot", "mlb_categorical",
+                  "mlb_logprob_backward", "mlb_scatter_class", "mlb_td_lambda_targets", "mlb_reward_normalize",
+                  "mlb_dsac_q_target"]
 
 
 def _p(t):
@@ -332,4 +344,75 @@ def sac_alpha_loss(logp, log_alpha, target_entropy):
 def exp_scalar(x):
     y = torch.empty_like(x)
     check(_L().mlb_exp_scalar(_p(x), _p(y), _st()))
+    return y
+
+
+# ---- original-paper agents (src/lb/sac_qmix.py, src/lb/sac_gru_discrete.py) ----------------------
+def softmax_forward(x):
+    """F.softmax over the last dimension (n <= 64 classes)."""
+    y = torch.empty_like(x)
+    n = x.shape[-1]
+    check(_L().mlb_softmax_forward(_p(_chk(x)), _p(y), x.numel() // n, n, _st()))
+    return y
+
+
+def softmax_backward(y, dy):
+    dx = torch.empty_like(y)
+    n = y.shape[-1]
+    check(_L().mlb_softmax_backward(_p(_chk(y)), _p(_chk(dy)), _p(dx), y.numel() // n, n, _st()))
+    return dx
+
+
+def concat_onehot(x, action, n):
+    """x [rows, F] float32, action [rows, heads] int32 -> [rows, F + heads*n]."""
+    rows, F = x.shape
+    heads = action.shape[-1]
+    out = torch.empty((rows, F + heads * n), dtype=torch.float32, device=x.device)
+    check(_L().mlb_concat_onehot(_p(_chk(x)), _p(action), _p(out), rows, F, heads, n, _st()))
+    return out
+
+
+def categorical(p, u=None, given=None, want_logp=True, want_p=False):
+    """Rows of probabilities [..., n] -> (class int32 [...], log p[class] or None, p[class] or None)."""
+    n = p.shape[-1]
+    rows = p.numel() // n
+    shape = p.shape[:-1]
+    act = torch.empty(shape, dtype=torch.int32, device=p.device)
+    logp = torch.empty(shape, dtype=torch.float32, device=p.device) if want_logp else None
+    ps = torch.empty(shape, dtype=torch.float32, device=p.device) if want_p else None
+    check(_L().mlb_categorical(_p(_chk(p)), _p(u), _p(given), _p(act), _p(logp), _p(ps), rows, n, _st()))
+    return act, logp, ps
+
+
+def logprob_backward(p, action, g, group):
+    d = torch.empty_like(p)
+    n = p.shape[-1]
+    check(_L().mlb_logprob_backward(_p(_chk(p)), _p(action), _p(_chk(g)), _p(d), p.numel() // n, n, group, _st()))
+    return d
+
+
+def scatter_class(g, action, n):
+    d = torch.empty(tuple(g.shape) + (n,), dtype=torch.float32, device=g.device)
+    check(_L().mlb_scatter_class(_p(_chk(g)), _p(action), _p(d), g.numel(), n, _st()))
+    return d
+
+
+def td_lambda_targets(reward, target_q, gamma=0.99, td_lambda=0.6):
+    B, T = reward.shape
+    ret = torch.empty_like(target_q)
+    check(_L().mlb_td_lambda_targets(_p(_chk(reward)), _p(_chk(target_q)), _p(ret), gamma, td_lambda, B, T, _st()))
+    return ret
+
+
+def reward_normalize(reward, scale):
+    B, T = reward.shape
+    out = torch.empty_like(reward)
+    check(_L().mlb_reward_normalize(_p(_chk(reward)), _p(out), scale, B, T, _st()))
+    return out
+
+
+def dsac_q_target(reward, q1n, q2n, logp_next, alpha, gamma):
+    y = torch.empty_like(reward)
+    check(_L().mlb_dsac_q_target(_p(_chk(reward)), _p(_chk(q1n)), _p(_chk(q2n)), _p(_chk(logp_next)), _p(alpha),
+                                 float(gamma), _p(y), reward.numel(), _st()))
     return y

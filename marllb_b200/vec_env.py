@@ -60,7 +60,7 @@ class VecLoadBalanceEnv:
                  queue_capacity: int = 160, decay: float = 0.9, seed_base: int = 0,
                  rng_table_len: int = 65536, feature_cache: bool = True,
                  record_assign: bool = False, action_dtype: str = "int32", env_id_base: int = 0,
-                 device: int = 0):
+                 device: int = 0, normalize_obs: bool = False):
         if action_type not in ("discrete", "continuous"):
             raise ValueError(f"Unknown action_type: {action_type}")          # env.py:184
         if reward_metric not in _lib.METRICS:
@@ -115,6 +115,10 @@ class VecLoadBalanceEnv:
         self._adtype = {_lib.ACTION_DISCRETE_I32: torch.int32, _lib.ACTION_CONTINUOUS_F32: torch.float32,
                         _lib.ACTION_DISCRETE_U8: torch.uint8}[cfg.action_kind]
         self._np_adtype = {torch.int32: np.int32, torch.float32: np.float32, torch.uint8: np.uint8}[self._adtype]
+        # running observation statistics (env.py:152-154): per env, float64, device-resident
+        self.normalize_obs = normalize_obs
+        self.obs_count = 0
+        self.obs_mean = self.obs_std = self.normalized_obs = None
         # pinned host buffers for the end-to-end path
         self._h_action = self._h_obs = self._h_reward = self._h_done = None
 
@@ -203,6 +207,8 @@ class VecLoadBalanceEnv:
         check(self._L.mlb_reset(self._h, _nptr(m), self._stream()), self._h)
         if m is not None:
             torch.cuda.current_stream().synchronize()  # pageable mask must outlive the async copy
+        if self.normalize_obs:
+            return self._normalize_observation(self.obs)                           # env.py:210-211
         return self.obs
 
     def step(self, action):
@@ -219,7 +225,25 @@ class VecLoadBalanceEnv:
         check(self._L.mlb_step(self._h, _dptr(a), _lib.DEVICE, None, None, None, _lib.DEVICE,
                                self._stream()), self._h)
         self._last_action = a  # keep alive until the kernel has consumed it
+        if self.normalize_obs:
+            return self._normalize_observation(self.obs), self.reward, self.done   # env.py:283-285
         return self.obs, self.reward, self.done
+
+    def _normalize_observation(self, obs):
+        """env.py:450-470 for every env at once: updates the running `obs_mean` / `obs_std` (float64
+        (E,S,11) device tensors, one set of statistics per env like one reference env object each) and
+        returns the normalised observation as a float64 (E,S,11) tensor (numpy promotes to float64 in the
+        reference too).  Bit-exact with the reference's arithmetic."""
+        E, S = self.num_envs, self.total_servers
+        if self.obs_mean is None:
+            self.obs_mean = torch.zeros((E, S, 11), dtype=torch.float64, device=self.device)
+            self.obs_std = torch.ones((E, S, 11), dtype=torch.float64, device=self.device)
+            self.normalized_obs = torch.empty((E, S, 11), dtype=torch.float64, device=self.device)
+        o = obs.to(device=self.device, dtype=torch.float32).contiguous()
+        self.obs_count += 1
+        check(self._L.mlb_normalize_obs(_dptr(o), _dptr(self.obs_mean), _dptr(self.obs_std), self.obs_count,
+                                        _dptr(self.normalized_obs), o.numel(), self._stream()), self._h)
+        return self.normalized_obs
 
     def pinned_actions(self) -> "torch.Tensor":
         """A pinned (E, S) host tensor of the action dtype; fill it and pass it to step_host to

@@ -152,6 +152,24 @@ def gold_fair_fn():
     save("fair_fn_cases", values=vals, n=nn, out=out, names=np.array(names))
 
 
+def gold_normalize():
+    """_normalize_observation (env.py:450-470): the same seeded reference env with and without
+    normalize_obs gives (raw float32 obs, normalised float64 obs) pairs, reset + 12 steps."""
+    env = ref_import.load("env")
+    S, T = 6, 12
+    raw_env = env.LoadBalanceEnv(num_servers=S, step_interval=0.0, seed=7, normalize_obs=False, max_steps=100)
+    nrm_env = env.LoadBalanceEnv(num_servers=S, step_interval=0.0, seed=7, normalize_obs=True, max_steps=100)
+    raw, nrm = [raw_env.reset()], [nrm_env.reset()]
+    act = np.random.RandomState(3).randint(0, 3, (T, S))
+    for k in range(T):
+        raw.append(raw_env.step(act[k])[0])
+        nrm.append(nrm_env.step(act[k])[0])
+    raw, nrm = np.stack(raw), np.stack(nrm)
+    assert raw.dtype == np.float32 and nrm.dtype == np.float64
+    save("normalize_cases", raw=raw, normalized=nrm, mean=nrm_env.obs_mean, std=nrm_env.obs_std,
+         count=np.int64(nrm_env.obs_count))
+
+
 def gold_alias():
     rng = np.random.RandomState(2)
     ps, probs, aliases, ns = [], [], [], []
@@ -303,6 +321,7 @@ if __name__ == "__main__":
     gold_features()
     gold_rewards()
     gold_fair_fn()
+    gold_normalize()
     gold_alias()
     gold_legacy()
     gold_flow(sys.argv[1:] or None)

@@ -113,3 +113,32 @@ def test_multi_agent_env_reference_shapes():
     clean = MultiAgentLoadBalanceEnv(num_agents=2, servers_per_agent=3, strict_reference=False, seed=0)
     o = clean.reset()
     assert o[0].shape == (33,) and clean.obs_dim == 33 and clean.get_state().shape == (6 * 11 + 10,)
+
+
+def test_batched_normalize_observation_bit_exact():
+    """_normalize_observation (env.py:450-470) for all envs in one kernel: the reference's float64 running
+    statistics, bit for bit, against (raw, normalised) pairs produced by the reference env itself."""
+    import torch
+    from marllb_b200 import VecLoadBalanceEnv
+    g = load_golden("normalize_cases")
+    raw, ref = g["raw"], g["normalized"]
+    T, S = raw.shape[0], raw.shape[1]
+    E = 5
+    env = VecLoadBalanceEnv(E, num_servers=S, normalize_obs=True)
+    scale = np.arange(1, E + 1, dtype=np.float32).reshape(E, 1, 1)         # env e sees e+1 times the obs
+    mean, std = np.zeros((E, S, 11)), np.ones((E, S, 11))
+    for k in range(T):
+        x = raw[k][None] * scale
+        out = env._normalize_observation(torch.as_tensor(x).cuda()).cpu().numpy()
+        # the reference formula, env by env
+        n = k + 1
+        delta = x - mean
+        mean = mean + delta / n
+        delta2 = x - mean
+        std = np.sqrt(np.maximum((std ** 2 * (n - 1) + delta * delta2) / n, 1e-8))
+        assert np.array_equal(out, (x - mean) / (std + 1e-8)), k
+        assert np.array_equal(out[0], ref[k]), k                           # env 0 = the reference env's own output
+    assert env.obs_count == int(g["count"])
+    assert np.array_equal(env.obs_mean[0].cpu().numpy(), g["mean"])
+    assert np.array_equal(env.obs_std[0].cpu().numpy(), g["std"])
+    env.close()
