@@ -147,6 +147,18 @@ int mlb_load_arrivals(mlb_env *h, const float *time, const float *work,
                       const int32_t *bucket, const float *u,
                       const int64_t *offsets, int loc, void *stream);
 
+/* Streamed traces (hour-long trace files do not have to be resident).  The arrivals of the
+ * NEXT chunk of env steps -- same layout as mlb_load_arrivals, HOST pointers (pinned for a truly asynchronous
+ * copy; they must stay valid until `copy_stream` has passed the call) -- are copied into a second buffer set
+ * on `copy_stream` while the envs keep stepping through the current chunk.  mlb_commit_arrivals, enqueued on
+ * the stepping stream between two steps, waits for that copy, swaps the two sets and rewinds the arrival
+ * cursors.  A chunk must hold exactly the arrivals of a whole number of step windows (time < t1 of its last
+ * step, in float32 like the kernel's comparison), so no flow is left behind at the swap.
+ * Replays what src/client/replay_fork_io.py:95-143 does against the real testbed. */
+int mlb_stage_arrivals(mlb_env *h, const float *time, const float *work, const int32_t *bucket,
+                       const float *u, const int64_t *offsets, void *copy_stream);
+int mlb_commit_arrivals(mlb_env *h, void *stream);
+
 /* Device-side synthetic Poisson arrivals (training_pipeline.py:141-155
  * semantics: exponential inter-arrivals at `rate`/s, kept while < horizon;
  * exponential work with mean `mean_work`), Philox4x32-10 keyed by

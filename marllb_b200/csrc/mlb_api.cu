@@ -31,6 +31,17 @@ struct mlb_env {
     std::vector<int64_t> h_off;
     std::vector<int32_t> h_n;
     bool have_arrivals = false;
+    // staged (next) chunk of a streamed trace: filled asynchronously, swapped in by mlb_commit_arrivals
+    float *stg_time = nullptr, *stg_work = nullptr, *stg_u = nullptr;
+    int32_t* stg_bucket = nullptr;
+    int64_t* stg_off = nullptr;
+    int32_t* stg_n = nullptr;
+    int64_t stg_total = 0;
+    std::vector<int64_t> stg_h_off;
+    std::vector<int32_t> stg_h_n;
+    cudaEvent_t stg_ready = nullptr;   // staged copies done
+    cudaEvent_t stg_free = nullptr;    // last kernel that read the buffers now used for staging has finished
+    bool stg_pending = false, stg_valid = false;
     void* d_action = nullptr;
     size_t action_bytes = 0;
     uint8_t* d_mask = nullptr;
@@ -341,6 +352,8 @@ int mlb_destroy(mlb_env* h) {
     for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->stg_ready) cudaEventDestroy(h->stg_ready);
+    if (h->stg_free) cudaEventDestroy(h->stg_free);
     delete h;
     return MLB_OK;
 }
@@ -572,6 +585,92 @@ int mlb_load_arrivals(mlb_env* h, const float* time, const float* work, const in
     CK(h, cudaMemcpyAsync(h->arr_n, h->h_n.data(), (size_t)EA * 4, cudaMemcpyHostToDevice, st));
     CK(h, cudaMemsetAsync(d.arr_cur, 0, (size_t)EA * 4, st));
     CK(h, cudaStreamSynchronize(st));  // host staging vectors must outlive the copies
+    h->have_arrivals = true;
+    return MLB_OK;
+}
+
+// ---- streamed traces: the next chunk of arrivals is copied in on a side stream while the envs step
+// through the current one; mlb_commit_arrivals swaps the two buffer sets on the stepping stream.
+int mlb_stage_arrivals(mlb_env* h, const float* time, const float* work, const int32_t* bucket, const float* u,
+                       const int64_t* offsets, void* copy_stream) {
+    if (!h || !offsets) return fail(h, MLB_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    DevState& d = h->d;
+    const bool need_b = needs_bucket(h->cfg.policy);
+    const bool empty = offsets[d.E * d.A] == 0;       // a chunk past the end of the trace: pointers may be null
+    if (!empty && (!time || !work)) return fail(h, MLB_EINVAL, "null argument");
+    if (!empty && h->cfg.policy == MLB_POLICY_ALIAS && (!bucket || !u)) return fail(h, MLB_EINVAL, "alias policy needs pre-drawn bucket/u arrays");
+    if (!empty && need_b && !bucket) return fail(h, MLB_EINVAL, "power-of-two policies need a pre-drawn bucket array");
+    if (h->cfg.record_assign) return fail(h, MLB_EINVAL, "record_assign is not available with streamed arrivals");
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    const int EA = d.E * d.A;
+    if (!h->stg_ready) {
+        CK(h, cudaEventCreateWithFlags(&h->stg_ready, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->stg_free, cudaEventDisableTiming));
+    }
+    if (h->stg_pending) CK(h, cudaEventSynchronize(h->stg_ready));   // host staging vectors are about to be rewritten
+    h->stg_h_off.assign(offsets, offsets + EA);
+    h->stg_h_n.resize(EA);
+    for (int i = 0; i < EA; i++) {
+        const int64_t n = offsets[i + 1] - offsets[i];
+        if (n < 0 || n > 0x7fffffff) return fail(h, MLB_EINVAL, "offsets must be non-decreasing (stream %d)", i);
+        h->stg_h_n[i] = (int32_t)n;
+    }
+    const int64_t total = offsets[EA] > 0 ? offsets[EA] : 1;
+    if (total > h->stg_total || (need_b && !h->stg_bucket)) {
+        CK(h, dalloc(h, &h->stg_time, (size_t)total));
+        CK(h, dalloc(h, &h->stg_work, (size_t)total));
+        if (need_b) {
+            CK(h, dalloc(h, &h->stg_bucket, (size_t)total));
+            CK(h, dalloc(h, &h->stg_u, (size_t)total));
+        }
+        h->stg_total = total;
+    }
+    if (!h->stg_off) {
+        CK(h, dalloc(h, &h->stg_off, (size_t)EA));
+        CK(h, dalloc(h, &h->stg_n, (size_t)EA));
+    }
+    CK(h, cudaStreamWaitEvent(cs, h->stg_free, 0));   // no-op until the first commit has recorded it
+    if (offsets[EA] > 0) {
+        const size_t nb = (size_t)offsets[EA] * 4;
+        CK(h, cudaMemcpyAsync(h->stg_time, time, nb, cudaMemcpyHostToDevice, cs));
+        CK(h, cudaMemcpyAsync(h->stg_work, work, nb, cudaMemcpyHostToDevice, cs));
+        if (need_b) {
+            CK(h, cudaMemcpyAsync(h->stg_bucket, bucket, nb, cudaMemcpyHostToDevice, cs));
+            if (u) {
+                CK(h, cudaMemcpyAsync(h->stg_u, u, nb, cudaMemcpyHostToDevice, cs));
+            } else {
+                CK(h, cudaMemsetAsync(h->stg_u, 0, nb, cs));
+            }
+        }
+    }
+    CK(h, cudaMemcpyAsync(h->stg_off, h->stg_h_off.data(), (size_t)EA * 8, cudaMemcpyHostToDevice, cs));
+    CK(h, cudaMemcpyAsync(h->stg_n, h->stg_h_n.data(), (size_t)EA * 4, cudaMemcpyHostToDevice, cs));
+    CK(h, cudaEventRecord(h->stg_ready, cs));
+    h->stg_pending = true;
+    h->stg_valid = true;
+    return MLB_OK;
+}
+
+int mlb_commit_arrivals(mlb_env* h, void* stream) {
+    if (!h) return MLB_EINVAL;
+    if (!h->stg_valid) return fail(h, MLB_ESTATE, "mlb_commit_arrivals without a staged chunk");
+    CK(h, cudaSetDevice(h->device));
+    DevState& d = h->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(h, cudaStreamWaitEvent(st, h->stg_ready, 0));
+    CK(h, cudaEventRecord(h->stg_free, st));          // every earlier step on `st` is done with the old chunk by then
+    std::swap(h->arr_time, h->stg_time); std::swap(h->arr_work, h->stg_work);
+    std::swap(h->arr_bucket, h->stg_bucket); std::swap(h->arr_u, h->stg_u);
+    std::swap(h->arr_off, h->stg_off); std::swap(h->arr_n, h->stg_n);
+    std::swap(h->arr_total, h->stg_total);
+    h->h_off.swap(h->stg_h_off);
+    h->h_n.swap(h->stg_h_n);
+    d.arr_time = h->arr_time; d.arr_work = h->arr_work;
+    d.arr_bucket = h->arr_bucket; d.arr_u = h->arr_u;
+    d.arr_off = h->arr_off; d.arr_n = h->arr_n;
+    CK(h, cudaMemsetAsync(d.arr_cur, 0, (size_t)d.E * d.A * 4, st));
+    h->stg_valid = false;
     h->have_arrivals = true;
     return MLB_OK;
 }

@@ -218,6 +218,7 @@ class RNNAgent(_Module):
         last_action = torch.as_tensor(np.asarray(last_action), dtype=torch.int64)[None, :, None, :]
         hidden_in = torch.as_tensor(hidden_in, dtype=torch.float32)
         qs, hidden_out = self.forward(state, last_action, hidden_in)
+        hidden_out = hidden_out.squeeze(-3)                                          # remove the agent dim :266
         probs = qs.squeeze(-3).contiguous()                                          # [1, #batch, heads, actions] :267
         uu = None if deterministic else _uniforms(probs.shape[:-1], u, self.device)
         act, _, _ = ops.categorical(probs, u=uu, want_logp=False)

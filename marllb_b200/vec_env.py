@@ -119,6 +119,9 @@ class VecLoadBalanceEnv:
         self.normalize_obs = normalize_obs
         self.obs_count = 0
         self.obs_mean = self.obs_std = self.normalized_obs = None
+        # streamed trace (attach_stream): chunk bookkeeping
+        self._trace = None
+        self._steps_done = 0
         # pinned host buffers for the end-to-end path
         self._h_action = self._h_obs = self._h_reward = self._h_done = None
 
@@ -179,6 +182,55 @@ class VecLoadBalanceEnv:
         check(self._L.mlb_load_arrivals(self._h, _nptr(time), _nptr(work), _nptr(bucket), _nptr(u),
                                         _nptr(offsets), _lib.HOST, self._stream()), self._h)
 
+    # ------------------------------------------------------------- streamed traces
+    def attach_stream(self, stream):
+        """Replay a `traces.TraceStream`: only the chunk being stepped through (and the next one) live in
+        HBM.  While the envs step through chunk c, a background thread reads and parses chunk c+1 into pinned
+        memory and `mlb_stage_arrivals` copies it in on a side CUDA stream; at the chunk boundary
+        `mlb_commit_arrivals` swaps the buffer sets on the stepping stream.  reset() restarts the trace."""
+        import threading
+        self._trace = stream
+        self._threading = threading
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._restart_stream()
+
+    def _restart_stream(self):
+        tr = self._trace
+        if getattr(self, "_prefetch", None) is not None:
+            self._prefetch.join()
+        tr.restart()
+        self._steps_done = 0
+        self._chunk_end, first = tr.next_chunk()
+        self.load_arrivals_csr(first["time"], first["work"], first["offsets"], first.get("bucket"), first.get("u"))
+        self._kick_prefetch()
+
+    def _kick_prefetch(self):
+        def work():
+            k_end, ch = self._trace.next_chunk()
+            pin = {}
+            for key in ("time", "work", "bucket", "u"):
+                if key in ch:
+                    t = torch.from_numpy(np.ascontiguousarray(ch[key]))
+                    pin[key] = t.pin_memory() if t.numel() else t
+            off = np.ascontiguousarray(ch["offsets"], np.int64)
+            with torch.cuda.device(self.device):
+                check(self._L.mlb_stage_arrivals(self._h, _dptr(pin["time"]), _dptr(pin["work"]), _dptr(pin.get("bucket")),
+                                                 _dptr(pin.get("u")), _nptr(off),
+                                                 C.c_void_p(self._copy_stream.cuda_stream)), self._h)
+            self._staged = (k_end, pin, off)          # keeps the pinned buffers alive until the next swap
+        self._prefetch = self._threading.Thread(target=work, daemon=True)
+        self._prefetch.start()
+
+    def _advance_stream(self):
+        """Called before a step: swap in the next chunk when the current one is used up."""
+        if self._steps_done < self._chunk_end:
+            return
+        self._prefetch.join()
+        self._live = self._staged
+        check(self._L.mlb_commit_arrivals(self._h, self._stream()), self._h)
+        self._chunk_end = self._staged[0]
+        self._kick_prefetch()
+
     def gen_poisson(self, rate: float, mean_work: float, horizon: float, seed: int = 0):
         """Synthetic Poisson arrivals generated on the device (training_pipeline.py:141-155)."""
         check(self._L.mlb_gen_poisson(self._h, rate, mean_work, horizon, seed, self._stream()), self._h)
@@ -204,6 +256,10 @@ class VecLoadBalanceEnv:
             m = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
             if m.shape != (self.num_envs,):
                 raise ValueError("mask must have shape (num_envs,)")
+        if self._trace is not None:
+            if m is not None:
+                raise ValueError("masked reset is not available while a trace stream is attached")
+            self._restart_stream()
         check(self._L.mlb_reset(self._h, _nptr(m), self._stream()), self._h)
         if m is not None:
             torch.cuda.current_stream().synchronize()  # pageable mask must outlive the async copy
@@ -222,6 +278,9 @@ class VecLoadBalanceEnv:
             a = torch.as_tensor(np.ascontiguousarray(action, self._np_adtype)).to(self.device)
         if a.numel() != E * S:
             raise ValueError(f"action must have {E}x{S} entries, got shape {tuple(a.shape)}")
+        if self._trace is not None:
+            self._advance_stream()
+            self._steps_done += 1
         check(self._L.mlb_step(self._h, _dptr(a), _lib.DEVICE, None, None, None, _lib.DEVICE,
                                self._stream()), self._h)
         self._last_action = a  # keep alive until the kernel has consumed it
@@ -269,6 +328,9 @@ class VecLoadBalanceEnv:
                 self._h_action = self.pinned_actions()
             self._h_action.numpy()[...] = np.asarray(action).reshape(E, S)
             src = self._h_action
+        if self._trace is not None:
+            self._advance_stream()
+            self._steps_done += 1
         check(self._L.mlb_step(self._h, _dptr(src), _lib.HOST, _dptr(self._h_obs),
                                _dptr(self._h_reward), _dptr(self._h_done), _lib.HOST, self._stream()), self._h)
         torch.cuda.current_stream().synchronize()
