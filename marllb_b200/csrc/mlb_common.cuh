@@ -1,5 +1,6 @@
 // Common device helpers for the marllb_b200 kernels (sm_100a).
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -86,5 +87,16 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
     return __ldcs(reinterpret_cast<const float2*>(p));
 }
 __device__ __forceinline__ float ldg_stream1(const float* p) { return __ldcs(p); }
+
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}).
+// Register arrays indexed inside `#pragma unroll` loops whose bodies hold data-dependent loops stayed in local
+// memory (the unroll request was dropped); with constant indices they are scalars.
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
 
 }  // namespace mlb

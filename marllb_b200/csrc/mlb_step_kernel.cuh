@@ -273,7 +273,7 @@ __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint
 // ---------------------------------------------------------------------------
 // event_kernel: R = servers per lane (Sa <= 32*R), SP = 32*R.  Warps are independent.
 #ifndef MLB_EV_MINBLOCKS
-#define MLB_EV_MINBLOCKS 12
+#define MLB_EV_MINBLOCKS 10
 #endif
 template <int POLICY, int R>
 __global__ void __launch_bounds__(128, MLB_EV_MINBLOCKS)
@@ -314,8 +314,8 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
     float hf[R];       // finish time of the oldest in-system flow (INF: idle)
     float ha[R];       // its arrival time
     uint32_t sc[R];    // assignment score as an order-preserving uint
-#pragma unroll
-    for (int r = 0; r < R; r++) {
+    static_for<R>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
         const int j = lane + 32 * r;
         hf[r] = MLB_INF;
         ha[r] = 0.f;
@@ -359,7 +359,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                 sm[(F_CHG0 + m) * SP + j] = (cnt < (uint32_t)d.K ? cnt : (uint32_t)d.K) << 24;
             }
         }
-    }
+    });
     __syncwarp();
     if (kAlias) {
         // weights as floats for the alias builder
@@ -396,8 +396,8 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
             const float wk = __shfl_sync(MLB_FULL, awk, i & 31);
             const float a = real ? ash : t1;
             // --- retire every flow that finished strictly before this event
-#pragma unroll
-            for (int r = 0; r < R; r++) {
+            static_for<R>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
                 if (hf[r] < a) {
                     const int j = lane + 32 * r;
                     uint32_t h = sm[F_HEAD * SP + j];
@@ -418,7 +418,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     sm[F_NON * SP + j] = (uint32_t)n;
                     if (kArgmin) sc[r] = server_score<POLICY>(d, n, sm[F_ACT * SP + j]);
                 }
-            }
+            });
             __syncwarp();
             if (!real) break;
             // --- choose a server
@@ -439,10 +439,10 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
             } else {
                 uint32_t bkey = sc[0];
                 int bj = lane;
-#pragma unroll
-                for (int r = 1; r < R; r++) {
-                    if (sc[r] < bkey) { bkey = sc[r]; bj = lane + 32 * r; }  // strict <: first minimum wins
-                }
+                static_for<R>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    if (r > 0 && sc[r] < bkey) { bkey = sc[r]; bj = lane + 32 * r; }  // strict <: first minimum wins
+                });
                 const uint32_t mkey = __reduce_min_sync(MLB_FULL, bkey);
                 kstar = (int)__reduce_min_sync(MLB_FULL, (uint32_t)(bkey == mkey ? bj : 0x7fffffff));
             }
@@ -462,13 +462,13 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     sm[F_NON * SP + k] = (uint32_t)(n + 1);                 // lbhash.h:142,167
                     uint32_t nsc = 0;
                     if (kArgmin) nsc = server_score<POLICY>(d, n + 1, sm[F_ACT * SP + k]);
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
+                    static_for<R>([&](auto rc) {
+                        constexpr int r = decltype(rc)::value;
                         if ((k >> 5) == r) {
                             if (n == 0) { hf[r] = fin; ha[r] = a; }
                             sc[r] = nsc;
                         }
-                    }
+                    });
                 }
                 if (d.record_assign) d.assign[aoff + cur + i] = seed0 + k;
             }
@@ -481,8 +481,8 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
 
     // ---------------- phase C: flow_duration samples, state write-back -------
     float* obs = d.obs + sbase * MLB_OBS_COLS;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
+    static_for<R>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
         const int j = lane + 32 * r;
         if (j < Sa) {
             const size_t gi = sbase + j;
@@ -508,7 +508,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                 d.res_chg[c] = sm[(F_CHG0 + m) * SP + j];
             }
         }
-    }
+    });
 }
 
 // ---------------------------------------------------------------------------
