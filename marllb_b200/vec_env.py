@@ -136,7 +136,12 @@ class VecLoadBalanceEnv:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def close(self):
+        t = getattr(self, "_prefetch", None)
+        if t is not None:                                   # a chunk of a streamed trace may still be staging
+            t.join()
+            self._prefetch = None
         if getattr(self, "_h", None) and self._h.value:
+            torch.cuda.synchronize(self.device)
             self._L.mlb_destroy(self._h)
             self._h = C.c_void_p()
 
