@@ -449,11 +449,15 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     // SED score table, same arithmetic as the oracle: (float)((double)(n+1) / (1e-9 + (double)w))
     {
         const int TQ = d.Q + 2;
-        std::vector<float> tab((size_t)8 * TQ, 0.f);
+        std::vector<uint32_t> tab((size_t)8 * TQ, 0u);
         for (int a = 0; a < c.n_discrete && a < 8; a++)
-            for (int n = 0; n < TQ; n++)
-                tab[(size_t)a * TQ + n] = (float)((double)(n + 1) / (1e-9 + (double)c.discrete_weights[a]));
-        float* t = nullptr;
+            for (int n = 0; n < TQ; n++) {
+                const float sc = (float)((double)(n + 1) / (1e-9 + (double)c.discrete_weights[a]));
+                uint32_t b;
+                memcpy(&b, &sc, 4);
+                tab[(size_t)a * TQ + n] = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);   // = f32_orderable(sc)
+            }
+        uint32_t* t = nullptr;
         CKC(dalloc(h, &t, tab.size()));
         CKC(cudaMemcpy(t, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
         d.sed_table = t;

@@ -52,7 +52,7 @@ struct DevState {
     int32_t* assign;        // parallel to arr_time (optional)
     // ---- RNG replay table [S][L] and sticky status word
     const uint32_t* mt_table;
-    const float* sed_table; // [n_discrete][Q+2] SED scores for discrete actions (host-built)
+    const uint32_t* sed_table; // [n_discrete][Q+2] SED scores for discrete actions as order-preserving uints (host-built)
     int* status;
 };
 

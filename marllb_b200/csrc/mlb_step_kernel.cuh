@@ -68,20 +68,17 @@ __host__ __device__ inline size_t feature_warp_smem_bytes(int SP) {
 // Assignment score of one server as an order-preserving uint.
 // node.c:395-404: f32 score = (n_flow_on + 1) / (1e-9 + weight), evaluated in double.
 // For discrete actions the quotient comes from a table built on the host with exactly
-// that arithmetic: sed_table[a * (Q + 2) + n].
+// that arithmetic, stored in its order-preserving uint form: sed_table[a * (Q + 2) + n]; `act` is the row offset.
 template <int POLICY>
 __device__ __forceinline__ uint32_t server_score(const DevState& d, int n, uint32_t act) {
     if (POLICY == MLB_POLICY_SED || POLICY == MLB_POLICY_SED2) {
-        float sc;
         if (d.action_kind == MLB_ACTION_CONTINUOUS_F32) {
             const double s = (double)(n + 1) / (1e-9 + (double)__uint_as_float(act));
-            sc = (float)s;
-        } else {
-            sc = __ldg(d.sed_table + act * (d.Q + 2) + n);
+            return f32_orderable((float)s);
         }
-        return f32_orderable(sc);
+        return __ldg(d.sed_table + act + n);   // the table holds order-preserving uints; act = row offset a * (Q + 2)
     } else {
-        return f32_orderable((float)n);  // node.c:419-431 (LSQ), :433-441 (LSQ2)
+        return (uint32_t)n;  // node.c:419-431 (LSQ), :433-441 (LSQ2): f32(n) compares like n for 0 <= n <= Q
     }
 }
 
@@ -346,7 +343,8 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                     atomicOr(d.status, ST_ERR_ACTION);
                     a = 0;
                 }
-                act = (uint32_t)a;                                          // env.py:346
+                // env.py:346; the SED policies keep the row offset into the score table instead of the index
+                act = (POLICY == MLB_POLICY_SED || POLICY == MLB_POLICY_SED2) ? (uint32_t)(a * (Q + 2)) : (uint32_t)a;
             }
             sm[F_ACT * SP + j] = act;
             if (kArgmin) sc[r] = server_score<POLICY>(d, n, act);
