@@ -154,7 +154,10 @@ int mlb_load_arrivals(mlb_env *h, const float *time, const float *work,
  * the stepping stream between two steps, waits for that copy, swaps the two sets and rewinds the arrival
  * cursors.  A chunk must hold exactly the arrivals of a whole number of step windows (time < t1 of its last
  * step, in float32 like the kernel's comparison), so no flow is left behind at the swap.
- * Replays what src/client/replay_fork_io.py:95-143 does against the real testbed. */
+ * Replays what src/client/replay_fork_io.py:95-143 does against the real testbed.
+ * Threading: mlb_stage_arrivals may be called from a second host thread while the first one is inside
+ * mlb_step / mlb_reset on the same handle (it only touches the staging buffer set); every other pair of calls
+ * on one handle must be serialised by the caller, like the reference env (not thread-safe). */
 int mlb_stage_arrivals(mlb_env *h, const float *time, const float *work, const int32_t *bucket,
                        const float *u, const int64_t *offsets, void *copy_stream);
 int mlb_commit_arrivals(mlb_env *h, void *stream);
