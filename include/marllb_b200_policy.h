@@ -158,6 +158,11 @@ int mlb_logprob_backward(const float *p, const int32_t *action, const float *g, 
                          int64_t rows, int32_t n, int32_t group, void *stream);
 /* backward of the gather of the chosen class: d[r][k] = (k == action[r]) ? g[r] : 0 */
 int mlb_scatter_class(const float *g, const int32_t *action, float *d, int64_t rows, int32_t n, void *stream);
+/* WeightedQMixingNetwork.forward (problem-05-qmix/src/mixing_network.py:231-246): out[m] = sum_a q[m][a]*w[m][a],
+ * and its backward dq = g*w, dw = g*q (g [M]) */
+int mlb_weighted_sum_forward(const float *q, const float *w, float *out, int32_t M, int32_t A, void *stream);
+int mlb_weighted_sum_backward(const float *g, const float *q, const float *w, float *dq, float *dw,
+                              int32_t M, int32_t A, void *stream);
 /* QMix_Trainer._build_td_lambda_targets (sac_qmix.py:449-460) over [B][T]:
  * ret[:,T-1] = tq[:,T-1]; ret[:,t] = lambda*gamma*ret[:,t+1] + (r[:,t] + (1-lambda)*gamma*tq[:,t+1]) */
 int mlb_td_lambda_targets(const float *reward, const float *target_q, float *ret, float gamma,

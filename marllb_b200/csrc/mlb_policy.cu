@@ -587,6 +587,24 @@ __global__ void scatter_class_kernel(const float* __restrict__ g, const int32_t*
     d[i] = action[r] == (int)(i - r * n) ? g[r] : 0.f;
 }
 
+// WeightedQMixingNetwork.forward (mixing_network.py:231-246): q_tot[m] = sum_a q[m][a] * w[m][a]; one thread per row
+__global__ void weighted_sum_fwd_kernel(const float* __restrict__ q, const float* __restrict__ w, float* __restrict__ out,
+                                        int M, int A) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float s = 0.f;
+    for (int a = 0; a < A; a++) s += q[(int64_t)m * A + a] * w[(int64_t)m * A + a];
+    out[m] = s;
+}
+__global__ void weighted_sum_bwd_kernel(const float* __restrict__ g, const float* __restrict__ q, const float* __restrict__ w,
+                                        float* __restrict__ dq, float* __restrict__ dw, int64_t n, int A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gm = g[i / A];
+    dq[i] = gm * w[i];
+    dw[i] = gm * q[i];
+}
+
 // sac_qmix.py:449-460 _build_td_lambda_targets: backward recursion over the sequence, one thread per batch row
 __global__ void td_lambda_kernel(const float* __restrict__ reward, const float* __restrict__ tq, float* __restrict__ ret,
                                  float gamma, float lam, int B, int T) {
@@ -910,6 +928,21 @@ int mlb_scatter_class(const float* g, const int32_t* action, float* d, int64_t r
     if (!g || !action || !d || n < 1) return MLB_EINVAL;
     if (rows == 0) return MLB_OK;
     scatter_class_kernel<<<nblk(rows * n, 256), 256, 0, (cudaStream_t)stream>>>(g, action, d, rows, n);
+    return ok();
+}
+
+int mlb_weighted_sum_forward(const float* q, const float* w, float* out, int32_t M, int32_t A, void* stream) {
+    if (!q || !w || !out || A < 1) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    weighted_sum_fwd_kernel<<<nblk(M, 128), 128, 0, (cudaStream_t)stream>>>(q, w, out, M, A);
+    return ok();
+}
+
+int mlb_weighted_sum_backward(const float* g, const float* q, const float* w, float* dq, float* dw, int32_t M,
+                              int32_t A, void* stream) {
+    if (!g || !q || !w || !dq || !dw || A < 1) return MLB_EINVAL;
+    if (M == 0) return MLB_OK;
+    weighted_sum_bwd_kernel<<<nblk((int64_t)M * A, 256), 256, 0, (cudaStream_t)stream>>>(g, q, w, dq, dw, (int64_t)M * A, A);
     return ok();
 }
 

@@ -55,6 +55,8 @@ def _L():
             "mlb_logprob_backward": [vp, vp, vp, vp, i64, i32, i32, vp],
             "mlb_scatter_class": [vp, vp, vp, i64, i32, vp],
             "mlb_td_lambda_targets": [vp, vp, vp, f32, f32, i32, i32, vp],
+            "mlb_weighted_sum_forward": [vp, vp, vp, i32, i32, vp],
+            "mlb_weighted_sum_backward": [vp, vp, vp, vp, vp, i32, i32, vp],
             "mlb_reward_normalize": [vp, vp, f32, i32, i32, vp],
             "mlb_dsac_q_target": [vp, vp, vp, vp, vp, f32, vp, i32, vp],
         }
@@ -73,7 +75,7 @@ POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_g
                   "mlb_sac_alpha_loss", "mlb_exp_scalar",
                   "mlb_softmax_forward", "mlb_softmax_backward", "mlb_concat_onehot", "mlb_categorical",
                   "mlb_logprob_backward", "mlb_scatter_class", "mlb_td_lambda_targets", "mlb_reward_normalize",
-                  "mlb_dsac_q_target"]
+                  "mlb_dsac_q_target", "mlb_weighted_sum_forward", "mlb_weighted_sum_backward"]
 
 
 def _p(t):
@@ -416,3 +418,17 @@ def dsac_q_target(reward, q1n, q2n, logp_next, alpha, gamma):
     check(_L().mlb_dsac_q_target(_p(_chk(reward)), _p(_chk(q1n)), _p(_chk(q2n)), _p(_chk(logp_next)), _p(alpha),
                                  float(gamma), _p(y), reward.numel(), _st()))
     return y
+
+
+def weighted_sum_forward(q, w):
+    M, A = q.shape
+    out = torch.empty(M, dtype=torch.float32, device=q.device)
+    check(_L().mlb_weighted_sum_forward(_p(_chk(q)), _p(_chk(w)), _p(out), M, A, _st()))
+    return out
+
+
+def weighted_sum_backward(g, q, w):
+    M, A = q.shape
+    dq, dw = torch.empty_like(q), torch.empty_like(w)
+    check(_L().mlb_weighted_sum_backward(_p(_chk(g)), _p(q), _p(w), _p(dq), _p(dw), M, A, _st()))
+    return dq, dw

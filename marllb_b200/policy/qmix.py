@@ -167,6 +167,67 @@ class QMixingNetwork:
         self._tape = None
         return dq
 
+    def get_monotonicity_info(self, agent_qs, state):
+        """dQ_tot/dQ_i for every agent, [M, A] (mixing_network.py:119-151): the mixer's own backward pass with
+        dq_tot = 1; the hypernet gradients it would accumulate are discarded."""
+        saved = [g.clone() for g in self.P.grads()]
+        q_tot = self.forward(agent_qs, state, save=True)
+        dq = self.backward(torch.ones(q_tot.shape[0], dtype=torch.float32, device=self.device))
+        for g, s0 in zip(self.P.grads(), saved):
+            g.copy_(s0)
+        return dq
+
+    def to(self, device):
+        return self
+
+    def state_dict(self):
+        return self.P.state_dict()
+
+    def load_state_dict(self, sd):
+        self.P.load_state_dict(sd)
+
+    def parameters(self):
+        return self.P.tensors()
+
+
+class WeightedQMixingNetwork:
+    """mixing_network.py:187-246 (WQMIX): Q_tot = sum_i w_i(s) Q_i with w = softmax(MLP(s)); forward returns
+    (q_tot [M, 1], weights [M, A]) like the reference."""
+
+    def __init__(self, num_agents, state_dim, hidden_dim=64, device=None):
+        self.num_agents, self.state_dim, self.hidden_dim = num_agents, state_dim, hidden_dim
+        self.device = _device(device)
+        if num_agents > 64:
+            raise ValueError("at most 64 agents (softmax kernel row length)")
+        self.P = Params(self.device)
+        for name, (i, o) in (("weight_network.0", (state_dim, hidden_dim)), ("weight_network.2", (hidden_dim, num_agents))):
+            lin = torch.nn.Linear(i, o)
+            self.P.add(name + ".weight", lin.weight)
+            self.P.add(name + ".bias", lin.bias)
+
+    def forward(self, agent_qs, state, save=False):
+        P = self.P.p
+        q = agent_qs.to(self.device, torch.float32).reshape(-1, self.num_agents).contiguous()
+        s = state.to(self.device, torch.float32).contiguous()
+        h = ops.linear(s, P["weight_network.0.weight"], P["weight_network.0.bias"], ops.ACT_RELU)
+        w = ops.softmax_forward(ops.linear(h, P["weight_network.2.weight"], P["weight_network.2.bias"]))
+        q_tot = ops.weighted_sum_forward(q, w)
+        if save:
+            self._tape = (q, s, h, w)
+        return q_tot.reshape(-1, 1), w
+
+    __call__ = forward
+
+    def backward(self, dq_tot):
+        """dq_tot [M] -> d agent_qs [M, A]; accumulates the weight network's gradients."""
+        q, s, h, w = self._tape
+        dq, dw = ops.weighted_sum_backward(dq_tot.reshape(-1).contiguous(), q, w)
+        dlogits = ops.softmax_backward(w, dw)
+        dh = ops.relu_backward(h, linear_backward(self.P, "weight_network.2.weight", "weight_network.2.bias", h, dlogits))
+        linear_backward(self.P, "weight_network.0.weight", "weight_network.0.bias", s, dh, need_dx=False)
+        self._tape = None
+        return dq
+
     def to(self, device):
         return self
 

@@ -225,6 +225,59 @@ class ReplayBuffer:
         return len(self.buffer) >= batch_size
 
 
+class PrioritizedReplayBuffer:
+    """replay_buffer.py:105-221: proportional prioritised replay (host-side storage, the reference's own numpy
+    sampling call, so the same numpy seed draws the same indices)."""
+
+    def __init__(self, capacity=1_000_000, alpha=0.6, beta=0.4, beta_increment=0.001, epsilon=1e-6, seed=None):
+        self.capacity, self.alpha, self.beta = capacity, alpha, beta
+        self.beta_increment, self.epsilon = beta_increment, epsilon
+        self.buffer = []
+        self.priorities = np.zeros(capacity, dtype=np.float32)
+        self.position = 0
+        self.size = 0
+        if seed is not None:
+            random.seed(seed)
+            np.random.seed(seed)
+
+    def push(self, state, action, reward, next_state, done, hidden=None):
+        conv = lambda x: x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
+        max_priority = self.priorities[:self.size].max() if self.size > 0 else 1.0    # :158
+        item = (conv(state), conv(action), reward, conv(next_state), done, conv(hidden) if hidden is not None else None)
+        if len(self.buffer) < self.capacity:
+            self.buffer.append(item)
+        else:
+            self.buffer[self.position] = item
+        self.priorities[self.position] = max_priority
+        self.position = (self.position + 1) % self.capacity
+        self.size = min(self.size + 1, self.capacity)
+
+    def sample(self, batch_size, device='cpu'):
+        """-> (states, actions, rewards, next_states, dones, hiddens, weights, indices)        :170-208"""
+        priorities = self.priorities[:self.size]
+        probabilities = priorities ** self.alpha
+        probabilities /= probabilities.sum()
+        indices = np.random.choice(self.size, batch_size, p=probabilities)
+        weights = (self.size * probabilities[indices]) ** (-self.beta)
+        weights /= weights.max()
+        self.beta = min(1.0, self.beta + self.beta_increment)
+        states, actions, rewards, next_states, dones, hiddens = zip(*[self.buffer[i] for i in indices])
+        f = lambda x: torch.as_tensor(np.array(x), dtype=torch.float32).to(device)
+        hid = f(hiddens) if hiddens[0] is not None else None
+        return (f(states), f(actions), f(rewards).unsqueeze(1), f(next_states), f(dones).unsqueeze(1), hid,
+                f(weights).unsqueeze(1), indices)
+
+    def update_priorities(self, indices, priorities):
+        for idx, priority in zip(indices, priorities):
+            self.priorities[idx] = priority + self.epsilon
+
+    def __len__(self):
+        return self.size
+
+    def is_ready(self, batch_size):
+        return self.size >= batch_size
+
+
 class SAC_GRU_Agent:
     """sac_agent.py:19-318."""
 

@@ -134,6 +134,46 @@ def sac():
     save("policy_sac", **out)
 
 
+def extras():
+    """WeightedQMixingNetwork, QMixingNetwork.get_monotonicity_info (mixing_network.py:119-151,187-246) and
+    PrioritizedReplayBuffer (replay_buffer.py:105-221)."""
+    mn = ref_import.load("mixing_network", "problem-05-qmix")
+    rb = ref_import.load("replay_buffer", "problem-04-sac-gru")
+    torch.manual_seed(2)
+    out = {}
+    wq = mn.WeightedQMixingNetwork(num_agents=4, state_dim=11, hidden_dim=16)
+    aq = torch.randn(9, 4, requires_grad=True)
+    st = torch.randn(9, 11)
+    q_tot, w = wq(aq, st)
+    coef = torch.randn(9, 1)
+    (q_tot * coef).sum().backward()
+    out.update(sd_np("wq.", wq.state_dict()))
+    out.update(wq_q=aq.detach().numpy(), wq_state=st.numpy(), wq_out=q_tot.detach().numpy(), wq_w=w.detach().numpy(),
+               wq_coef=coef.numpy(), wq_dq=aq.grad.numpy())
+    out.update({"wqg." + k: v.grad.numpy().copy() for k, v in wq.named_parameters()})
+    mix = mn.QMixingNetwork(num_agents=3, state_dim=9, mixing_embed_dim=32, hypernet_embed_dim=64)
+    aq2, st2 = torch.randn(7, 3, requires_grad=True), torch.randn(7, 9)
+    out.update(sd_np("mono.", mix.state_dict()))
+    out.update(mono_q=aq2.detach().numpy(), mono_state=st2.numpy(),
+               mono_grad=mix.get_monotonicity_info(aq2, st2).detach().numpy())
+    # prioritised replay: ring, max-priority insertion, numpy sampling, importance weights, beta schedule
+    buf = rb.PrioritizedReplayBuffer(capacity=16, alpha=0.6, beta=0.4, beta_increment=0.01, seed=3)
+    rng = np.random.RandomState(0)
+    for i in range(21):
+        buf.push(rng.randn(5).astype(np.float32), rng.randn(2).astype(np.float32), float(i), rng.randn(5).astype(np.float32),
+                 float(i % 7 == 0), rng.randn(1, 1, 4).astype(np.float32))
+        if i == 9:
+            buf.update_priorities([0, 3, 5], [2.5, 0.1, 7.0])
+    np.random.seed(11)
+    res = buf.sample(6)
+    out.update(per_rewards=res[2].numpy(), per_states=res[0].numpy(), per_hiddens=res[5].numpy(), per_weights=res[6].numpy(),
+               per_indices=np.asarray(res[7]), per_beta=np.float64(buf.beta), per_priorities=buf.priorities.copy(),
+               per_size=np.int64(len(buf)), per_position=np.int64(buf.position))
+    save("policy_extras", **out)
+
+
 if __name__ == "__main__":
-    qmix()
-    sac()
+    if "extras" not in sys.argv:
+        qmix()
+        sac()
+    extras()
