@@ -247,6 +247,14 @@ int mlb_reward_metric(int metric, const double *values, const int32_t *n, int32_
 int mlb_legacy_seed(uint32_t *mt_state, const uint32_t *seeds, int32_t E, void *stream);
 int mlb_legacy_obs(uint32_t *mt_state, int32_t E, int32_t S, float *obs, void *stream);
 
+/* The reference's whole simulation-mode step for E envs in one launch (env.py:254-262): `_simulate_observation`
+ * (env.py:425-448) from each env's own RandomState stream, then -- when `reward` is not NULL -- the reward metric
+ * over column `field` of all S servers (every server is active in this mode: n_flow_on >= 5).  One warp per env,
+ * chunked warp-parallel MT19937 twist; same state layout as mlb_legacy_seed / mlb_legacy_obs (the three can be
+ * mixed on one state).  S <= 256.  `status` (device int, caller-zeroed) receives ST bits on a corrupt stream. */
+int mlb_legacy_step(uint32_t *mt_state, int32_t E, int32_t S, int32_t metric, int32_t field, float *obs,
+                    double *reward, int32_t *status, void *stream);
+
 /* Batched _normalize_observation (env.py:450-470): running mean / std update and normalisation of
  * n = E*S*11 observation entries in float64, the reference's arithmetic operation for operation
  * (count = obs_count AFTER the increment of env.py:461, >= 1; mean starts at 0, std at 1: env.py:152-153).

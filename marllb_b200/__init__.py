@@ -18,12 +18,12 @@ include/marllb_b200.h; there is no CPU fallback.
 from ._build import build  # noqa: F401
 
 __all__ = ["build", "LoadBalanceEnv", "LoadBalanceEnvGym", "MultiAgentLoadBalanceEnv",
-           "VecLoadBalanceEnv", "RewardFunction", "ReservoirSampler", "MultiMetricReservoir",
+           "VecLoadBalanceEnv", "VecLegacyEnv", "RewardFunction", "ReservoirSampler", "MultiMetricReservoir",
            "PerServerFeatures", "BatchedReservoirs", "QMIXRollout", "SACRollout", "DeviceReplay"]
 
 _LAZY = {
     "LoadBalanceEnv": "env", "LoadBalanceEnvGym": "env",
-    "MultiAgentLoadBalanceEnv": "multi_agent_env", "VecLoadBalanceEnv": "vec_env",
+    "MultiAgentLoadBalanceEnv": "multi_agent_env", "VecLoadBalanceEnv": "vec_env", "VecLegacyEnv": "legacy_vec",
     "RewardFunction": "rewards", "ReservoirSampler": "reservoir",
     "MultiMetricReservoir": "reservoir", "PerServerFeatures": "reservoir",
     "BatchedReservoirs": "reservoir",

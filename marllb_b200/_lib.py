@@ -34,7 +34,7 @@ EXPORTS = [
     "mlb_step", "mlb_get_assignments", "mlb_device_ptr", "mlb_get_state", "mlb_status",
     "mlb_launch_count", "mlb_profile_begin", "mlb_profile_end", "mlb_profile_pair_ms", "mlb_mt19937_fill", "mlb_reservoir_add", "mlb_reservoir_features",
     "mlb_reward_metric", "mlb_legacy_seed", "mlb_legacy_obs", "mlb_normalize_obs",
-    "mlb_stage_arrivals", "mlb_commit_arrivals",
+    "mlb_stage_arrivals", "mlb_commit_arrivals", "mlb_legacy_step",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
         "mlb_normalize_obs": (C.c_int, [vp, vp, vp, i64, vp, i64, vp]),
         "mlb_stage_arrivals": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "mlb_commit_arrivals": (C.c_int, [vp, vp]),
+        "mlb_legacy_step": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -147,6 +147,140 @@ __global__ void legacy_obs_kernel(uint32_t* __restrict__ state, int E, int S, fl
     }
 }
 
+// ---- warp-per-env legacy step -----------------------------------------------------------------------------
+// The reference's whole simulation-mode step is `_simulate_observation` + the reward (env.py:254-262, 425-448):
+// per server one randint(5, 20) (masked rejection: 1 + #rejected words) and six uniform() draws (2 words each),
+// in server order, from ONE MT19937 stream per env.  One warp per env:
+//   * the state row [624 words | position] of the env is contiguous, so every access below is a coalesced 128-byte
+//     line; the twist runs 32 words at a time (word k needs words k, k+1 and k+397 of the previous round or
+//     k-227 of this one: no dependence inside a 32-word chunk once all reads precede the writes), at the moment
+//     numpy would run it (position 624), so state and position stay numpy's own representation;
+//   * tempered words are staged in shared memory in consumption order, on demand and clipped at the end of the
+//     round, so a step never twists further than numpy would have;
+//   * where a server's words start depends on every rejection before it: lane 0 walks that chain over the staged
+//     words (rejections are rare: one trial in 16), then lane s evaluates server s in the reference's float64 /
+//     float32 arithmetic; rows leave through shared memory as coalesced stores; the reward is reward_staged.
+#define MLB_LG_STAGE 1024           // staging ring (words), power of two, >= 13 * 32 + rejections + one chunk
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// in-place twist of a whole state row by one warp (numpy's mt19937_gen), 32 words per iteration
+__device__ __forceinline__ void mt_twist_warp(uint32_t* st, int lane) {
+    for (int base = 0; base < 624; base += 32) {
+        const int k = base + lane;
+        uint32_t nw = 0;
+        if (k < 624) {
+            const uint32_t a = st[k], b = st[k + 1 == 624 ? 0 : k + 1], c = st[k + 397 >= 624 ? k - 227 : k + 397];
+            const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+            nw = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        __syncwarp();                               // every read of this chunk precedes its writes
+        if (k < 624) st[k] = nw;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+legacy_step_kernel(uint32_t* __restrict__ state, int E, int S, int metric, int field, float* __restrict__ obs,
+                   double* __restrict__ reward, int* __restrict__ status) {
+    __shared__ uint32_t s_stage[4][MLB_LG_STAGE];
+    __shared__ float s_rows[4][32 * MLB_OBS_COLS];
+    __shared__ int s_off[4][33];
+    __shared__ float s_rv[4][256];                 // reward-field value of every server
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * 4 + warp;
+    if (e >= E) return;
+    uint32_t* st = state + (size_t)e * 625;
+    uint32_t* stage = s_stage[warp];
+    float* rows = s_rows[warp];
+    int* off = s_off[warp];
+    int pos = (int)st[624];                         // numpy's `pos`: next unread word of the current round
+    uint32_t staged = 0, used = 0;                  // words staged / consumed so far in this step (ring counters)
+    float* rv = s_rv[warp];
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int nb = S - s0 < 32 ? S - s0 : 32;
+        // ---- lane 0 walks the rejection chain; the warp stages more words whenever it runs dry
+        int done = 0;                               // servers of this batch whose start offset is known
+        uint32_t cur = used;                        // start offset of server `done`
+        for (;;) {
+            if (lane == 0) {
+                while (done < nb) {
+                    uint32_t o = cur;
+                    bool dry = false;
+                    for (;;) {                      // randint(5, 20): masked rejection, env.py:436
+                        if (o >= staged) { dry = true; break; }
+                        if ((stage[o & (MLB_LG_STAGE - 1)] & 15u) <= 14u) break;
+                        o++;
+                    }
+                    if (dry || o + 13 > staged) break;
+                    off[done] = (int)(o - used);    // accepted randint word; the 12 uniform words follow
+                    cur = o + 13;
+                    done++;
+                }
+            }
+            done = __shfl_sync(MLB_FULL, done, 0);
+            cur = __shfl_sync(MLB_FULL, cur, 0);
+            if (done == nb) break;
+            if (staged - used > MLB_LG_STAGE - 64) {          // > 500 rejections in one batch: not a real stream
+                if (lane == 0) atomicOr(status, ST_ERR_RNG);
+                break;
+            }
+            if (pos == 624) {                       // numpy twists exactly here
+                mt_twist_warp(st, lane);
+                pos = 0;
+            }
+            const int take = 624 - pos < 32 ? 624 - pos : 32;
+            if (lane < take) stage[(staged + lane) & (MLB_LG_STAGE - 1)] = mt_temper(st[pos + lane]);
+            staged += take;
+            pos += take;
+            __syncwarp();
+        }
+        __syncwarp();
+        // ---- lane s: server s0 + s (env.py:436-446); uniform(lo, hi) = lo + (hi - lo) * random_sample()
+        if (lane < done) {
+            const uint32_t o = used + (uint32_t)off[lane];
+            auto word = [&](int i) { return stage[(o + i) & (MLB_LG_STAGE - 1)]; };
+            auto rs = [&](int i) {                  // random_sample from words i, i + 1
+                const uint32_t a = word(i) >> 5, b = word(i + 1) >> 6;
+                return (a * 67108864.0 + b) / 9007199254740992.0;
+            };
+            const float c0 = (float)(5 + (int)(word(0) & 15u));
+            const float c1 = (float)__dadd_rn(5.0, __dmul_rn(15.0 - 5.0, rs(1)));
+            const float c2 = (float)__dadd_rn(10.0, __dmul_rn(25.0 - 10.0, rs(3)));
+            const float c3 = (float)__dadd_rn(1.0, __dmul_rn(5.0 - 1.0, rs(5)));
+            const float c6 = (float)__dadd_rn(8.0, __dmul_rn(18.0 - 8.0, rs(7)));
+            const float c7 = (float)__dadd_rn(15.0, __dmul_rn(30.0 - 15.0, rs(9)));
+            const float c8 = (float)__dadd_rn(2.0, __dmul_rn(8.0 - 2.0, rs(11)));
+            float* o11 = rows + lane * MLB_OBS_COLS;
+            o11[0] = c0; o11[1] = c1; o11[2] = c2; o11[3] = c3;
+            o11[4] = __fmul_rn(c1, 0.9f);           // derived columns: float32 products (numpy >= 2), env.py:440-446
+            o11[5] = __fmul_rn(c2, 0.9f);
+            o11[6] = c6; o11[7] = c7; o11[8] = c8;
+            o11[9] = __fmul_rn(c6, 0.85f);
+            o11[10] = __fmul_rn(c6, 0.9f);
+            rv[s0 + lane] = o11[field];
+        }
+        __syncwarp();
+        float* dst = obs + ((size_t)e * S + s0) * MLB_OBS_COLS;
+        for (int i = lane; i < done * MLB_OBS_COLS; i += 32) dst[i] = rows[i];
+        used = cur;
+        __syncwarp();
+    }
+    // unread staged words all belong to the current round (staging is on demand and clipped at the round end)
+    if (lane == 0) st[624] = (uint32_t)(pos - (int)(staged - used));
+    if (reward) {
+        // every server is active (n_flow_on >= 5 > 0, env.py:410-417): the metric runs over all S values
+        __syncwarp();
+        const double r = reward_staged<float>(metric, rv, nullptr, S);
+        if (lane == 0) reward[e] = r;
+    }
+}
+
 #define CKL()                                          \
     do {                                               \
         if (cudaGetLastError() != cudaSuccess) return MLB_ECUDA; \
@@ -219,6 +353,16 @@ int mlb_legacy_obs(uint32_t* mt_state, int32_t E, int32_t S, float* obs, void* s
     if (!mt_state || !obs || E < 0 || S < 1) return MLB_EINVAL;
     if (E == 0) return MLB_OK;
     legacy_obs_kernel<<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(mt_state, E, S, obs);
+    CKL();
+    return MLB_OK;
+}
+
+int mlb_legacy_step(uint32_t* mt_state, int32_t E, int32_t S, int32_t metric, int32_t field, float* obs,
+                    double* reward, int32_t* status, void* stream) {
+    if (!mt_state || !obs || !status || E < 0 || S < 1 || S > 256) return MLB_EINVAL;
+    if (reward && (metric < 0 || metric >= MLB_REWARD_COUNT_ || field < 0 || field >= MLB_OBS_COLS)) return MLB_EINVAL;
+    if (E == 0) return MLB_OK;
+    legacy_step_kernel<<<(E + 3) / 4, 128, 0, (cudaStream_t)stream>>>(mt_state, E, S, metric, field, obs, reward, status);
     CKL();
     return MLB_OK;
 }

@@ -142,3 +142,51 @@ def test_batched_normalize_observation_bit_exact():
     assert np.array_equal(env.obs_mean[0].cpu().numpy(), g["mean"])
     assert np.array_equal(env.obs_std[0].cpu().numpy(), g["std"])
     env.close()
+
+
+def test_vec_legacy_env_matches_reference_streams():
+    """The reference's actual simulation-mode step for many envs in one launch (mlb_legacy_step, one warp per env):
+    every env reproduces its own RandomState(seed) stream -- against the reference fixtures (7 steps at 16 / 64 / 5
+    servers: 9 MT19937 twists at 64 servers, two server batches) and against the one-thread-per-env kernel over 300
+    steps including the final generator state."""
+    import ctypes as C
+    import torch
+    from marllb_b200 import VecLegacyEnv, _lib
+    g = load_golden("legacy_env")
+    for S, seed, metric in ((16, 7, "jain"), (64, 99, "variance"), (5, 3, "gini")):
+        seeds = np.array([seed, seed + 1, seed, 12345], np.uint32)
+        env = VecLegacyEnv(4, num_servers=S, seeds=seeds, reward_metric=metric, max_steps=6)
+        o = env.reset().cpu().numpy()
+        assert np.array_equal(o[0], g[f"s{S}_obs"][0]) and np.array_equal(o[2], o[0]) and not np.array_equal(o[1], o[0])
+        for k in range(6):
+            o, r, d = env.step()
+            o, r = o.cpu().numpy(), r.cpu().numpy()
+            assert np.array_equal(o[0], g[f"s{S}_obs"][k + 1]) and np.array_equal(o[2], o[0])
+            assert r[0] == pytest.approx(g[f"s{S}_rew"][k], rel=1e-12) and r[2] == r[0]
+            assert bool(d[0]) == bool(g[f"s{S}_done"][k])
+        env.check_status()
+    # long run, many seeds, odd server count: warp kernel == thread kernel, word for word
+    E, S, T = 37, 40, 300
+    seeds = (np.arange(E) * 7919 + 5).astype(np.uint32)
+    env = VecLegacyEnv(E, num_servers=S, seeds=seeds)
+    L = _lib.load()
+    st = torch.empty((E, 625), dtype=torch.int32, device="cuda")
+    ref_obs = torch.empty((E, S, 11), dtype=torch.float32, device="cuda")
+    sd = torch.as_tensor(seeds.view(np.int32)).cuda()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.mlb_legacy_seed(C.c_void_p(st.data_ptr()), C.c_void_p(sd.data_ptr()), E, stream))
+    env.reset()
+    _lib.check(L.mlb_legacy_obs(C.c_void_p(st.data_ptr()), E, S, C.c_void_p(ref_obs.data_ptr()), stream))
+    assert torch.equal(env.obs, ref_obs)
+    for k in range(T):
+        o, r, d = env.step()
+        _lib.check(L.mlb_legacy_obs(C.c_void_p(st.data_ptr()), E, S, C.c_void_p(ref_obs.data_ptr()), stream))
+        assert torch.equal(o, ref_obs), k
+    # same generator position; the thread kernel twists lazily (at the next draw), the warp kernel like numpy too:
+    # both leave position 624 untwisted, so the state words agree as well
+    assert torch.equal(env._mt, st)
+    # jain of column 10 over all servers, float64 (rewards.py:21-67)
+    x = o[:, :, 10].double()
+    want = (x.sum(1) ** 2) / (S * (x * x).sum(1))
+    np.testing.assert_allclose(r.cpu().numpy(), want.cpu().numpy(), rtol=1e-12)
+    env.check_status()
