@@ -151,10 +151,12 @@ __global__ void legacy_obs_kernel(uint32_t* __restrict__ state, int E, int S, fl
 // The reference's whole simulation-mode step is `_simulate_observation` + the reward (env.py:254-262, 425-448):
 // per server one randint(5, 20) (masked rejection: 1 + #rejected words) and six uniform() draws (2 words each),
 // in server order, from ONE MT19937 stream per env.  One warp per env:
-//   * the state row [624 words | position] of the env is contiguous, so every access below is a coalesced 128-byte
-//     line; the twist runs 32 words at a time (word k needs words k, k+1 and k+397 of the previous round or
-//     k-227 of this one: no dependence inside a 32-word chunk once all reads precede the writes), at the moment
-//     numpy would run it (position 624), so state and position stay numpy's own representation;
+//   * the state row [624 words | position] of the env is contiguous, so every access is a coalesced 128-byte line
+//     (keeping the row in shared memory for the step was measured slower: 9 KB per warp leaves 24 warps per SM);
+//     the twist runs in three phases of up to 224 words (word k needs words k, k+1 and k+397 of the previous round or k-227 of this one:
+//     inside 224 consecutive words nothing depends on a word written in the same phase once all reads precede
+//     the writes), at the moment numpy would run it (position 624), so state and position stay numpy's own
+//     representation;
 //   * tempered words are staged in shared memory in consumption order, on demand and clipped at the end of the
 //     round, so a step never twists further than numpy would have;
 //   * where a server's words start depends on every rejection before it: lane 0 walks that chain over the staged
@@ -169,18 +171,27 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     return y;
 }
 
-// in-place twist of a whole state row by one warp (numpy's mt19937_gen), 32 words per iteration
+// in-place twist of a whole state row by one warp (numpy's mt19937_gen), 224 words per phase
 __device__ __forceinline__ void mt_twist_warp(uint32_t* st, int lane) {
-    for (int base = 0; base < 624; base += 32) {
-        const int k = base + lane;
-        uint32_t nw = 0;
-        if (k < 624) {
-            const uint32_t a = st[k], b = st[k + 1 == 624 ? 0 : k + 1], c = st[k + 397 >= 624 ? k - 227 : k + 397];
-            const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-            nw = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+#pragma unroll 1
+    for (int base = 0; base < 624; base += 224) {
+        uint32_t nw[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const int k = base + lane + 32 * j;
+            nw[j] = 0;
+            if (k < 624) {
+                const uint32_t a = st[k], b = st[k + 1 == 624 ? 0 : k + 1], c = st[k + 397 >= 624 ? k - 227 : k + 397];
+                const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+                nw[j] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
         }
-        __syncwarp();                               // every read of this chunk precedes its writes
-        if (k < 624) st[k] = nw;
+        __syncwarp();                               // every read of this phase precedes its writes
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const int k = base + lane + 32 * j;
+            if (k < 624) st[k] = nw[j];
+        }
         __syncwarp();
     }
 }
@@ -195,7 +206,7 @@ legacy_step_kernel(uint32_t* __restrict__ state, int E, int S, int metric, int f
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = blockIdx.x * 4 + warp;
     if (e >= E) return;
-    uint32_t* st = state + (size_t)e * 625;
+    uint32_t* const st = state + (size_t)e * 625;  // stays in global memory: L2-resident for the step, 40 warps per SM
     uint32_t* stage = s_stage[warp];
     float* rows = s_rows[warp];
     int* off = s_off[warp];
@@ -207,6 +218,19 @@ legacy_step_kernel(uint32_t* __restrict__ state, int E, int S, int metric, int f
         // ---- lane 0 walks the rejection chain; the warp stages more words whenever it runs dry
         int done = 0;                               // servers of this batch whose start offset is known
         uint32_t cur = used;                        // start offset of server `done`
+        // the batch consumes at least 13 words per server: stage those in one go (never more than numpy would draw)
+        for (int needw = 13 * nb - (int)(staged - used); needw > 0;) {
+            if (pos == 624) {
+                mt_twist_warp(st, lane);
+                pos = 0;
+            }
+            const int take = 624 - pos < needw ? 624 - pos : needw;
+            for (int i = lane; i < take; i += 32) stage[(staged + i) & (MLB_LG_STAGE - 1)] = mt_temper(st[pos + i]);
+            staged += take;
+            pos += take;
+            needw -= take;
+        }
+        __syncwarp();
         for (;;) {
             if (lane == 0) {
                 while (done < nb) {
