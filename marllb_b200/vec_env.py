@@ -309,6 +309,37 @@ class VecLoadBalanceEnv:
                                         _dptr(self.normalized_obs), o.numel(), self._stream()), self._h)
         return self.normalized_obs
 
+    # ------------------------------------------------------------- CUDA graph replay of the step
+    def capture(self, warmup: int = 1):
+        """Capture `step(graph_action)` (the four kernels of one env step) into a CUDA graph.  Small batches
+        (config C2: 4096 envs) are bound by launch gaps, not by the kernels; a replay has none.  Write the next
+        actions into the static buffer `graph_action` [E, S] and call `step_graph()`.  The `warmup` + 1 steps run
+        here advance the envs (call reset() afterwards for a fresh episode)."""
+        if self._trace is not None or self.normalize_obs:
+            raise RuntimeError("capture() covers the plain device step (no trace stream, no normalisation)")
+        dev = self.device
+        self.graph_action = torch.zeros((self.num_envs, self.total_servers), dtype=self._adtype, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self.graph_action)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        n0 = self.launch_count
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.step(self.graph_action)
+        self.graph_launches = self.launch_count - n0          # kernels inside one replay
+        self.graph_replays = 0
+        return self
+
+    def step_graph(self):
+        """Replay the captured step; returns (obs, reward, done) like step()."""
+        self._graph.replay()
+        self.graph_replays += 1
+        return self.obs, self.reward, self.done
+
     def pinned_actions(self) -> "torch.Tensor":
         """A pinned (E, S) host tensor of the action dtype; fill it and pass it to step_host to
         skip the staging copy."""

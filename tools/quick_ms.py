@@ -18,9 +18,10 @@ def main():
     ap.add_argument("--servers", type=int, default=64)
     ap.add_argument("--burnin", type=int, default=256)
     ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
     a = ap.parse_args()
     E, S = a.envs, a.servers
-    total = a.burnin + a.steps + 8
+    total = a.burnin + a.steps + 16
     env = VecLoadBalanceEnv(E, num_servers=S, max_steps=total + 1)
     env.set_speeds(np.where(np.arange(S) % 2 == 0, 1.0, 2.0).astype(np.float32))
     rate = 128.0 * S / 64          # bench c5: 128 flows/s/agent at 64 servers, rho = 0.8
@@ -30,11 +31,17 @@ def main():
     acts = [torch.randint(0, 3, (E, S), device="cuda", dtype=torch.uint8, generator=g) for _ in range(8)]
     for k in range(a.burnin):
         env.step(acts[k % 8])
+    if a.graph:
+        env.capture()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(a.steps):
-        env.step(acts[k % 8])
+        if a.graph:
+            env.graph_action.copy_(acts[k % 8])
+            env.step_graph()
+        else:
+            env.step(acts[k % 8])
     e1.record()
     torch.cuda.synchronize()
     env.check_status()
