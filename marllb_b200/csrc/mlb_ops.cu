@@ -159,8 +159,9 @@ __global__ void legacy_obs_kernel(uint32_t* __restrict__ state, int E, int S, fl
 //     representation;
 //   * tempered words are staged in shared memory in consumption order, on demand and clipped at the end of the
 //     round, so a step never twists further than numpy would have;
-//   * where a server's words start depends on every rejection before it: lane 0 walks that chain over the staged
-//     words (rejections are rare: one trial in 16), then lane s evaluates server s in the reference's float64 /
+//   * where a server's words start depends on every rejection before it: a fix-point over the lanes (guess, count
+//     the rejected words at the guess, exclusive scan) settles all 32 starts in two or three rounds -- rejections
+//     are rare, one trial in 16 --, then lane s evaluates server s in the reference's float64 /
 //     float32 arithmetic; rows leave through shared memory as coalesced stores; the reward is reward_staged.
 #define MLB_LG_STAGE 1024           // staging ring (words), power of two, >= 13 * 32 + rejections + one chunk
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
@@ -201,23 +202,27 @@ legacy_step_kernel(uint32_t* __restrict__ state, int E, int S, int metric, int f
                    double* __restrict__ reward, int* __restrict__ status) {
     __shared__ uint32_t s_stage[4][MLB_LG_STAGE];
     __shared__ float s_rows[4][32 * MLB_OBS_COLS];
-    __shared__ int s_off[4][33];
     __shared__ float s_rv[4][256];                 // reward-field value of every server
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = blockIdx.x * 4 + warp;
     if (e >= E) return;
-    uint32_t* const st = state + (size_t)e * 625;  // stays in global memory: L2-resident for the step, 40 warps per SM
+    uint32_t* const st = state + (size_t)e * 625;  // stays in global memory: L2-resident for the step
+    if (lane < 20) prefetch_l2(st + lane * 32);    // the whole row is needed within this step (staging, then the twist)
     uint32_t* stage = s_stage[warp];
     float* rows = s_rows[warp];
-    int* off = s_off[warp];
     int pos = (int)st[624];                         // numpy's `pos`: next unread word of the current round
     uint32_t staged = 0, used = 0;                  // words staged / consumed so far in this step (ring counters)
     float* rv = s_rv[warp];
     for (int s0 = 0; s0 < S; s0 += 32) {
         const int nb = S - s0 < 32 ? S - s0 : 32;
-        // ---- lane 0 walks the rejection chain; the warp stages more words whenever it runs dry
-        int done = 0;                               // servers of this batch whose start offset is known
-        uint32_t cur = used;                        // start offset of server `done`
+        // ---- where does each server's draw start?  Server s starts 13 words after server s-1 plus every word
+        // randint(5, 20) rejected on the way (masked rejection, env.py:436).  Fix-point over the lanes:
+        // lane s guesses its start from the rejections R_s counted so far before it, counts the rejected words k_s at
+        // that guess, and an exclusive scan of k gives the next R.  After i rounds the first i servers are exact, and
+        // with one rejection in 16 trials two or three rounds settle all 32.
+        int done = nb;
+        uint32_t cur = used;
+        uint32_t my_o = used;                       // accepted randint word of this lane's server
         // the batch consumes at least 13 words per server: stage those in one go (never more than numpy would draw)
         for (int needw = 13 * nb - (int)(staged - used); needw > 0;) {
             if (pos == 624) {
@@ -232,26 +237,34 @@ legacy_step_kernel(uint32_t* __restrict__ state, int E, int S, int metric, int f
         }
         __syncwarp();
         for (;;) {
-            if (lane == 0) {
-                while (done < nb) {
-                    uint32_t o = cur;
-                    bool dry = false;
-                    for (;;) {                      // randint(5, 20): masked rejection, env.py:436
-                        if (o >= staged) { dry = true; break; }
-                        if ((stage[o & (MLB_LG_STAGE - 1)] & 15u) <= 14u) break;
-                        o++;
-                    }
-                    if (dry || o + 13 > staged) break;
-                    off[done] = (int)(o - used);    // accepted randint word; the 12 uniform words follow
-                    cur = o + 13;
-                    done++;
+            uint32_t R = 0;
+            bool isshort = false;
+            for (int round = 0; round <= nb; round++) {
+                uint32_t k = 0;
+                isshort = false;
+                if (lane < nb) {
+                    const uint32_t o = used + 13u * (uint32_t)lane + R;
+                    while (o + k < staged && (stage[(o + k) & (MLB_LG_STAGE - 1)] & 15u) == 15u) k++;
+                    isshort = o + k + 13u > staged;          // words not staged yet count as "not rejected" for now
+                    my_o = o + k;
                 }
+                uint32_t incl = k;
+#pragma unroll
+                for (int d2 = 1; d2 < 32; d2 <<= 1) {
+                    const uint32_t t = __shfl_up_sync(MLB_FULL, incl, d2);
+                    if (lane >= d2) incl += t;
+                }
+                const uint32_t newR = incl - k;
+                const bool same = newR == R;
+                R = newR;
+                cur = __shfl_sync(MLB_FULL, used + 13u * (uint32_t)nb + incl, nb - 1);
+                if (__all_sync(MLB_FULL, same)) break;
             }
-            done = __shfl_sync(MLB_FULL, done, 0);
-            cur = __shfl_sync(MLB_FULL, cur, 0);
-            if (done == nb) break;
+            // at the fix-point the lowest short lane has an exact start, so it really needs more words
+            if (!__any_sync(MLB_FULL, isshort)) break;
             if (staged - used > MLB_LG_STAGE - 64) {          // > 500 rejections in one batch: not a real stream
                 if (lane == 0) atomicOr(status, ST_ERR_RNG);
+                done = 0;
                 break;
             }
             if (pos == 624) {                       // numpy twists exactly here
@@ -267,7 +280,7 @@ legacy_step_kernel(uint32_t* __restrict__ state, int E, int S, int metric, int f
         __syncwarp();
         // ---- lane s: server s0 + s (env.py:436-446); uniform(lo, hi) = lo + (hi - lo) * random_sample()
         if (lane < done) {
-            const uint32_t o = used + (uint32_t)off[lane];
+            const uint32_t o = my_o;
             auto word = [&](int i) { return stage[(o + i) & (MLB_LG_STAGE - 1)]; };
             auto rs = [&](int i) {                  // random_sample from words i, i + 1
                 const uint32_t a = word(i) >> 5, b = word(i + 1) >> 6;
