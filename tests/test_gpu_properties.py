@@ -136,3 +136,39 @@ def test_c2_full_size_long_episode_modes_agree_and_flows_are_conserved():
     assert (cnt[:, 0] > 128).mean() > 0.9                                            # reservoirs really are in the replacement regime
     for e in envs:
         e.close()
+
+
+def test_device_poisson_generator_statistics():
+    """mlb_gen_poisson follows `_generate_poisson_trace` (training_pipeline.py:141-155): exponential gaps at `rate`,
+    arrivals kept while < horizon, exponential work; streams are time-sorted, independent per (env, agent) and a
+    function of the seed only."""
+    from marllb_b200 import VecLoadBalanceEnv
+    E, rate, mean_work, horizon = 512, 40.0, 0.3, 25.0
+    env = VecLoadBalanceEnv(E, num_servers=8, num_agents=2, policy="alias")
+    env.gen_poisson(rate, mean_work, horizon, seed=7)
+    counts, gaps, works, buckets, us = [], [], [], [], []
+    for e in range(0, E, 8):
+        for a in range(2):
+            s = env.get_arrivals(e, a)
+            t = s["time"]
+            assert t.dtype == np.float32 and np.all(np.diff(t) >= 0) and (len(t) == 0 or t[-1] < horizon)
+            counts.append(len(t)); gaps.append(np.diff(t.astype(np.float64))); works.append(s["work"])
+            buckets.append(s["bucket"]); us.append(s["u"])
+    counts = np.array(counts, np.float64)
+    n = len(counts)
+    assert abs(counts.mean() - rate * horizon) < 4 * np.sqrt(rate * horizon / n)          # Poisson mean
+    assert 0.7 < counts.var() / (rate * horizon) < 1.4                                    # ... and variance
+    g = np.concatenate(gaps)
+    assert abs(g.mean() * rate - 1) < 0.02 and abs(g.std() / g.mean() - 1) < 0.03         # exponential gaps (CV = 1)
+    w = np.concatenate(works)
+    assert abs(w.mean() / mean_work - 1) < 0.02 and w.min() >= 0
+    b, u = np.concatenate(buckets), np.concatenate(us)
+    assert b.min() == 0 and b.max() == 7 and abs(np.bincount(b, minlength=8) / len(b) - 0.125).max() < 0.01
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    first = env.get_arrivals(0, 0)["time"].copy()
+    assert not np.array_equal(first[:16], env.get_arrivals(0, 1)["time"][:16])            # streams differ
+    env.gen_poisson(rate, mean_work, horizon, seed=7)
+    assert np.array_equal(first, env.get_arrivals(0, 0)["time"])                          # same seed, same stream
+    env.gen_poisson(rate, mean_work, horizon, seed=8)
+    assert not np.array_equal(first[:16], env.get_arrivals(0, 0)["time"][:16])
+    env.close()
