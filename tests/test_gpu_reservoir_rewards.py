@@ -157,3 +157,30 @@ def test_env_step_with_fair_fn_reward():
             rtol = 1e-3 if metric.endswith("_exp") else 1e-5
             np.testing.assert_allclose(rew.cpu().numpy(), r_ref, rtol=rtol, atol=1e-300, err_msg=metric)
         env.close()
+
+
+def test_reference_statistical_properties_of_the_sampler():
+    """The reference's statistical tests restated on the batched device sampler (tests/test_reservoir.py:243-316):
+    chi-square uniformity of Algorithm R over 500 seeded trials (capacity 100, stream of 1000 distinct items, one
+    trial per reservoir, all trials in one launch) and convergence of the sample mean."""
+    import torch
+    from marllb_b200.reservoir import BatchedReservoirs
+    trials, cap, n = 500, 100, 1000
+    b = BatchedReservoirs(trials, cap, seeds=np.arange(trials))            # ReservoirSampler(capacity, seed=trial)
+    stream = np.tile(np.arange(n, dtype=np.float32), (trials, 1))
+    b.add(stream, stream * 1e-3)
+    b.check_status()
+    vals = b.values[:, :cap].cpu().numpy().astype(np.int64)
+    counts = np.bincount(vals.reshape(-1), minlength=n).astype(np.float64)
+    expected = trials * cap / n
+    chi_square = float(((counts - expected) ** 2 / expected).sum())
+    assert chi_square < 1100, chi_square                                   # :286-287 (dof 999, alpha 0.05: ~1073)
+    for row in vals[:16]:
+        assert len(set(row.tolist())) == cap                               # a reservoir never holds an item twice
+    # :289-316: mean of a sample of N(100, 15) values stays close to the stream mean
+    rng = np.random.RandomState(42)
+    data = rng.normal(100.0, 15.0, (1, 10000)).astype(np.float32)
+    s = BatchedReservoirs(1, 128, seeds=[42])
+    s.add(data, np.arange(10000, dtype=np.float32)[None] * 1e-3)
+    mean = float(s.features(0.9, 10.0)[0, 0])
+    assert abs(mean - float(data.mean())) < 5.0
