@@ -241,6 +241,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # host side of the end-to-end step: pinned buffers on the NUMA node next to this rank's GPU
+    from marllb_b200.shard import bind_host_to_gpu
+    prev_affinity = bind_host_to_gpu(local) if (world > 1 and not os.environ.get("MLB_NO_NUMA_BIND")) else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = dict(WORKLOADS[args.workload])
@@ -475,6 +478,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu and rollout is None and sac is None:
             del env
             torch.cuda.empty_cache()
+            if prev_affinity is not None:
+                os.sched_setaffinity(0, prev_affinity)       # the CPU baseline uses every host core
             v, steps, cores = cpu_oracle_rate(wl, n_envs=0 or max(4 * (os.cpu_count() or 1), 32),
                                               burnin=args.burnin, budget_s=args.cpu_budget, threads=0)
             out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",

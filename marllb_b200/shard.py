@@ -28,3 +28,26 @@ def owner_of(env_id: int, total_envs: int, world: int) -> int:
     if env_id < cut:
         return env_id // (base + 1)
     return rem + (env_id - cut) // max(base, 1)
+
+
+def bind_host_to_gpu(device: int = 0):
+    """Pin the calling process to the CPU cores (hence the NUMA node) closest to `device`, as NVML reports them.
+    Pinned host buffers allocated afterwards land on that node, so the per-step device->host copy of the
+    observations does not cross the socket interconnect -- what limits the end-to-end step once several ranks of
+    one box copy at the same time.  Returns the previous affinity set (restore with os.sched_setaffinity(0, prev))
+    or None when NVML or the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device
+        if vis:
+            ids = vis.split(",")
+            if device < len(ids) and ids[device].strip().isdigit():
+                phys = int(ids[device])
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return prev
+    except Exception:
+        return None
