@@ -133,3 +133,15 @@ def test_spaces_and_traces_host_logic(tmp_path):
     assert parts[0]["time"].tolist() == [0.5, 3.0] and parts[1]["time"].tolist() == [0.75]
     pt = poisson_trace(100.0, 2.0, rng=np.random.RandomState(0), servers=4)
     assert np.all(np.diff(pt["time"]) >= 0) and pt["time"].max() < 2.0 and set(pt) == {"time", "work", "bucket", "u"}
+
+
+def test_bind_host_to_gpu_is_a_noop_without_a_gpu():
+    """shard.bind_host_to_gpu never raises: without NVML / a device it returns None and leaves the affinity alone."""
+    import os
+    from marllb_b200.shard import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    prev = bind_host_to_gpu(0)
+    assert prev is None or prev == before
+    if prev is not None:
+        os.sched_setaffinity(0, prev)
+    assert os.sched_getaffinity(0) == before
