@@ -23,7 +23,15 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-os.environ["NCCL_DEBUG"] = os.environ.get("MLB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+# A NCCL_DEBUG level the caller exported is left alone (its output goes wherever the caller pointed it).  Otherwise
+# NCCL logs at INFO into a file, so that stdout stays the one JSON line and the communicator evidence (nranks,
+# NVLS / ring choice) can still be read afterwards.
+if "NCCL_DEBUG" not in os.environ:
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+    if "NCCL_DEBUG_FILE" not in os.environ:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_rank%h_%p.log")
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
@@ -232,6 +240,27 @@ def workload_config(args, wl):
             "parallelism": f"env-sharded x{args.gpus} (no data-path collective)"}
 
 
+def build_env(wl, total_steps, rank=0, local=0, feature_cache=True, rng_mode="replay"):
+    """The benchmarked env, exactly: used by run_ours and by tests/test_gpu_bench_parity.py (which steps THIS env and
+    feeds sampled envs' device-generated arrivals to the CPU oracle).  Returns (env, speeds, action pool, generator)."""
+    import torch
+    from marllb_b200 import VecLoadBalanceEnv
+    E, A, S, K = wl["envs"], wl["agents"], wl["servers"], wl["K"]
+    env = VecLoadBalanceEnv(E, num_servers=S, num_agents=A, reservoir_capacity=K, max_steps=10 ** 9,
+                            action_type="continuous" if wl.get("policy") == "sac" else "discrete",
+                            action_dtype="uint8", env_id_base=rank * E, device=local,
+                            feature_cache=feature_cache, rng_mode=rng_mode)
+    speeds = np.where(np.arange(S * A) % 2 == 0, 1.0, 2.0).astype(np.float32)
+    env.set_speeds(speeds)
+    mean_work = RHO * float(speeds[:S].sum()) / wl["rate"]
+    env.gen_poisson(wl["rate"], mean_work, (total_steps + 1) * DT, seed=1234)
+    env.reset()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99 + rank)
+    pool = [torch.randint(0, 3, (E, S * A), generator=g, device="cuda", dtype=torch.uint8) for _ in range(8)]
+    return env, speeds, pool, g
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -252,18 +281,7 @@ def run_ours(args):
     E, A, S, K = wl["envs"], wl["agents"], wl["servers"], wl["K"]
     e2e_steps = min(args.steps, args.e2e_steps)
     total_steps = args.burnin + args.warmup + args.steps + 20 + e2e_steps
-    env = VecLoadBalanceEnv(E, num_servers=S, num_agents=A, reservoir_capacity=K, max_steps=10 ** 9,
-                            action_type="continuous" if wl.get("policy") == "sac" else "discrete",
-                            action_dtype="uint8", env_id_base=rank * E, device=local,
-                            feature_cache=not args.no_feature_cache)
-    speeds = np.where(np.arange(S * A) % 2 == 0, 1.0, 2.0).astype(np.float32)
-    env.set_speeds(speeds)
-    mean_work = RHO * float(speeds[:S].sum()) / wl["rate"]
-    env.gen_poisson(wl["rate"], mean_work, (total_steps + 1) * DT, seed=1234)
-    env.reset()
-    g = torch.Generator(device="cuda")
-    g.manual_seed(99 + rank)
-    pool = [torch.randint(0, 3, (E, S * A), generator=g, device="cuda", dtype=torch.uint8) for _ in range(8)]
+    env, speeds, pool, g = build_env(wl, total_steps, rank, local, not args.no_feature_cache, args.rng_mode)
     rollout = None
     if wl.get("policy") == "qmix":
         from marllb_b200.policy import QMIXAgent, ops as pops
@@ -503,6 +521,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-feature-cache", action="store_true")
+    ap.add_argument("--rng-mode", default="replay", choices=["replay", "philox"],
+                    help="reservoir index stream: replayed RandomState rows shared by all envs (reference parity) "
+                         "or per-env counter-based Philox")
     ap.add_argument("--no-graph", action="store_true", help="c3: launch the rollout step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

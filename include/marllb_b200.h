@@ -56,6 +56,16 @@ enum {
     MLB_ACTION_DISCRETE_U8 = 2   /* same as DISCRETE_I32, one byte per server    */
 };
 
+/* Reservoir index stream (the `j = rng.randint(0, count + 1)` of reservoir.py:76).
+ *   MLB_RNG_REPLAY: every reservoir of server j replays np.random.RandomState(rng_seed_base + j) from a table of
+ *     rng_table_len raw MT19937 words -- bit-for-bit the reference's stream, shared by all envs (reference parity;
+ *     needs S * rng_table_len * 4 bytes of table and fails with MLB_ERNG when a row is used up).
+ *   MLB_RNG_PHILOX: word c of the stream of (global env g, server j) is
+ *     philox4x32_10(counter = {c >> 2, j, g, 0x52535652}, key = {rng_seed_base, 0x4d4c4232})[c & 3],
+ *     consumed with the same masked-rejection rule.  Independent per env, no table, no length cap; results do not
+ *     depend on how envs are sharded (g = env_id_base + local index).  CPU twin: oracle/flow_oracle.c. */
+enum { MLB_RNG_REPLAY = 0, MLB_RNG_PHILOX = 1 };
+
 /* reward metrics 0-8: problem-03-rl-environment/src/rewards.py:297-307;
  * 9-14: the original testbed's fair_fn table, src/lb/env.py:73-156 ('var' and 'max' of that table
  * are MLB_REWARD_VARIANCE and MLB_REWARD_MAX) */
@@ -119,7 +129,8 @@ typedef struct mlb_config {
     int32_t env_id_base;       /* global id of env 0 (multi-GPU sharding): keys the
                                   synthetic-arrival streams so results do not depend
                                   on how envs are split over GPUs                  */
-    int32_t reserved[6];
+    int32_t rng_mode;          /* MLB_RNG_* (0 = replay: the default, and what zeroed reserved words meant) */
+    int32_t reserved[5];
 } mlb_config;
 
 typedef struct mlb_env mlb_env; /* opaque handle */

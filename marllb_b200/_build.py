@@ -20,29 +20,58 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the marllb_b200 CUDA library cannot be built")
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+HASH_PATH = LIB_PATH + ".hash"
+
+
+def _source_hash() -> str:
+    """sha256 over every source the library is built from + the flags.  Content, not mtimes: the built .so
+    travels to GPU boxes in a snapshot whose timestamps mean nothing."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     deps.append(os.path.join(os.path.dirname(_HERE), "include", "marllb_b200.h"))
     deps.append(os.path.join(os.path.dirname(_HERE), "include", "marllb_b200_policy.h"))
-    return any(os.path.getmtime(p) > t for p in deps)
+    for p in deps:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile marllb_b200/libmarllb_b200.so with nvcc for sm_100a (cross-compiles without a GPU)."""
     if not force and not _stale():
         return LIB_PATH
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *srcs]
-    if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True, cwd=CSRC)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    import fcntl
+    # one builder at a time (torchrun starts N ranks at once); the others wait, then find a fresh library
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            want = _source_hash()
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+            cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *srcs]
+            if os.path.exists("/usr/bin/g++"):
+                cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd))
+            subprocess.run(cmd, check=True, cwd=CSRC)
+            os.replace(tmp, LIB_PATH)
+            with open(HASH_PATH + ".tmp", "w") as f:
+                f.write(want + "\n")
+            os.replace(HASH_PATH + ".tmp", HASH_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -16,6 +16,7 @@ OK, EINVAL, ECUDA, ENOMEM, ESTATE, ERNG, EACTION = 0, -1, -2, -3, -4, -5, -6
 HOST, DEVICE = 0, 1
 POLICIES = {"sed": 0, "lsq": 1, "alias": 2, "sed2": 3, "lsq2": 4}    # node.c:393-460
 ACTION_DISCRETE_I32, ACTION_CONTINUOUS_F32, ACTION_DISCRETE_U8 = 0, 1, 2
+RNG_MODES = {"replay": 0, "philox": 1}
 METRICS = {"jain": 0, "variance": 1, "std": 2, "cv": 3, "max": 4, "min": 5,
            "product": 6, "range": 7, "gini": 8,           # rewards.py:297-307
            # the original testbed's fair_fn table, src/lb/env.py:152-161
@@ -49,7 +50,7 @@ class Config(C.Structure):
                 ("max_steps", C.c_int32), ("rng_seed_base", C.c_uint32),
                 ("rng_table_len", C.c_int32), ("feature_cache", C.c_int32),
                 ("record_assign", C.c_int32), ("env_id_base", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("rng_mode", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class MlbError(RuntimeError):
@@ -67,8 +68,9 @@ def load():
     if _lib is not None:
         return _lib
     path = os.environ.get("MARLLB_B200_LIB") or _build.LIB_PATH   # override: A/B builds of the same library
-    if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("MARLLB_B200_REBUILD") == "1"):
-        path = _build.build()
+    if path == _build.LIB_PATH:
+        # content-hash staleness check (see _build._source_hash); builds under a file lock
+        path = _build.build(force=os.environ.get("MARLLB_B200_REBUILD") == "1")
     L = C.CDLL(path)
     vp, i32, i64, u64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
     sig = {

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +59,9 @@ struct mlb_env {
     int prof_cap = 0, prof_n = 0;
     size_t state_bytes[MLB_F_COUNT_] = {0};
     void* state_ptr[MLB_F_COUNT_] = {nullptr};
+    // mlb_stage_arrivals may run on a second host thread next to mlb_step (see the header): the allocation list
+    // and the error text are the two things both threads write
+    std::mutex mu;
 };
 
 static std::string g_create_err;
@@ -68,7 +72,12 @@ static int fail(mlb_env* h, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (h) h->err = buf; else g_create_err = buf;
+    if (h) {
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->err = buf;
+    } else {
+        g_create_err = buf;
+    }
     return code;
 }
 
@@ -85,6 +94,7 @@ static cudaError_t dalloc(mlb_env* h, T** p, size_t n) {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
     if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(h->mu);
         h->allocs.push_back(q);
         *p = reinterpret_cast<T*>(q);
     }
@@ -95,6 +105,12 @@ static cudaError_t dalloc(mlb_env* h, T** p, size_t n) {
 __global__ void fill_f32_kernel(float* p, size_t n, float v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = v;
+}
+
+// speeds[S] (device) broadcast to every env's row of d.speed [E][S]
+__global__ void bcast_rows_kernel(float* __restrict__ dst, const float* __restrict__ row, int S, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __ldg(row + (int)(i % (size_t)S));
 }
 
 // reset(): zero every per-env slice of the selected envs (env.py:186-213;
@@ -131,21 +147,6 @@ __global__ void reset_kernel(const DevState d, const uint8_t* __restrict__ mask)
         d.done[e] = 0;
         d.step[e] = 0;
     }
-}
-
-// Philox4x32-10 (Salmon et al. 2011), counter-based
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
 // One warp per (env, agent) stream: exponential inter-arrivals (rate/s) kept
@@ -191,25 +192,29 @@ __global__ void gen_poisson_kernel(float* __restrict__ time, float* __restrict__
 }
 
 // ------------------------------------------------------------------ helpers
-template <int POLICY>
+template <int POLICY, int RNG>
 static const void* event_fn_r(int R) {
     switch (R) {
-    case 1: return (const void*)event_kernel<POLICY, 1>;
-    case 2: return (const void*)event_kernel<POLICY, 2>;
-    case 4: return (const void*)event_kernel<POLICY, 4>;
-    default: return (const void*)event_kernel<POLICY, 8>;
+    case 1: return (const void*)event_kernel<POLICY, 1, RNG>;
+    case 2: return (const void*)event_kernel<POLICY, 2, RNG>;
+    case 4: return (const void*)event_kernel<POLICY, 4, RNG>;
+    default: return (const void*)event_kernel<POLICY, 8, RNG>;
     }
 }
 static int lanes_r(int Sa) { return Sa <= 32 ? 1 : (Sa <= 64 ? 2 : (Sa <= 128 ? 4 : 8)); }
-static const void* event_fn(int policy, int Sa) {
-    const int R = lanes_r(Sa);
+template <int RNG>
+static const void* event_fn_p(int policy, int R) {
     switch (policy) {
-    case MLB_POLICY_SED: return event_fn_r<MLB_POLICY_SED>(R);
-    case MLB_POLICY_LSQ: return event_fn_r<MLB_POLICY_LSQ>(R);
-    case MLB_POLICY_SED2: return event_fn_r<MLB_POLICY_SED2>(R);
-    case MLB_POLICY_LSQ2: return event_fn_r<MLB_POLICY_LSQ2>(R);
-    default: return event_fn_r<MLB_POLICY_ALIAS>(R);
+    case MLB_POLICY_SED: return event_fn_r<MLB_POLICY_SED, RNG>(R);
+    case MLB_POLICY_LSQ: return event_fn_r<MLB_POLICY_LSQ, RNG>(R);
+    case MLB_POLICY_SED2: return event_fn_r<MLB_POLICY_SED2, RNG>(R);
+    case MLB_POLICY_LSQ2: return event_fn_r<MLB_POLICY_LSQ2, RNG>(R);
+    default: return event_fn_r<MLB_POLICY_ALIAS, RNG>(R);
     }
+}
+static const void* event_fn(int policy, int Sa, int rng) {
+    const int R = lanes_r(Sa);
+    return rng == MLB_RNG_PHILOX ? event_fn_p<MLB_RNG_PHILOX>(policy, R) : event_fn_p<MLB_RNG_REPLAY>(policy, R);
 }
 static const void* feature_fn(int Sa, bool small) {
     switch (lanes_r(Sa)) {
@@ -256,7 +261,7 @@ static int launch_cfg(mlb_env* h) {
     if (h->ft_smem > 227 * 1024 || h->ev_smem > 227 * 1024)
         return fail(h, MLB_EINVAL, "configuration needs %zu B of shared memory per block (> 227 KB)",
                     h->ft_smem > h->ev_smem ? h->ft_smem : h->ev_smem);
-    cudaError_t e = set_smem(event_fn(c.policy, c.servers_per_agent), h->ev_smem, h->ev_threads, 4 * MLB_EV_MINBLOCKS);
+    cudaError_t e = set_smem(event_fn(c.policy, c.servers_per_agent, c.rng_mode), h->ev_smem, h->ev_threads, 4 * MLB_EV_MINBLOCKS);
     if (e == cudaSuccess) e = set_smem(feature_fn(c.servers_per_agent, h->ft_threads <= 128 && !getenv("MLB_FT_BIG")), h->ft_smem, h->ft_threads, h->ft_threads <= 128 ? 48 : 32);
     h->use_pair = h->d.KP == 128 && h->d.K == 128 && c.feature_cache == 1 && !getenv("MLB_NO_PAIR");
     h->d.use_pair = h->use_pair ? 1 : 0;
@@ -378,6 +383,11 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     if ((double)c.num_envs * c.num_agents * c.servers_per_agent * (double)c.queue_cap >= 4294967296.0)
         return fail(nullptr, MLB_EINVAL, "num_envs * servers * queue_cap must stay below 2^32 (32-bit ring offsets)");
 
+    if (c.rng_mode != MLB_RNG_REPLAY && c.rng_mode != MLB_RNG_PHILOX) return fail(nullptr, MLB_EINVAL, "unknown rng_mode %d", c.rng_mode);
+    if (c.rng_mode == MLB_RNG_REPLAY &&
+        (double)c.num_agents * c.servers_per_agent * (double)(c.rng_table_len > 0 ? c.rng_table_len : 65536) >= 4294967296.0)
+        return fail(nullptr, MLB_EINVAL, "servers * rng_table_len must stay below 2^32 (32-bit replay-table offsets)");
+
     mlb_env* h = new (std::nothrow) mlb_env();
     if (!h) return fail(nullptr, MLB_ENOMEM, "host allocation failed");
     h->cfg = c;
@@ -405,6 +415,7 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     d.reward_metric = c.reward_metric; d.reward_field = c.reward_field; d.max_steps = c.max_steps;
     d.L = c.rng_table_len > 0 ? c.rng_table_len : 65536;
     d.feature_cache = c.feature_cache; d.record_assign = c.record_assign;
+    d.rng_mode = c.rng_mode; d.rng_key = c.rng_seed_base; d.env_id_base = c.env_id_base;
     for (int i = 0; i < 8; i++) d.dw[i] = c.discrete_weights[i];
     d.min_w = c.min_weight; d.max_w = c.max_weight; d.dt = c.dt;
     d.decay = c.decay; d.log2_decay = (float)std::log2(c.decay);
@@ -433,8 +444,8 @@ int mlb_create(const mlb_config* cfg, mlb_env** out) {
     CKC(dalloc(h, reinterpret_cast<uint8_t**>(&h->d_action), h->action_bytes));
     CKC(cudaMemset(d.status, 0, sizeof(int)));
 
-    // RNG replay table: row j = raw MT19937 words of RandomState(seed_base + j)
-    {
+    // RNG replay table: row j = raw MT19937 words of RandomState(seed_base + j); none in philox mode
+    if (c.rng_mode == MLB_RNG_REPLAY) {
         std::vector<uint32_t> tab((size_t)d.S * d.L);
         for (int j = 0; j < d.S; j++) {
             MT19937 g(c.rng_seed_base + (uint32_t)j);
@@ -505,8 +516,9 @@ int mlb_set_speeds(mlb_env* h, const float* speeds, int64_t n, int loc, void* st
             CK(h, cudaMemcpyAsync(d.speed, rep.data(), rep.size() * 4, cudaMemcpyHostToDevice, st));
             CK(h, cudaStreamSynchronize(st));
         } else {
-            for (int e = 0; e < d.E; e++)
-                CK(h, cudaMemcpyAsync(d.speed + (size_t)e * d.S, speeds, (size_t)d.S * 4, kind, st));
+            bcast_rows_kernel<<<148 * 4, 256, 0, st>>>(d.speed, speeds, d.S, (size_t)d.E * d.S);
+            h->launches++;
+            CK(h, cudaGetLastError());
         }
     } else {
         return fail(h, MLB_EINVAL, "speeds: n must be S=%d or E*S=%lld", d.S, (long long)d.E * d.S);
@@ -755,7 +767,7 @@ static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_
     const int wpb = h->ev_threads / 32;
     const int ev_blocks = (int)(((int64_t)(e1 - e0) * dv.A + wpb - 1) / wpb);
     if (pe) CK(h, cudaEventRecord(pe[0], st));
-    CK(h, cudaLaunchKernel(event_fn(dv.policy, dv.Sa), dim3(ev_blocks), dim3(h->ev_threads), ev_args, h->ev_smem, st));
+    CK(h, cudaLaunchKernel(event_fn(dv.policy, dv.Sa, dv.rng_mode), dim3(ev_blocks), dim3(h->ev_threads), ev_args, h->ev_smem, st));
     if (pe) CK(h, cudaEventRecord(pe[1], st));
     void* ft_args[] = {&dv};
     if (h->use_pair) {

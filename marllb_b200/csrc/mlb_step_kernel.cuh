@@ -104,22 +104,67 @@ __device__ __forceinline__ int res_draw_slot(uint32_t cnt, uint32_t& cur, const 
     return v < (uint32_t)K ? (int)v : -1;  // reservoir.py:78-85
 }
 
+// Philox4x32-10 (Salmon et al., SC'11), the counter-based generator of rng_mode = MLB_RNG_PHILOX.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Word `c` of the index stream of (global env g, server j): the stream every reservoir of that server draws from
+// (both metrics: the reference hands the same seed to every metric's sampler, reservoir.py:261-265), each with its
+// own cursor.  Twin: ora_philox_word in oracle/flow_oracle.c.  Out of line: the 10 rounds would otherwise be inlined
+// at both add sites of the event kernel.
+#define MLB_PHILOX_TAG 0x52535652u   /* "RSVR" */
+#define MLB_PHILOX_KEY1 0x4d4c4232u  /* "MLB2" */
+static __device__ __noinline__ uint32_t philox_stream_word(uint32_t c, uint32_t j, uint32_t g, uint32_t key0) {
+    uint32_t r[4];
+    philox4x32_10(c >> 2, j, g, MLB_PHILOX_TAG, key0, MLB_PHILOX_KEY1, r);
+    const uint32_t lo = (c & 1u) ? r[1] : r[0], hi = (c & 1u) ? r[3] : r[2];
+    return (c & 2u) ? hi : lo;
+}
+
+// res_draw_slot for rng_mode = MLB_RNG_PHILOX: the same masked-rejection rule (numpy's randint(0, count+1)) over the
+// counter-based stream; no table, no length cap.
+__device__ __forceinline__ int res_draw_slot_philox(uint32_t cnt, uint32_t& cur, uint32_t j, uint32_t g, uint32_t key0, int K) {
+    if (cnt < (uint32_t)K) return (int)cnt;  // fill phase, reservoir.py:65-73
+    const uint32_t mask = 0xffffffffu >> __clz(cnt);
+    uint32_t c = cur, v;
+    do {
+        v = philox_stream_word(c, j, g, key0) & mask;
+        c++;
+    } while (v > cnt);
+    cur = c;
+    return v < (uint32_t)K ? (int)v : -1;  // reservoir.py:78-85
+}
+
 // per-warp view of the global arrays (32-bit offsets below these bases)
 // 32-bit element offsets from the array bases in the kernel parameters (which live in the constant bank, not
 // in registers): the event kernel is register-starved at 48 resident warps per SM
 struct WarpGlobals {
     uint32_t res4;      // this agent's reservoirs [Sa][2][KP], in units of 4 floats (mlb_create checks the range)
     uint32_t ring;      // [Sa][Q] (arrival, finish) float2 index
-    uint32_t mt;        // replay rows of this agent's servers [Sa][L]
+    uint32_t mt;        // replay rows of this agent's servers [Sa][L]; philox mode: index of the agent's first server
+    uint32_t genv;      // philox mode: global env id
 };
 
 // ReservoirSampler.add by the owning lane of server j, metric m.
-template <int SP>
+template <int SP, int RNG>
 __device__ __forceinline__ void res_add(const DevState& d, uint32_t* sm, const WarpGlobals& g, int m, int j,
                                         float value, float ts) {
     const uint32_t cnt = sm[(F_CNT0 + m) * SP + j];
     uint32_t c = sm[(F_CUR0 + m) * SP + j];
-    const int slot = res_draw_slot(cnt, c, d.mt_table + ((size_t)g.mt + (size_t)j * d.L), d.L, d.K, d.status);
+    const int slot = RNG == MLB_RNG_PHILOX
+                         ? res_draw_slot_philox(cnt, c, g.mt + (uint32_t)j, g.genv, d.rng_key, d.K)
+                         : res_draw_slot(cnt, c, d.mt_table + ((size_t)g.mt + (size_t)j * d.L), d.L, d.K, d.status);
     sm[(F_CUR0 + m) * SP + j] = c;
     sm[(F_CNT0 + m) * SP + j] = cnt + 1;
     if (slot >= 0) {
@@ -272,7 +317,7 @@ __device__ __noinline__ double reward_staged(int metric, const T* rv, const uint
 #ifndef MLB_EV_MINBLOCKS
 #define MLB_EV_MINBLOCKS 10
 #endif
-template <int POLICY, int R>
+template <int POLICY, int R, int RNG>
 __global__ void __launch_bounds__(128, MLB_EV_MINBLOCKS)
 event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -304,7 +349,8 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
     WarpGlobals g;
     g.res4 = (uint32_t)(sbase * 2 * (d.KP >> 2));
     g.ring = (uint32_t)(sbase * d.Q);
-    g.mt = (uint32_t)((size_t)seed0 * d.L);
+    g.mt = RNG == MLB_RNG_PHILOX ? (uint32_t)seed0 : (uint32_t)((size_t)seed0 * d.L);
+    g.genv = (uint32_t)(d.env_id_base + e);
     const int Q = d.Q;
 
     // ---------------- phase 0: load state, action -> weights -----------------
@@ -406,7 +452,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                         n -= 1;                                             // src/vpp/lb/lbhash.h:120
                         float2 nx = make_float2(0.f, MLB_INF);
                         if (n > 0) nx = d.ring[g.ring + j * Q + h];          // in flight during the add
-                        res_add<SP>(d, sm, g, 0, j, __fsub_rn(fin, arr), fin);  // lbhash.h:122-124
+                        res_add<SP, RNG>(d, sm, g, 0, j, __fsub_rn(fin, arr), fin);  // lbhash.h:122-124
                         arr = nx.x;
                         fin = nx.y;
                     } while (fin < a);
@@ -495,7 +541,7 @@ event_kernel(const __grid_constant__ DevState d, const void* __restrict__ action
                 pos = (pos + 1 == (uint32_t)Q) ? 0u : pos + 1;
                 float nx = 0.f;
                 if (q + 1 < n) nx = d.ring[g.ring + j * Q + pos].x;          // in flight during the add
-                res_add<SP>(d, sm, g, 1, j, __fsub_rn(t1, arr), t1);
+                res_add<SP, RNG>(d, sm, g, 1, j, __fsub_rn(t1, arr), t1);
                 arr = nx;
             }
 #pragma unroll

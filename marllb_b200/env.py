@@ -74,6 +74,7 @@ class LoadBalanceEnv:
         queue_capacity: int = 160,
         realtime: bool = False,
         device: int = 0,
+        num_lb_agents: int = 1,
     ):
         self.num_servers = num_servers
         self.action_type = action_type
@@ -129,8 +130,13 @@ class LoadBalanceEnv:
         else:
             if reward_field not in FEATURE_NAMES:
                 raise ValueError(f"Unknown reward_field: {reward_field}")
+            # num_lb_agents > 1: the A LB agents of MultiAgentLoadBalanceEnv (multi_agent_env.py:57-76) each assign
+            # their own arrival stream to their own block of num_servers / A servers
+            if num_servers % num_lb_agents:
+                raise ValueError("num_servers must be a multiple of num_lb_agents")
+            A = num_lb_agents
             self._vec = VecLoadBalanceEnv(
-                1, num_servers=num_servers, num_agents=1, action_type=action_type,
+                1, num_servers=num_servers // A, num_agents=A, action_type=action_type,
                 discrete_weights=self.discrete_weights, max_weight=max_weight, min_weight=min_weight,
                 reward_metric=reward_metric, reward_field=reward_field, step_interval=step_interval,
                 max_steps=max_steps, policy=policy, reservoir_capacity=reservoir_capacity,
@@ -139,12 +145,16 @@ class LoadBalanceEnv:
                 self._vec.set_speeds(server_speeds)
             hz = horizon if horizon is not None else float(step_interval) * max_steps
             if arrivals is not None:
-                self._vec.load_arrivals([arrivals])
+                streams = [arrivals] if isinstance(arrivals, dict) else list(arrivals)
+                if len(streams) != A:
+                    raise ValueError(f"arrivals: expected {A} streams (one per LB agent), got {len(streams)}")
+                self._vec.load_arrivals(streams)
             elif trace is not None:
-                from .traces import load_trace
-                self._vec.load_arrivals([load_trace(trace, horizon=hz)])
+                from .traces import load_trace, split_round_robin
+                tr = load_trace(trace, horizon=hz)
+                self._vec.load_arrivals([tr] if A == 1 else split_round_robin(tr, A))   # row r -> agent r mod A
             else:
-                rate = arrival_rate if arrival_rate is not None else 8.0 * num_servers
+                rate = arrival_rate if arrival_rate is not None else 8.0 * num_servers / A   # per LB agent
                 self._vec.gen_poisson(rate, mean_work, hz, seed=0 if seed is None else int(seed))
 
     # ------------------------------------------------------------------ spaces

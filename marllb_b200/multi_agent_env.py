@@ -28,9 +28,11 @@ class MultiAgentLoadBalanceEnv:
         self.total_servers = num_agents * servers_per_agent                  # multi_agent_env.py:59
         self.global_reward = global_reward
         self.strict_reference = strict_reference
+        # flow-level simulation (mode='flow' or trace= / arrivals= / arrival_rate=): the wrapped env runs one
+        # VecLoadBalanceEnv(1, num_agents=A) -- every LB agent assigns its own arrival stream over its own servers --
+        # like LoadBalanceEnv does for one agent (env.py:132-137 here); `arrivals` is then a list of A streams
         if env_kwargs.get('mode') == 'flow' or any(k in env_kwargs for k in ('trace', 'arrivals', 'arrival_rate')):
-            raise ValueError("flow-level multi-agent simulation is batched: use "
-                             "marllb_b200.VecLoadBalanceEnv(num_agents=...)")
+            env_kwargs = dict(env_kwargs, num_lb_agents=num_agents)
         self.env = LoadBalanceEnv(num_servers=self.total_servers, action_type=action_type,
                                   reward_metric=reward_metric, max_steps=max_steps,
                                   use_shm=use_shm, **env_kwargs)             # multi_agent_env.py:63-69

@@ -144,16 +144,55 @@ class Adam:
             ops.adam_step(b.flat_p, b.flat_g, self._m, self._v, self.lr, self.t)
 
     def state_dict(self):
-        return {"step": self.t, "exp_avg": [m.clone() for m in self.m], "exp_avg_sq": [v.clone() for v in self.v],
-                "lr": self.lr}
+        """torch.optim.Adam's own layout -- {'state': {i: {step, exp_avg, exp_avg_sq}}, 'param_groups': [...]} with the
+        parameters numbered in bucket order (= the reference's optimiser parameter order, sac_agent.py:93-106,
+        qmix_agent.py:108-113) -- so checkpoints move between the reference agents and these in both directions."""
+        group = dict(torch.optim.Adam([torch.zeros(1)], lr=self.lr).state_dict()["param_groups"][0])
+        group["lr"] = self.lr
+        group["params"] = list(range(len(self.params)))
+        state = {}
+        if self.t > 0:                       # torch creates the per-parameter state on the first step
+            for i, (m, v) in enumerate(zip(self.m, self.v)):
+                state[i] = {"step": torch.tensor(float(self.t)), "exp_avg": m.detach().clone(),
+                            "exp_avg_sq": v.detach().clone()}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.t = int(sd["step"])
+        """Accepts torch.optim.Adam's layout (reference checkpoints) and this package's round-1 layout
+        ({'step', 'exp_avg': [...], 'exp_avg_sq': [...]})."""
+        if "param_groups" in sd:
+            groups = sd["param_groups"]
+            idx = [i for g in groups for i in g["params"]]
+            if len(idx) != len(self.params):
+                raise ValueError(f"optimizer state has {len(idx)} parameters, this optimiser has {len(self.params)}")
+            g0 = groups[0]
+            if tuple(g0.get("betas", (0.9, 0.999))) != (0.9, 0.999) or g0.get("eps", 1e-8) != 1e-8 \
+                    or g0.get("weight_decay", 0) != 0 or g0.get("amsgrad", False):
+                raise ValueError("only torch.optim.Adam defaults (betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad) are supported")
+            self.lr = float(g0.get("lr", self.lr))
+            st = sd["state"]
+            if not st:
+                self.t = 0
+                self._m.zero_()
+                self._v.zero_()
+            else:
+                steps = {int(float(st[i]["step"])) for i in idx if i in st}
+                if len(steps) != 1 or any(i not in st for i in idx):
+                    raise ValueError("optimizer state must hold every parameter at the same step count")
+                self.t = steps.pop()
+                for k, i in enumerate(idx):
+                    if tuple(st[i]["exp_avg"].shape) != tuple(self.m[k].shape):
+                        raise ValueError(f"optimizer state of parameter {i}: shape {tuple(st[i]['exp_avg'].shape)} "
+                                         f"vs {tuple(self.m[k].shape)}")
+                    self.m[k].copy_(st[i]["exp_avg"])
+                    self.v[k].copy_(st[i]["exp_avg_sq"])
+        else:
+            self.t = int(sd["step"])
+            for m, s_ in zip(self.m, sd["exp_avg"]):
+                m.copy_(s_)
+            for v, s_ in zip(self.v, sd["exp_avg_sq"]):
+                v.copy_(s_)
         self._t_dev.fill_(self.t)
-        for m, s in zip(self.m, sd["exp_avg"]):
-            m.copy_(s)
-        for v, s in zip(self.v, sd["exp_avg_sq"]):
-            v.copy_(s)
 
 
 def linear_backward(P, wname, bname, x, dy, need_dx=True):

@@ -562,8 +562,11 @@ class QMIXAgent:
             self.agent_networks_target[i].load_state_dict(sd)
         self.mixer.load_state_dict(ck['mixer'])
         self.mixer_target.load_state_dict(ck['mixer'])
-        if isinstance(ck.get('optimizer'), dict) and 'exp_avg' in ck['optimizer']:
-            self.optimizer.load_state_dict(ck['optimizer'])
+        if isinstance(ck.get('optimizer'), dict):
+            self.optimizer.load_state_dict(ck['optimizer'])       # torch.optim.Adam layout (qmix_agent.py:331)
+        else:
+            import warnings
+            warnings.warn("QMIX checkpoint holds no optimizer state: Adam restarts from zero moments")
         self.total_updates = ck['total_updates']
         print(f"QMIX agent loaded from {filepath}")
 

@@ -429,12 +429,15 @@ class SAC_GRU_Agent:
         self.q2_target.load_state_dict(ck['q2_target_state_dict'])
         for name, opt in (('policy_optimizer_state_dict', self.policy_optimizer),
                           ('q1_optimizer_state_dict', self.q1_optimizer), ('q2_optimizer_state_dict', self.q2_optimizer)):
-            if isinstance(ck.get(name), dict) and 'exp_avg' in ck[name]:
-                opt.load_state_dict(ck[name])
+            if isinstance(ck.get(name), dict):
+                opt.load_state_dict(ck[name])                     # torch.optim.Adam layout (sac_agent.py:300-302)
+            else:
+                import warnings
+                warnings.warn(f"SAC checkpoint holds no {name}: Adam restarts from zero moments")
         if self.auto_entropy_tuning and 'log_alpha' in ck:
             self.log_alpha.copy_(ck['log_alpha'].detach().to(self.device))
             self.alpha = ops.exp_scalar(self.log_alpha)
-            if isinstance(ck.get('alpha_optimizer_state_dict'), dict) and 'exp_avg' in ck['alpha_optimizer_state_dict']:
+            if isinstance(ck.get('alpha_optimizer_state_dict'), dict):
                 self.alpha_optimizer.load_state_dict(ck['alpha_optimizer_state_dict'])
         self.total_steps = ck['total_steps']
         print(f"Agent loaded from {filepath}")

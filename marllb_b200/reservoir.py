@@ -5,7 +5,10 @@ API mirror of simulation-mode/problem-01-reservoir-sampling/src/reservoir.py
 state assembly of src/features.py:232-303, computed by the batched kernels of
 csrc/mlb_ops.cu (`mlb_reservoir_add`, `mlb_reservoir_features`).
 `BatchedReservoirs` is the native batched form; `ReservoirSampler` is a batch
-of one.  Timestamps are float32 seconds (src/vpp/lb/shm.h:23-25).
+of one.  Timestamps are stored on the device as float32 seconds (src/vpp/lb/shm.h:23-25)
+RELATIVE to a float64 host-side epoch (the first timestamp seen): the reference keeps float64
+`time.time()` values (reservoir.py:42,62,140), whose differences -- all the decay weights depend
+on -- would be lost in float32 at epoch scale (128 s resolution near 1.8e9).
 """
 from __future__ import annotations
 
@@ -48,16 +51,31 @@ class BatchedReservoirs:
         self.count = torch.zeros(num, dtype=torch.int32, device=self.device)
         self.cursor = torch.zeros(num, dtype=torch.int32, device=self.device)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = None          # float64 host-side time base; device timestamps are (t - epoch) in float32
 
-    @staticmethod
-    def _stream():
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _rel_time(self, t, set_epoch=False):
+        """float64 timestamps (array-like or tensor) -> float32 device tensor of seconds since `epoch`."""
+        if isinstance(t, torch.Tensor):
+            t64 = t.detach().to(dtype=torch.float64)
+        else:
+            t64 = torch.as_tensor(np.asarray(t, np.float64))
+        if self.epoch is None:
+            if not set_epoch or t64.numel() == 0:
+                return t64.to(torch.float32).to(self.device)
+            # simulated time (seconds since reset, float32-exact in the env kernels) is kept as is; wall-clock
+            # time (time.time() ~ 1.8e9, float32 resolution 128 s) is rebased on the first timestamp seen
+            t0 = float(t64.reshape(-1)[0].item())
+            self.epoch = t0 if abs(t0) >= 2.0 ** 20 else 0.0
+        return (t64 - self.epoch).to(torch.float32).to(self.device)
 
     def add(self, values, timestamps, n_add=None) -> torch.Tensor:
         """values/timestamps: (R, M) samples per reservoir, fed in order; n_add: (R,) counts
         (default M each).  Returns the (R, M) uint8 accepted flags."""
         v = torch.as_tensor(values, dtype=torch.float32).to(self.device).reshape(self.num, -1).contiguous()
-        t = torch.as_tensor(timestamps, dtype=torch.float32).to(self.device).reshape(self.num, -1).contiguous()
+        t = self._rel_time(timestamps, set_epoch=True).reshape(self.num, -1).contiguous()
         M = v.shape[1]
         n = (torch.full((self.num,), M, dtype=torch.int32, device=self.device) if n_add is None
              else torch.as_tensor(n_add, dtype=torch.int32).to(self.device).contiguous())
@@ -70,7 +88,7 @@ class BatchedReservoirs:
 
     def features(self, decay: float = 0.9, now=0.0) -> torch.Tensor:
         """(R, 5) float32: mean, p90, std, mean_decay, p90_decay (reservoir.py:105-163)."""
-        nw = torch.as_tensor(now, dtype=torch.float32).to(self.device).expand(self.num).contiguous()
+        nw = self._rel_time(now).expand(self.num).contiguous()
         out = torch.empty((self.num, 5), dtype=torch.float32, device=self.device)
         check(self._L.mlb_reservoir_features(_p(self.values), _p(self.timestamps), _p(self.count), self.num,
                                              self.capacity, float(decay), _p(nw), _p(out), self._stream()))
@@ -86,6 +104,7 @@ class BatchedReservoirs:
         self.values.zero_()
         self.timestamps.zero_()
         self.count.zero_()
+        self.epoch = None
 
 
 class ReservoirSampler:
@@ -107,7 +126,10 @@ class ReservoirSampler:
 
     @property
     def timestamps(self) -> np.ndarray:
-        return self._b.timestamps[0, :self.capacity].cpu().numpy().astype(np.float64)
+        ts = self._b.timestamps[0, :self.capacity].cpu().numpy().astype(np.float64)
+        if self._b.epoch is not None:                       # zero-filled (unused) slots stay 0 like the reference's
+            ts[:self.get_size()] += self._b.epoch
+        return ts
 
     def add(self, value: float, timestamp: Optional[float] = None) -> bool:
         if timestamp is None:
@@ -117,7 +139,7 @@ class ReservoirSampler:
         return bool(acc.item())
 
     def add_many(self, values, timestamps) -> np.ndarray:
-        acc = self._b.add(np.asarray(values, np.float32)[None], np.asarray(timestamps, np.float32)[None])
+        acc = self._b.add(np.asarray(values, np.float32)[None], np.asarray(timestamps, np.float64)[None])
         self._b.check_status()
         return acc[0].cpu().numpy().astype(bool)
 

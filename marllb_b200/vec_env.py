@@ -50,6 +50,10 @@ class VecLoadBalanceEnv:
     `discrete_weights`, `max_weight`, `min_weight`, `reward_metric`,
     `reward_field`, `step_interval`, `max_steps`) plus `num_envs`, `num_agents`
     (multi_agent_env.py:44-53) and the flow-level knobs of SURVEY App. B.
+    `rng_mode`: "replay" (default) -- reservoirs of server j replay np.random.RandomState(seed_base + j), the
+    reference's stream (reservoir.py:45,76), the same in every env; "philox" -- a counter-based stream per
+    (global env, server) with the same masked-rejection rule (include/marllb_b200.h), for large batches whose
+    envs should not share sampling decisions.
     """
 
     def __init__(self, num_envs: int, num_servers: int = 4, num_agents: int = 1,
@@ -60,7 +64,7 @@ class VecLoadBalanceEnv:
                  queue_capacity: int = 160, decay: float = 0.9, seed_base: int = 0,
                  rng_table_len: int = 65536, feature_cache: bool = True,
                  record_assign: bool = False, action_dtype: str = "int32", env_id_base: int = 0,
-                 device: int = 0, normalize_obs: bool = False):
+                 device: int = 0, normalize_obs: bool = False, rng_mode: str = "replay"):
         if action_type not in ("discrete", "continuous"):
             raise ValueError(f"Unknown action_type: {action_type}")          # env.py:184
         if reward_metric not in _lib.METRICS:
@@ -68,6 +72,9 @@ class VecLoadBalanceEnv:
                              f"Supported: {list(_lib.METRICS.keys())}")      # rewards.py:321-323
         if policy not in _lib.POLICIES:
             raise ValueError(f"Unknown policy: {policy}")
+        if rng_mode not in _lib.RNG_MODES:
+            raise ValueError(f"Unknown rng_mode: {rng_mode} (replay: the reference's RandomState(seed_base + server) "
+                             f"stream shared by all envs; philox: counter-based, independent per env)")
         if isinstance(reward_field, str):
             if reward_field not in _lib.FEATURE_NAMES:
                 raise ValueError(f"Unknown reward_field: {reward_field}")
@@ -98,6 +105,8 @@ class VecLoadBalanceEnv:
         cfg.rng_seed_base, cfg.rng_table_len = seed_base, rng_table_len
         cfg.feature_cache, cfg.record_assign = int(feature_cache), int(record_assign)
         cfg.env_id_base = env_id_base
+        cfg.rng_mode = _lib.RNG_MODES[rng_mode]
+        self.rng_mode = rng_mode
         self.cfg = cfg
         self.num_envs, self.num_agents, self.servers_per_agent = num_envs, num_agents, num_servers
         self.total_servers = num_agents * num_servers
@@ -131,9 +140,8 @@ class VecLoadBalanceEnv:
         check(self._L.mlb_device_ptr(self._h, what, C.byref(p), C.byref(n)), self._h)
         return torch.as_tensor(_DevView(p.value, shape, dtype, self), device=self.device)
 
-    @staticmethod
-    def _stream():
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def close(self):
         t = getattr(self, "_prefetch", None)
@@ -202,7 +210,8 @@ class VecLoadBalanceEnv:
     def _restart_stream(self):
         tr = self._trace
         if getattr(self, "_prefetch", None) is not None:
-            self._prefetch.join()
+            self._prefetch.join()                 # an error of the abandoned chunk is irrelevant after a restart
+            self._prefetch = None
         tr.restart()
         self._steps_done = 0
         self._chunk_end, first = tr.next_chunk()
@@ -210,27 +219,46 @@ class VecLoadBalanceEnv:
         self._kick_prefetch()
 
     def _kick_prefetch(self):
+        self._staged = None
+        self._prefetch_error = None
+
         def work():
-            k_end, ch = self._trace.next_chunk()
-            pin = {}
-            for key in ("time", "work", "bucket", "u"):
-                if key in ch:
-                    t = torch.from_numpy(np.ascontiguousarray(ch[key]))
-                    pin[key] = t.pin_memory() if t.numel() else t
-            off = np.ascontiguousarray(ch["offsets"], np.int64)
-            with torch.cuda.device(self.device):
-                check(self._L.mlb_stage_arrivals(self._h, _dptr(pin["time"]), _dptr(pin["work"]), _dptr(pin.get("bucket")),
-                                                 _dptr(pin.get("u")), _nptr(off),
-                                                 C.c_void_p(self._copy_stream.cuda_stream)), self._h)
-            self._staged = (k_end, pin, off)          # keeps the pinned buffers alive until the next swap
+            try:
+                k_end, ch = self._trace.next_chunk()
+                pin = {}
+                for key in ("time", "work", "bucket", "u"):
+                    if key in ch:
+                        t = torch.from_numpy(np.ascontiguousarray(ch[key]))
+                        pin[key] = t.pin_memory() if t.numel() else t
+                off = np.ascontiguousarray(ch["offsets"], np.int64)
+                with torch.cuda.device(self.device):
+                    check(self._L.mlb_stage_arrivals(self._h, _dptr(pin["time"]), _dptr(pin["work"]), _dptr(pin.get("bucket")),
+                                                     _dptr(pin.get("u")), _nptr(off),
+                                                     C.c_void_p(self._copy_stream.cuda_stream)), self._h)
+                self._staged = (k_end, pin, off)          # keeps the pinned buffers alive until the next swap
+            except BaseException as exc:                  # surfaced by _join_prefetch on the stepping thread
+                self._prefetch_error = exc
         self._prefetch = self._threading.Thread(target=work, daemon=True)
         self._prefetch.start()
+
+    def _join_prefetch(self):
+        """Wait for the staging thread; a failure there (parse error, MlbError of mlb_stage_arrivals) is
+        re-raised here instead of leaving a stale chunk behind."""
+        t = getattr(self, "_prefetch", None)
+        if t is not None:
+            t.join()
+            self._prefetch = None
+        err, self._prefetch_error = getattr(self, "_prefetch_error", None), None
+        if err is not None:
+            raise RuntimeError(f"streamed-trace prefetch failed: {err}") from err
 
     def _advance_stream(self):
         """Called before a step: swap in the next chunk when the current one is used up."""
         if self._steps_done < self._chunk_end:
             return
-        self._prefetch.join()
+        self._join_prefetch()
+        if self._staged is None:
+            raise RuntimeError("streamed-trace prefetch produced no chunk")
         self._live = self._staged
         check(self._L.mlb_commit_arrivals(self._h, self._stream()), self._h)
         self._chunk_end = self._staged[0]
@@ -398,22 +426,41 @@ class VecLoadBalanceEnv:
         return ev.value, ft.value, n.value
 
     # ------------------------------------------------------------ state dumps
-    def get_state(self, field: str) -> np.ndarray:
+    def _state_spec(self, field):
         E, S, K = self.num_envs, self.total_servers, self.reservoir_capacity
         KP = (K + 31) // 32 * 32
-        spec = {"n_flow_on": (_lib.F_N_FLOW_ON, np.int32, (E, S)),
-                "res_values": (_lib.F_RES_VALUES, np.float32, (E, S, 2, KP)),
-                "res_ts": (_lib.F_RES_TS, np.float32, (E, S, 2, KP)),
-                "res_count": (_lib.F_RES_COUNT, np.uint32, (E, 2, S)),
-                "res_cursor": (_lib.F_RES_CURSOR, np.uint32, (E, 2, S)),
-                "dropped": (_lib.F_DROPPED, np.uint32, (E, S)),
-                "last_fin": (_lib.F_LAST_FIN, np.float32, (E, S)),
-                "head": (_lib.F_HEAD, np.uint32, (E, S)),
-                "step": (_lib.F_STEP, np.int32, (E,)),
-                "obs": (_lib.F_OBS, np.float32, (E, S, 11)),
-                "arr_cursor": (_lib.F_ARR_CURSOR, np.int32, (E, self.num_agents))}[field]
-        out = np.empty(spec[2], spec[1])
-        check(self._L.mlb_get_state(self._h, spec[0], _nptr(out), out.nbytes, _lib.HOST), self._h)
+        return {"n_flow_on": (_lib.F_N_FLOW_ON, torch.int32, (E, S)),
+                "res_values": (_lib.F_RES_VALUES, torch.float32, (E, S, 2, KP)),
+                "res_ts": (_lib.F_RES_TS, torch.float32, (E, S, 2, KP)),
+                "res_count": (_lib.F_RES_COUNT, torch.int32, (E, 2, S)),       # uint32 on the device
+                "res_cursor": (_lib.F_RES_CURSOR, torch.int32, (E, 2, S)),
+                "dropped": (_lib.F_DROPPED, torch.int32, (E, S)),
+                "last_fin": (_lib.F_LAST_FIN, torch.float32, (E, S)),
+                "head": (_lib.F_HEAD, torch.int32, (E, S)),
+                "step": (_lib.F_STEP, torch.int32, (E,)),
+                "obs": (_lib.F_OBS, torch.float32, (E, S, 11)),
+                "arr_cursor": (_lib.F_ARR_CURSOR, torch.int32, (E, self.num_agents))}[field]
+
+    def state_view(self, field: str) -> "torch.Tensor":
+        """Zero-copy device view of a state field (leading dimension = env); unsigned counters appear as int32."""
+        what, dt, shape = self._state_spec(field)
+        return self._view(what, shape, dt)
+
+    def get_state(self, field: str, envs=None) -> np.ndarray:
+        """Host copy of a state field; `envs` (index list) restricts it to those envs -- at bench sizes the
+        reservoir arrays are tens of GB, a parity check pulls a handful of envs."""
+        K = self.reservoir_capacity
+        unsigned = field in ("res_count", "res_cursor", "dropped", "head")
+        if envs is not None:
+            idx = torch.as_tensor(np.asarray(envs, np.int64), device=self.device)
+            torch.cuda.current_stream(self.device).synchronize()
+            out = self.state_view(field).index_select(0, idx).cpu().numpy()
+            out = out.view(np.uint32) if unsigned else out
+        else:
+            what, dt, shape = self._state_spec(field)
+            npdt = {torch.int32: np.uint32 if unsigned else np.int32, torch.float32: np.float32}[dt]
+            out = np.empty(shape, npdt)
+            check(self._L.mlb_get_state(self._h, what, _nptr(out), out.nbytes, _lib.HOST), self._h)
         if field in ("res_values", "res_ts"):
             out = out[..., :K]
         return out

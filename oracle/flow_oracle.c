@@ -108,6 +108,29 @@ DEFINE_PAIRWISE(pw_f32, float)
 DEFINE_PAIRWISE(pw_f64, double)
 
 /* =========================================================================
+ * Philox4x32-10: counter-based stream of rng_mode 1 (twin of csrc/mlb_step_kernel.cuh)
+ * ========================================================================= */
+void ora_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+uint32_t ora_philox_word(uint32_t c, uint32_t j, uint32_t g, uint32_t key0) {
+    const uint32_t ctr[4] = {c >> 2, j, g, 0x52535652u}, key[2] = {key0, 0x4d4c4232u};
+    uint32_t out[4];
+    ora_philox4x32_10(ctr, key, out);
+    return out[c & 3u];
+}
+
+/* =========================================================================
  * ReservoirSampler (reservoir.py:17-233)
  * ========================================================================= */
 static int g_last_slot_dummy;
@@ -120,6 +143,12 @@ ora_reservoir_t *ora_reservoir_create(int capacity, uint32_t seed) {
     ora_mt_seed(&r->rng, seed);                                            /* :45 */
     (void)g_last_slot_dummy;
     return r;
+}
+
+void ora_reservoir_set_philox(ora_reservoir_t *r, uint32_t key0, uint32_t server, uint32_t env) {
+    r->rng_mode = 1;
+    r->ph_key0 = key0; r->ph_server = server; r->ph_env = env;
+    r->ph_cursor = 0;
 }
 
 void ora_reservoir_destroy(ora_reservoir_t *r) {
@@ -144,7 +173,15 @@ static int reservoir_add_slot(ora_reservoir_t *r, float value, double ts) {
         r->count++;
         return slot;
     }
-    uint32_t j = ora_mt_randint(&r->rng, (uint32_t)r->count);              /* :76 randint(0, count+1) */
+    uint32_t j;
+    if (r->rng_mode == 1) { /* same masked rejection as RandomState.randint, over the counter-based words */
+        const uint32_t rng = (uint32_t)r->count;
+        uint32_t mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        do { j = ora_philox_word(r->ph_cursor++, r->ph_server, r->ph_env, r->ph_key0) & mask; } while (j > rng);
+    } else {
+        j = ora_mt_randint(&r->rng, (uint32_t)r->count);                   /* :76 randint(0, count+1) */
+    }
     r->count++;                                                            /* :81/:84 */
     if (j < (uint32_t)r->capacity) {                                       /* :78-80 */
         r->values[j] = value;
@@ -479,7 +516,12 @@ ora_env *ora_env_create(const ora_env_cfg *cfg, const float *speeds) {
     e->res = (ora_reservoir_t **)calloc((size_t)S * 2, sizeof(void *));
     for (int j = 0; j < S; j++)
         for (int m = 0; m < 2; m++) /* same seed for both metrics: reservoir.py:261-265; seed=j: basic_usage.py:157-163 */
-            e->res[j * 2 + m] = ora_reservoir_create(cfg->reservoir_k, cfg->seed_base + (uint32_t)j);
+        {
+            ora_reservoir_t *r = ora_reservoir_create(cfg->reservoir_k, cfg->seed_base + (uint32_t)j);
+            r->rng_mode = cfg->rng_mode;
+            r->ph_key0 = cfg->seed_base; r->ph_server = (uint32_t)j; r->ph_env = cfg->env_id;
+            e->res[j * 2 + m] = r;
+        }
     e->a_time = (const float **)calloc((size_t)A, sizeof(void *));
     e->a_work = (const float **)calloc((size_t)A, sizeof(void *));
     e->a_u = (const float **)calloc((size_t)A, sizeof(void *));
@@ -523,6 +565,7 @@ void ora_env_reset(ora_env *e) {
         for (int m = 0; m < 2; m++) { /* a fresh MultiMetricReservoir(seed=j) per episode */
             ora_reservoir_reset(e->res[j * 2 + m]);
             ora_mt_seed(&e->res[j * 2 + m]->rng, e->cfg.seed_base + (uint32_t)j);
+            e->res[j * 2 + m]->ph_cursor = 0;
         }
     for (int i = 0; i < e->cfg.num_agents; i++) e->a_cursor[i] = 0;
 }

@@ -37,7 +37,8 @@ class _Cfg(C.Structure):
                 ("min_weight", C.c_float), ("max_weight", C.c_float),
                 ("dt", C.c_float), ("decay", C.c_double),
                 ("reward_metric", C.c_int32), ("reward_field", C.c_int32),
-                ("max_steps", C.c_int32), ("seed_base", C.c_uint32)]
+                ("max_steps", C.c_int32), ("seed_base", C.c_uint32),
+                ("rng_mode", C.c_int32), ("env_id", C.c_uint32)]
 
 
 _lib = None
@@ -50,6 +51,10 @@ def lib():
     L = C.CDLL(build())
     vp, i32, i64, u32, f64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_double, C.c_float
     L.ora_mt_fill.argtypes = [u32, vp, i64]
+    L.ora_philox4x32_10.argtypes = [vp, vp, vp]
+    L.ora_reservoir_set_philox.argtypes = [vp, u32, u32, u32]
+    L.ora_philox_word.restype = u32
+    L.ora_philox_word.argtypes = [u32, u32, u32, u32]
     L.ora_reservoir_create.restype = vp
     L.ora_reservoir_create.argtypes = [C.c_int, u32]
     L.ora_reservoir_destroy.argtypes = [vp]
@@ -93,6 +98,16 @@ def mt_fill(seed: int, n: int) -> np.ndarray:
     return out
 
 
+def philox4x32_10(ctr, key) -> np.ndarray:
+    c, k, out = np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), np.empty(4, np.uint32)
+    lib().ora_philox4x32_10(_p(c), _p(k), _p(out))
+    return out
+
+
+def philox_word(c: int, server: int, env: int, key0: int) -> int:
+    return int(lib().ora_philox_word(c, server, env, key0))
+
+
 class Reservoir:
     """C restatement of reference ReservoirSampler (reservoir.py:17-233)."""
 
@@ -107,6 +122,9 @@ class Reservoir:
 
     def add(self, value, timestamp):
         return bool(lib().ora_reservoir_add(self._h, float(np.float32(value)), float(timestamp)))
+
+    def set_philox(self, key0, server, env):
+        lib().ora_reservoir_set_philox(self._h, key0, server, env)
 
     def last_slot(self):
         return lib().ora_reservoir_last_slot(self._h)
@@ -174,7 +192,8 @@ class FlowEnv:
                  reservoir_k=128, queue_cap=160, dt=0.25, decay=0.9, policy="sed",
                  action_type="discrete", discrete_weights=None, min_weight=0.1,
                  max_weight=10.0, reward_metric="jain",
-                 reward_field="flow_duration_avg_decay", max_steps=10000, seed_base=0):
+                 reward_field="flow_duration_avg_decay", max_steps=10000, seed_base=0,
+                 rng_mode="replay", env_id=0):
         cfg = _Cfg()
         cfg.num_agents, cfg.servers_per_agent = num_agents, servers_per_agent
         cfg.reservoir_k, cfg.queue_cap = reservoir_k, queue_cap
@@ -189,6 +208,7 @@ class FlowEnv:
         cfg.reward_metric = METRICS.index(reward_metric)
         cfg.reward_field = FIELDS.index(reward_field) if isinstance(reward_field, str) else int(reward_field)
         cfg.max_steps, cfg.seed_base = max_steps, seed_base
+        cfg.rng_mode, cfg.env_id = {"replay": 0, "philox": 1}[rng_mode], env_id
         self.cfg = cfg
         self.A, self.Sa = num_agents, servers_per_agent
         self.S, self.K = num_agents * servers_per_agent, reservoir_k

@@ -60,6 +60,21 @@ def gold_reservoir():
         out[key + "_now"] = np.float64(now)
         out[key + "_fv"] = r.get_feature_vector(0.9, current_time=now)
     save("reservoir_streams", **out)
+    # wall-clock timestamps (the reference's default: time.time(), float64, reservoir.py:62,140)
+    out = {}
+    rng = np.random.RandomState(21)
+    for cap, seed, n, t0 in ((128, 9, 900, 1.8e9), (32, 2, 300, 1.7605e9 + 0.123)):
+        r = res.ReservoirSampler(capacity=cap, seed=seed)
+        v = rng.exponential(0.3, n).astype(np.float32)
+        t = t0 + np.cumsum(rng.exponential(0.05, n))            # float64 epoch seconds, ~45 s of samples
+        acc = np.array([r.add(float(v[i]), timestamp=float(t[i])) for i in range(n)], np.uint8)
+        now = float(t[-1] + 0.25)
+        key = f"c{cap}_s{seed}"
+        out[key + "_in_v"], out[key + "_in_t"], out[key + "_acc"] = v, t, acc
+        out[key + "_values"], out[key + "_ts"] = r.values.copy(), r.timestamps.copy()
+        out[key + "_now"] = np.float64(now)
+        out[key + "_fv"] = r.get_feature_vector(0.9, current_time=now)
+    save("reservoir_wallclock", **out)
 
 
 def gold_features():

@@ -172,8 +172,84 @@ def extras():
     save("policy_extras", **out)
 
 
+def checkpoints():
+    """Checkpoint FILES written by the unmodified reference agents after two updates (torch.optim.Adam state
+    included: sac_agent.py:257-287, qmix_agent.py:309-322) + every parameter after a THIRD update run by the
+    reference after its own load() of that file.  The product must resume from these files to the same numbers."""
+    sa = ref_import.load("sac_agent", "problem-04-sac-gru")
+    qa = ref_import.load("qmix_agent", "problem-05-qmix")
+    out = {}
+    # ---- SAC
+    torch.manual_seed(3)
+    S, A, B = 22, 4, 8
+    kw = dict(state_dim=S, action_dim=A, hidden_dim=64, gru_dim=32, batch_size=B, device="cpu")
+    agent = sa.SAC_GRU_Agent(**kw)
+    rng = np.random.RandomState(19)
+    fixed = (torch.as_tensor(rng.randn(B, S), dtype=torch.float32),
+             torch.as_tensor(np.tanh(rng.randn(B, A)), dtype=torch.float32),
+             torch.as_tensor(rng.rand(B, 1), dtype=torch.float32),
+             torch.as_tensor(rng.randn(B, S), dtype=torch.float32),
+             torch.as_tensor((rng.rand(B, 1) < 0.2).astype(np.float32)),
+             torch.as_tensor(rng.randn(1, B, 32) * 0.2, dtype=torch.float32))
+    for n, t in zip(("states", "actions", "rewards", "next_states", "dones", "hiddens"), fixed):
+        out["sac_batch_" + n] = t.numpy()
+    agent.replay_buffer.is_ready = lambda n: True
+    agent.replay_buffer.sample = lambda n, d: fixed
+    for u in (1, 2):
+        torch.manual_seed(200 + u)
+        agent.update_parameters(1)
+    agent.save(os.path.join(HERE, "ref_sac_ckpt.pt"))
+    resumed = sa.SAC_GRU_Agent(**kw)
+    resumed.load(os.path.join(HERE, "ref_sac_ckpt.pt"))
+    resumed.replay_buffer.is_ready = lambda n: True
+    resumed.replay_buffer.sample = lambda n, d: fixed
+    torch.manual_seed(203)
+    e_next, e_new = torch.randn(B, A), torch.randn(B, A)
+    torch.manual_seed(203)
+    losses = resumed.update_parameters(1)
+    out["sac_upd3_eps_next"], out["sac_upd3_eps_new"] = e_next.numpy(), e_new.numpy()
+    out["sac_upd3_losses"] = np.array([losses['q1'], losses['q2'], losses['policy'], losses['alpha']])
+    out["sac_upd3_alpha"] = np.array([resumed.alpha.item()])
+    for pre, net in (("policy.", resumed.policy), ("q1.", resumed.q1), ("q2.", resumed.q2), ("q1t.", resumed.q1_target)):
+        out.update(sd_np("sac_upd3." + pre, net.state_dict()))
+    # ---- QMIX
+    torch.manual_seed(4)
+    qkw = dict(num_agents=3, state_dim=9, obs_dim=12, action_dim=5, hidden_dim=32, gru_dim=16, mixing_embed_dim=8,
+               hypernet_embed_dim=16, batch_size=4, max_seq_len=6, device="cpu", target_update_interval=2)
+    qagent = qa.QMIXAgent(**qkw)
+    rng = np.random.RandomState(6)
+    Bq, T, Aq, K = 4, 6, 3, 5
+    batch = {'observations': rng.randn(Bq, T, Aq, 12), 'actions': rng.randint(0, K, (Bq, T, Aq, 1)).astype(np.float64),
+             'rewards': rng.rand(Bq, T, Aq), 'states': rng.randn(Bq, T, 9),
+             'dones': np.zeros((Bq, T)), 'seq_lengths': np.array([5, 6, 3, 6], np.int32)}
+    for b, L in enumerate(batch['seq_lengths']):
+        batch['observations'][b, L:] = 0; batch['actions'][b, L:] = 0; batch['rewards'][b, L:] = 0
+        batch['states'][b, L:] = 0
+        batch['dones'][b, L - 1] = 1.0
+    for k, v in batch.items():
+        out["qmix_batch_" + k] = v
+    qagent.episode_buffer.is_ready = lambda n: True
+    qagent.episode_buffer.sample_batch = lambda n, m: batch
+    qagent.update(); qagent.update()
+    qagent.save(os.path.join(HERE, "ref_qmix_ckpt.pt"))
+    qres = qa.QMIXAgent(**qkw)
+    qres.load(os.path.join(HERE, "ref_qmix_ckpt.pt"))
+    qres.episode_buffer.is_ready = lambda n: True
+    qres.episode_buffer.sample_batch = lambda n, m: batch
+    stats = qres.update()
+    out["qmix_upd3_stats"] = np.array([stats['loss'], stats['q_tot'], stats['target_q_tot']])
+    for i, n in enumerate(qres.agent_networks):
+        out.update(sd_np(f"qmix_upd3.ag{i}.", n.state_dict()))
+    out.update(sd_np("qmix_upd3.agmix.", qres.mixer.state_dict()))
+    save("policy_ckpt", **out)
+
+
 if __name__ == "__main__":
+    if "ckpt" in sys.argv:
+        checkpoints()
+        sys.exit(0)
     if "extras" not in sys.argv:
         qmix()
         sac()
     extras()
+    checkpoints()

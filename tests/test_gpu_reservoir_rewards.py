@@ -57,6 +57,26 @@ def test_reservoir_streams():
         np.testing.assert_allclose(f, g[key + "_fv"], rtol=OBS_RTOL)
 
 
+def test_reservoir_wallclock_timestamps():
+    """The reference's default timestamps are float64 time.time() values (reservoir.py:42,62,140): ~1.8e9, where
+    float32 resolves 128 s.  The facade rebases them on a float64 host-side epoch, so decay weights still see the
+    true differences between samples (fixture: unmodified reference fed epoch-scale timestamps)."""
+    from marllb_b200.reservoir import ReservoirSampler
+    g = load_golden("reservoir_wallclock")
+    keys = sorted({k.rsplit("_in_v", 1)[0] for k in g if k.endswith("_in_v")})
+    assert keys
+    for key in keys:
+        cap, seed = int(key.split("_")[0][1:]), int(key.split("_")[1][1:])
+        s = ReservoirSampler(capacity=cap, seed=seed)
+        acc = s.add_many(g[key + "_in_v"], g[key + "_in_t"])
+        assert np.array_equal(acc.astype(np.uint8), g[key + "_acc"])
+        assert np.array_equal(s.values, g[key + "_values"])
+        # rebased float32 seconds: < 1e-5 s over the ~45 s the samples span (128 s without the epoch)
+        np.testing.assert_allclose(s.timestamps, g[key + "_ts"], rtol=0, atol=1e-5)
+        f = s.get_feature_vector(0.9, float(g[key + "_now"]))
+        np.testing.assert_allclose(f, g[key + "_fv"], rtol=OBS_RTOL)
+
+
 def test_features_cases_batched():
     import torch
     from marllb_b200.reservoir import BatchedReservoirs
