@@ -227,7 +227,7 @@ def run_reference(args):
     }))
 
 
-def workload_config(args, wl):
+def workload_config(args, wl, world=None):
     pol = {"qmix": "QMIX epsilon-greedy action selection (eps=0.05) fused with the env step",
            "sac": "SAC-GRU actor sampling + env step + one SAC update (batch 256) per step",
            None: "random policy"}[wl.get("policy")]
@@ -237,7 +237,9 @@ def workload_config(args, wl):
             "reservoir_k": wl["K"], "flows_per_s_per_agent": wl["rate"], "dt_s": DT,
             "burnin_steps": args.burnin,
             "l2_policy": "per-step working set (>17 GB of reservoirs per GPU) far exceeds the 126 MB L2",
-            "parallelism": f"env-sharded x{args.gpus} (no data-path collective)"}
+            "parallelism": (f"env-sharded x{world or args.gpus}: no data-path collective in the env step"
+                            + ("; SAC gradient buckets all-reduced over NCCL (captured in the step's CUDA graph)"
+                               if wl.get("policy") == "sac" else ""))}
 
 
 def build_env(wl, total_steps, rank=0, local=0, feature_cache=True, rng_mode="replay"):
@@ -261,49 +263,60 @@ def build_env(wl, total_steps, rank=0, local=0, feature_cache=True, rng_mode="re
     return env, speeds, pool, g
 
 
-def run_ours(args):
+def _setup_policy(wl, env, rank, local, gen):
+    """QMIX (c3) / SAC (c4) rollouts on top of the env; returns (rollout, sac, draw pools)."""
     import torch
-    import torch.distributed as dist
-    from marllb_b200 import VecLoadBalanceEnv
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    # host side of the end-to-end step: pinned buffers on the NUMA node next to this rank's GPU
-    from marllb_b200.shard import bind_host_to_gpu
-    prev_affinity = bind_host_to_gpu(local) if (world > 1 and not os.environ.get("MLB_NO_NUMA_BIND")) else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wl = dict(WORKLOADS[args.workload])
-    if args.envs:
-        wl["envs"] = args.envs
-    E, A, S, K = wl["envs"], wl["agents"], wl["servers"], wl["K"]
-    e2e_steps = min(args.steps, args.e2e_steps)
-    total_steps = args.burnin + args.warmup + args.steps + 20 + e2e_steps
-    env, speeds, pool, g = build_env(wl, total_steps, rank, local, not args.no_feature_cache, args.rng_mode)
-    rollout = None
+    E, A, S = wl["envs"], wl["agents"], wl["servers"]
+    rollout = sac = sac_agent = None
+    upool = rpool = None
     if wl.get("policy") == "qmix":
-        from marllb_b200.policy import QMIXAgent, ops as pops
+        from marllb_b200.policy import QMIXAgent
         from marllb_b200.rollout import QMIXRollout
         torch.manual_seed(7)   # random-init weights of the reference architecture
         agent = QMIXAgent(num_agents=A, state_dim=4 * A * S + 10, obs_dim=S * 11, action_dim=S, hidden_dim=64, gru_dim=64,
                           mixing_embed_dim=32, hypernet_embed_dim=64, device=torch.device("cuda", local))
         rollout = QMIXRollout(env, agent)
-        upool = [torch.rand((E, A), generator=g, device="cuda") for _ in range(8)]
-        rpool = [torch.randint(0, S, (E, A), generator=g, device="cuda", dtype=torch.int32) for _ in range(8)]
-
-    sac = None
+        upool = [torch.rand((E, A), generator=gen, device="cuda") for _ in range(8)]
+        rpool = [torch.randint(0, S, (E, A), generator=gen, device="cuda", dtype=torch.int32) for _ in range(8)]
     if wl.get("policy") == "sac":
-        from marllb_b200.policy import SAC_GRU_Agent, ops as pops
+        from marllb_b200.policy import SAC_GRU_Agent
         from marllb_b200.rollout import SACRollout
         torch.manual_seed(7)   # same initial weights on every rank
         sac_agent = SAC_GRU_Agent(state_dim=S * 11, action_dim=S, hidden_dim=256, gru_dim=128, batch_size=256,
                                   device=torch.device("cuda", local))
         sac = SACRollout(env, sac_agent)
+    return rollout, sac, sac_agent, upool, rpool
+
+
+def measure(args, name, world, rank, local, main):
+    """One workload at N = world GPUs: burn-in, K timed steps (CUDA events, barrier + synchronize on both sides, max over
+    ranks), per-kernel CUDA events; for the main workload also the end-to-end leg through host buffers and a second
+    timed window late in the episode.  Returns the result dict on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    from marllb_b200.policy import ops as pops
+
+    wl = dict(WORKLOADS[name])
+    if args.envs and main:
+        wl["envs"] = args.envs
+    E, A, S, K = wl["envs"], wl["agents"], wl["servers"], wl["K"]
+    steps, warmup = (args.steps, args.warmup) if main else (args.config_steps, max(3, args.warmup))
+    burnin = args.burnin if main else min(args.burnin, args.config_burnin)
+    e2e_steps = min(steps, args.e2e_steps) if main else 0
+    late = main and args.late_burnin > burnin and wl.get("policy") is None
+    total_steps = burnin + warmup + steps + 20 + e2e_steps + 24
+    env, speeds, pool, g = build_env(wl, total_steps, rank, local, not args.no_feature_cache, args.rng_mode)
+    mean_work = RHO * float(speeds[:S].sum()) / wl["rate"]
+    rollout, sac, sac_agent, upool, rpool = _setup_policy(wl, env, rank, local, g)
+    has_policy = rollout is not None or sac is not None
+    sac_gen = None
+    if sac is not None:
         sac_gen = torch.Generator(device="cuda")
         sac_gen.manual_seed(5 + rank)
     graphed = False
+
+    def cur_step():
+        return int(env.get_state("step", envs=[0])[0])      # steps the envs have taken (device counter, env.py:230)
 
     def do_step(k):
         if sac is not None:
@@ -326,7 +339,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.burnin):
+    def launches_now():
+        return env.launch_count + (pops.LAUNCHES if has_policy else 0)
+
+    for k in range(burnin):
         do_step(k)
     prof_eager = None
     if rollout is not None and not args.no_graph:
@@ -338,173 +354,347 @@ def run_ours(args):
         prof_eager = env.profile_end()
         rollout.capture(0.05)
         graphed = True
-    if sac is not None and not args.no_graph and world == 1:
+    if sac is not None and not args.no_graph:
+        n_fill = 0
         while len(sac.replay) < sac.replay.capacity:      # the graph samples from a full ring
             do_step(0)
+            n_fill += 1
+        # a full ring costs capacity / E steps of simulated time: fresh arrivals from here on
+        c0 = cur_step()
+        env.gen_poisson(wl["rate"], mean_work, (c0 + warmup + steps + 64) * DT, seed=1234, t_start=c0 * DT, window=1)
         env.profile_begin(10)
         for k in range(10):
             do_step(k)
         prof_eager = env.profile_end()
-        sac.capture(1)
+        sac.capture(1)          # under data parallelism the NCCL all-reduces are captured with it
         graphed = True
-    for k in range(args.warmup):
-        do_step(k)
-    env.check_status()
-    cur0 = env.get_state("arr_cursor").astype(np.int64).sum()
-    l0 = env.launch_count + (pops.LAUNCHES if (rollout is not None or sac is not None) else 0)
+
+    def timed_window(n_steps):
+        for k in range(warmup):
+            do_step(k)
+        env.check_status()
+        cur0 = env.get_state("arr_cursor").astype(np.int64).sum()
+        l0 = launches_now()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.profile_begin(n_steps)   # CUDA events around each kernel, on the launching stream
+        barrier()
+        ev0.record()
+        for k in range(n_steps):
+            do_step(k)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        prof = env.profile_end()
+        pair_ms = getattr(env, "last_pair_ms", 0.0)
+        n_launch = launches_now() - l0
+        flows = env.get_state("arr_cursor").astype(np.int64).sum() - cur0
+        env.check_status()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        fl = torch.tensor([float(flows)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(fl, op=dist.ReduceOp.SUM)
+        return float(t.item()), ms, prof, pair_ms, n_launch, float(fl.item())
+
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and main:
         clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env.profile_begin(args.steps)   # CUDA events around each of the two kernels, on the launching stream
-    barrier()
-    ev0.record()
-    for k in range(args.steps):
-        do_step(k)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    ev_ms, ft_ms, prof_steps = env.profile_end()
+    ms_max, ms, prof, pair_ms, launches, flows = timed_window(steps)
+    clk = clocks.stop() if (rank == 0 and main) else None
+    ev_ms, ft_ms, prof_steps = prof
     if prof_eager is not None:
         ev_ms, ft_ms, prof_steps = prof_eager
-    clk = clocks.stop() if rank == 0 else None
-    launches = env.launch_count + (pops.LAUNCHES if (rollout is not None or sac is not None) else 0) - l0
+        pair_ms = None
     if graphed:
-        launches = (rollout if rollout is not None else sac).graph_launches * args.steps
-    flows = env.get_state("arr_cursor").astype(np.int64).sum() - cur0
-    env.check_status()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    fl = torch.tensor([float(flows)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
-    value = world * E * A * args.steps / (ms_max * 1e-3)
+        launches = (rollout if rollout is not None else sac).graph_launches * steps
+    value = world * E * A * steps / (ms_max * 1e-3)
 
-    # ---- end to end through the public API with HOST buffers (pinned H2D actions, D2H obs/reward/done)
-    if sac is not None:
-        # per step a trainer needs the rewards / dones back; the Gaussian draws go in from pinned memory
-        h_eps = [torch.randn((E, S), dtype=torch.float32).pin_memory() for _ in range(2)]
-        d_eps = torch.empty((E, S), dtype=torch.float32, device="cuda")
+    # C4: the replicas must stay in lock-step (identical initial weights + identical averaged gradients): checksum of
+    # every parameter, max - min over the ranks
+    param_spread = None
+    if sac_agent is not None:
+        cs = torch.stack([b.flat_p.double().sum() for b in (sac_agent.policy_optimizer.bucket, sac_agent.q1_optimizer.bucket,
+                                                          sac_agent.q2_optimizer.bucket)]).sum().reshape(1)
+        hi, lo = cs.clone(), cs.clone()
+        if world > 1:
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        param_spread = float((hi - lo).item())
+
+    peak, which = measured_peaks()
+    F = flows / (world * E * A * steps)
+    bytes_as = algorithmic_bytes_per_agent_step(S, K, F)   # S = servers per agent
+    b_event, b_stats = algorithmic_bytes_split(S, K, F)
+    step_s = ms * 1e-3 / steps
+    env_s = (ev_ms + ft_ms) * 1e-3 / max(prof_steps, 1)     # env kernels only (== step_s without a policy)
+    res = {"value": value, "ms_per_step": ms_max / steps, "steps": steps, "burnin_steps": burnin,
+           "flows_per_agent_step": F, "gpu_launches": int(launches), "cuda_graph": graphed,
+           "env_kernels_ms": env_s * 1e3,
+           "roofline_step": {"algorithmic_bytes_per_agent_step": bytes_as,
+                             "achieved": bytes_as * E * A / env_s / 1e9, "frac": bytes_as * E * A / env_s / 1e9 / peak,
+                             "of": "env-step kernels (event + statistics pass)"}}
+    if has_policy:
+        res["policy_ms_per_step"] = (step_s - env_s) * 1e3
+    if param_spread is not None:
+        res["param_checksum_spread_over_ranks"] = param_spread
+    if not main:
+        env.close()
+        del env, rollout, sac, sac_agent, pool
+        torch.cuda.empty_cache()
+        return res if rank == 0 else None
+
+    # ---- end to end through the public API with HOST buffers
+    e2e_changed = None
+    if has_policy:
+        # what a trainer exchanges with the device-resident rollout per step: exploration draws in (pinned H2D),
+        # rewards / dones (/ chosen actions) out (pinned D2H); observations stay on the device
         o_rew = torch.empty((E,), dtype=torch.float64, pin_memory=True)
         o_done = torch.empty((E,), dtype=torch.uint8, pin_memory=True)
+        if sac is not None:
+            h_eps = [torch.randn((E, S), dtype=torch.float32).pin_memory() for _ in range(2)]
+            d_eps = torch.empty((E, S), dtype=torch.float32, device="cuda")
 
-        def e2e_step(k):
-            d_eps.copy_(h_eps[k % 2], non_blocking=True)
-            if graphed:
-                (_, r_, dn_, _), _ = sac.step_graph()   # (Gaussian draws come from the device generator here)
-            else:
-                _, r_, dn_, _ = sac.step(eps=d_eps)
-                sac.update(1, sac_gen)
-            o_rew.copy_(r_, non_blocking=True)
-            o_done.copy_(dn_, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        h2d, d2h = E * S * 4, E * 8 + E
+            def e2e_step(k):
+                d_eps.copy_(h_eps[k % 2], non_blocking=True)
+                if graphed:
+                    (_, r_, dn_, _), _ = sac.step_graph()   # (Gaussian draws come from the device generator here)
+                else:
+                    _, r_, dn_, _ = sac.step(eps=d_eps)
+                    sac.update(1, sac_gen)
+                o_rew.copy_(r_, non_blocking=True)
+                o_done.copy_(dn_, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            h2d, e2e_d2h = E * S * 4, E * 8 + E
+        else:
+            h_u = [torch.empty((E, A), dtype=torch.float32, pin_memory=True).copy_(upool[i]) for i in range(2)]
+            h_r = [torch.empty((E, A), dtype=torch.int32, pin_memory=True).copy_(rpool[i]) for i in range(2)]
+            d_u, d_r = torch.empty_like(upool[0]), torch.empty_like(rpool[0])
+            o_act = torch.empty((E, A), dtype=torch.int32, pin_memory=True)
+
+            def e2e_step(k):
+                if graphed:
+                    rollout.graph_u.copy_(h_u[k % 2], non_blocking=True)
+                    rollout.graph_rnd.copy_(h_r[k % 2], non_blocking=True)
+                    _, r_, dn_, a_ = rollout.step_graph()
+                else:
+                    d_u.copy_(h_u[k % 2], non_blocking=True)
+                    d_r.copy_(h_r[k % 2], non_blocking=True)
+                    _, r_, dn_, a_ = rollout.step(0.05, d_u, d_r)
+                o_rew.copy_(r_, non_blocking=True)
+                o_done.copy_(dn_, non_blocking=True)
+                o_act.copy_(a_, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            h2d, e2e_d2h = E * A * 8, E * 8 + E + E * A * 4
+        torch.cuda.synchronize()
         e2e_step(0)
-    elif rollout is None:
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = world * E * A * e2e_steps / float(te.item())
+        e2e_api = "device-resident rollout: exploration draws in, rewards / dones / actions out per step"
+    else:
         h_act = []
         for p_ in pool[:2]:
             t_ = env.pinned_actions()
             t_.copy_(p_.view_as(t_))
             h_act.append(t_)
         torch.cuda.synchronize()
-        env.step_host(h_act[0])  # allocates pinned output buffers, untimed
-        e2e_step = lambda k: env.step_host(h_act[k % 2])
-        h2d, d2h = env.e2e_bytes
-    else:
-        # what a trainer exchanges with the rollout per step: exploration draws in (pinned H2D),
-        # rewards / dones / chosen actions out (pinned D2H); observations stay on the device
-        h_u = [torch.empty((E, A), dtype=torch.float32, pin_memory=True).copy_(upool[i]) for i in range(2)]
-        h_r = [torch.empty((E, A), dtype=torch.int32, pin_memory=True).copy_(rpool[i]) for i in range(2)]
-        d_u, d_r = torch.empty_like(upool[0]), torch.empty_like(rpool[0])
-        o_rew = torch.empty((E,), dtype=torch.float64, pin_memory=True)
-        o_done = torch.empty((E,), dtype=torch.uint8, pin_memory=True)
-        o_act = torch.empty((E, A), dtype=torch.int32, pin_memory=True)
 
-        def e2e_step(k):
-            if not graphed:
-                d_u.copy_(h_u[k % 2], non_blocking=True)
-                d_r.copy_(h_r[k % 2], non_blocking=True)
-            if graphed:
-                rollout.graph_u.copy_(h_u[k % 2], non_blocking=True)
-                rollout.graph_rnd.copy_(h_r[k % 2], non_blocking=True)
-                _, r_, dn_, a_ = rollout.step_graph()
-            else:
-                _, r_, dn_, a_ = rollout.step(0.05, d_u, d_r)
-            o_rew.copy_(r_, non_blocking=True)
-            o_done.copy_(dn_, non_blocking=True)
-            o_act.copy_(a_, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        h2d, d2h = E * A * 8, E * 8 + E + E * A * 4
-        torch.cuda.synchronize()
-        e2e_step(0)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(k)
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        def e2e_leg(mode):
+            env.step_host(h_act[0], obs=mode)  # allocates pinned output buffers / builds the host mirror, untimed
+            barrier()
+            t0 = time.perf_counter()
+            moved = 0
+            for k in range(e2e_steps):
+                env.step_host(h_act[k % 2], obs=mode)
+                moved += env.last_d2h_bytes
+            torch.cuda.synchronize()
+            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return world * E * A * e2e_steps / float(te.item()), moved / max(e2e_steps, 1)
+
+        e2e_value, e2e_d2h = e2e_leg("full")
+        e2e_changed = e2e_leg("changed")
+        h2d = env.e2e_bytes[0]
+        e2e_api = "VecLoadBalanceEnv.step_host(actions): full (E,S,11) float32 observations into pinned host memory"
+
+    # ---- second timed window, late in the episode (acceptance of Algorithm R ~ K / count: few touched reservoirs)
+    late_res = None
+    if late:
+        chunk, win = 448, 1
+        while True:
+            c0 = cur_step()
+            if c0 >= args.late_burnin:
+                break
+            n = min(chunk, args.late_burnin - c0)
+            tail = warmup + steps + 4 * (e2e_steps + 1) + 8 if c0 + n >= args.late_burnin else 0
+            env.gen_poisson(wl["rate"], mean_work, (c0 + n + tail) * DT, seed=1234, t_start=c0 * DT, window=win)
+            win += 1
+            for k in range(n):
+                do_step(k)
+        l_ms_max, l_ms, l_prof, l_pair, _, l_flows = timed_window(steps)
+        l_ev, l_ft, l_n = l_prof
+        l_F = l_flows / (world * E * A * steps)
+        l_bytes = algorithmic_bytes_per_agent_step(S, K, l_F)
+        late_res = {"burnin_steps": args.late_burnin, "ms_per_step": l_ms_max / steps,
+                    "value": world * E * A * steps / (l_ms_max * 1e-3),
+                    "event_kernel_ms": l_ev / max(l_n, 1), "statistics_pass_ms": l_ft / max(l_n, 1),
+                    "pair_kernel_ms": l_pair / max(l_n, 1), "flows_per_agent_step": l_F,
+                    "algorithmic_frac": l_bytes * E * A / (l_ms * 1e-3 / steps) / 1e9 / peak,
+                    "note": "most reservoirs are untouched in a step this deep into an episode and are not re-read, "
+                            "so the algorithmic fraction (all reservoirs re-read) overstates DRAM use; the event "
+                            "kernel dominates here"}
+        e2e_late_full = e2e_leg("full")
+        e2e_late = e2e_leg("changed")
+        late_res["e2e"] = {"value": e2e_late_full[0], "d2h_bytes_per_step": e2e_late_full[1],
+                           "changed_rows": {"value": e2e_late[0], "d2h_bytes_per_step": e2e_late[1]}}
+
+    if rank != 0:
+        return None
+    ft_avg_s = ft_ms * 1e-3 / max(prof_steps, 1)
+    ev_avg_s = ev_ms * 1e-3 / max(prof_steps, 1)
+    pr_avg_s = (pair_ms or 0.0) * 1e-3 / max(prof_steps, 1)
+    traffic = tsrc = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic, tsrc = tj.get(name, {}), tj.get("_source")
+    phys_step = (traffic.get("statistics_pass_total", 0) + traffic.get("event_kernel", 0)) if traffic else None
+    step_achieved = bytes_as * E * A / step_s / 1e9
+    res.update({
+        "roofline": {
+            "bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+            "peak_source": which,
+            "kernel": "whole env step = mlb::event_kernel + mlb::pair_kernel<.,0> + mlb::pair_kernel<.,1> + "
+                      "mlb::feature_kernel (four launches); headline frac = algorithmic bytes of the step / step time",
+            "algorithmic_bytes_per_agent_step": bytes_as,
+            # NOT sampled in this run: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
+            # the same command, per launch, committed under profiles/ (see traffic_source)
+            "traffic": phys_step, "traffic_source": tsrc,
+            "physical": ({"achieved": phys_step / step_s / 1e9, "frac": phys_step / step_s / 1e9 / peak,
+                          "note": "profiled DRAM bytes (profiles/traffic.json) over THIS run's step time"}
+                         if phys_step else None),
+            "kernels": [
+                {"kernel": "mlb::event_kernel<SED>", "ms": ev_avg_s * 1e3, "algorithmic_bytes_per_agent_step": b_event,
+                 "achieved": b_event * E * A / ev_avg_s / 1e9 if ev_avg_s > 0 else None,
+                 "traffic": traffic.get("event_kernel") if traffic else None, "bound": "issue / latency"},
+                {"kernel": "statistics pass: mlb::pair_kernel x2 + mlb::feature_kernel (three launches)",
+                 "ms": ft_avg_s * 1e3, "pair_kernels_ms": pr_avg_s * 1e3,
+                 "algorithmic_bytes_per_agent_step": b_stats,
+                 "achieved": b_stats * E * A / ft_avg_s / 1e9, "frac": b_stats * E * A / ft_avg_s / 1e9 / peak,
+                 "traffic": traffic.get("statistics_pass_total") if traffic else None,
+                 "physical_frac": (traffic["statistics_pass_total"] / ft_avg_s / 1e9 / peak) if traffic and traffic.get("statistics_pass_total") else None,
+                 "note": "the algorithmic fraction can exceed 1: reservoirs untouched in a step keep their cached features "
+                         "and are not re-read (SURVEY 8d asks for both numbers)", "bound": "hbm"}],
+            "kernel_share_of_step": {"event": ev_ms / max(ft_ms + ev_ms, 1e-9), "statistics": ft_ms / max(ft_ms + ev_ms, 1e-9)},
+            "flows_per_agent_step": F, "late_episode": late_res},
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": e2e_d2h, "steps": e2e_steps, "api": e2e_api,
+                "changed_rows": ({"value": e2e_changed[0], "d2h_bytes_per_step": e2e_changed[1],
+                                  "api": "step_host(actions, obs='changed'): n_flow_on column + only the rows in which a "
+                                         "reservoir slot was written, applied by host threads to the persistent host "
+                                         "observation array (bit-equal result)"} if e2e_changed else None)},
+        "clocks": clk})
+    env.close()
+    del env, pool
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_legs(args, wl):
+    """CPU numbers reported beside the GPU line: (ii) the C restatement of the composed flow
+    env on all host threads = `cpu_baseline`; (iii) the reference's own C reservoir micro-benchmark (oracle/_ref, built
+    from the reference's reservoir.c by oracle/Makefile: a native upper bound for one add); (i) the reference's literal
+    simulation-mode step (random features + reward, env.py:215-286) through its C restatement on all threads."""
+    import re
+    n_envs = max(4 * (os.cpu_count() or 1), 32)
+    v, steps, cores = cpu_oracle_rate(wl, n_envs=n_envs, burnin=args.burnin, budget_s=args.cpu_budget, threads=0)
+    out = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+           "sample": f"{n_envs} envs of the same workload, {steps} steps after {args.burnin} burn-in steps, "
+                     f"oracle/flow_oracle.c on {cores} threads",
+           "note": "a LITERAL port of the reference's Python arithmetic (every touched reservoir re-sorted, float64 pow "
+                   "per slot), as the parity oracle must be: a baseline for orientation, not an optimised CPU program"}
+    exe = os.path.join(ROOT, "oracle", "_ref", "reservoir_c_bench")
+    if os.path.exists(exe):
+        try:
+            txt = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+            m = re.search(r"Throughput:\s*([0-9.]+)\s*M ops/sec", txt)
+            if m:
+                out["reference_c_reservoir_add"] = {"value": float(m.group(1)) * 1e6, "unit": "adds/s", "cores": 1,
+                                                    "kind": "reference",
+                                                    "what": "reference's reservoir.c benchmark (reservoir.c:77-102), unmodified"}
+        except Exception as exc:   # noqa: BLE001
+            out["reference_c_reservoir_add"] = {"unavailable": str(exc)}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import flow_oracle as fo
+        S = wl["servers"] * wl["agents"]
+        t0, n = time.perf_counter(), 0
+        g = fo.LegacyObs(1)
+        while time.perf_counter() - t0 < 1.0:
+            for _ in range(200):
+                fo.reward_from_obs("jain", 10, g.next(S))
+            n += 200
+        out["reference_literal_step"] = {"value": n / (time.perf_counter() - t0), "unit": "env-steps/s", "cores": 1,
+                                         "kind": "port", "what": "what LoadBalanceEnv.step literally does in simulation "
+                                         "mode (env.py:425-448 random features + reward), C restatement, one thread; "
+                                         "the Python original: 681 steps/s at 64 servers (BASELINE.md)"}
+    except Exception as exc:       # noqa: BLE001
+        out["reference_literal_step"] = {"unavailable": str(exc)}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    # host side of the end-to-end step: pinned buffers on the NUMA node next to this rank's GPU
+    from marllb_b200.shard import bind_host_to_gpu
+    prev_affinity = bind_host_to_gpu(local) if (world > 1 and not os.environ.get("MLB_NO_NUMA_BIND")) else None
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * A * e2e_steps / float(te.item())
-
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = dict(WORKLOADS[args.workload])
+    res = measure(args, args.workload, world, rank, local, main=True)
+    configs = {}
+    if not args.no_configs and args.workload == "c5":
+        for name in ("c2", "c3", "c4"):
+            r = measure(args, name, world, rank, local, main=False)
+            if rank == 0:
+                r["config"] = workload_config(args, WORKLOADS[name], world)["workload"]
+                configs[name] = r
     if rank == 0:
-        F = float(fl.item()) / (world * E * A * args.steps)
-        bytes_as = algorithmic_bytes_per_agent_step(S, K, F)   # S = servers per agent
-        b_event, b_feature = algorithmic_bytes_split(S, K, F)
-        peak, which = measured_peaks()
-        # a step = event_kernel + feature_kernel; the dominant one is feature_kernel.  Its average
-        # launch duration comes from CUDA events recorded around it inside the timed region.
-        ft_avg_s = ft_ms * 1e-3 / max(prof_steps, 1)
-        ev_avg_s = ev_ms * 1e-3 / max(prof_steps, 1)
-        achieved = b_feature * E * A / ft_avg_s / 1e9
-        step_achieved = bytes_as * E * A / (ms * 1e-3 / args.steps) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get(args.workload, {}).get("feature_kernel")
         out = {
-            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "metric": "agent-steps/sec", "value": res["value"], "unit": "agent-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, wl),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": which,
-                         "kernel": "reservoir statistics pass = mlb::pair_kernel + mlb::feature_kernel (two launches)",
-                         "kernel_ms": ft_avg_s * 1e3,
-                         "pair_kernel_ms": getattr(env, "last_pair_ms", 0.0) / max(prof_steps, 1) if prof_eager is None else None,
-                         "kernel_share_of_step": ft_ms / max(ft_ms + ev_ms, 1e-9),
-                         "algorithmic_bytes_per_agent_step": b_feature,
-                         "other_kernels": [{"kernel": "mlb::event_kernel<SED>", "kernel_ms": ev_avg_s * 1e3,
-                                            "algorithmic_bytes_per_agent_step": b_event,
-                                            "achieved": b_event * E * A / ev_avg_s / 1e9 if ev_avg_s > 0 else None}],
-                         "step": {"algorithmic_bytes_per_agent_step": bytes_as, "achieved": step_achieved,
-                                  "frac": step_achieved / peak},
-                         # algorithmic bytes assume every reservoir is re-read each step; reservoirs untouched in a
-                         # step are not (their features are invariant), so achieved can exceed the DRAM peak while
-                         # the physical traffic (`traffic`, ncu) over the same time stays below it
-                         "physical": ({"achieved": traffic / ft_avg_s / 1e9, "frac": traffic / ft_avg_s / 1e9 / peak}
-                                      if traffic else None),
-                         "flows_per_agent_step": F,
-                         "policy_ms_per_step": (ms / args.steps - (ev_ms + ft_ms) / max(prof_steps, 1)) if (rollout is not None or sac is not None) else None,
-                         "cuda_graph": graphed},
-            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": int(launches), "clocks": clk,
+            "data": "synthetic", "config": workload_config(args, wl, world),
+            "roofline": res["roofline"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
         }
-        if world == 1 and not args.no_cpu and rollout is None and sac is None:
-            del env
-            torch.cuda.empty_cache()
+        if configs:
+            # the other BASELINE.json configurations at the same N (short runs; c4 is the one with a collective:
+            # SAC update sharded over the GPUs, NCCL all-reduce of the gradient buckets inside the CUDA graph)
+            out["configs"] = configs
+        nccl_log = os.environ.get("NCCL_DEBUG_FILE")
+        if world > 1:
+            out["nccl"] = {"nranks": world, "version": ".".join(map(str, torch.cuda.nccl.version())),
+                           "debug": os.environ.get("NCCL_DEBUG"), "log": nccl_log}
+        if world == 1 and not args.no_cpu and wl.get("policy") is None:
             if prev_affinity is not None:
                 os.sched_setaffinity(0, prev_affinity)       # the CPU baseline uses every host core
-            v, steps, cores = cpu_oracle_rate(wl, n_envs=0 or max(4 * (os.cpu_count() or 1), 32),
-                                              burnin=args.burnin, budget_s=args.cpu_budget, threads=0)
-            out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                                   "sample": f"{max(4 * (os.cpu_count() or 1), 32)} envs of the same workload, "
-                                             f"{steps} steps after {args.burnin} burn-in steps, oracle/flow_oracle.c on {cores} threads"}
+            out["cpu_baseline"] = cpu_legs(args, wl)
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -518,6 +708,11 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--burnin", type=int, default=256, help="untimed steps that bring reservoirs to steady state")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--late-burnin", type=int, default=2048,
+                    help="second timed window after this many steps of the episode (0: skip)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short c2 / c3 / c4 runs of the `configs` sub-dict")
+    ap.add_argument("--config-steps", type=int, default=30)
+    ap.add_argument("--config-burnin", type=int, default=160)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-feature-cache", action="store_true")

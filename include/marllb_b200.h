@@ -180,6 +180,14 @@ int mlb_commit_arrivals(mlb_env *h, void *stream);
 int mlb_gen_poisson(mlb_env *h, double rate, double mean_work, double horizon,
                     uint64_t seed, void *stream);
 
+/* The same generator for the time window [t_start, t_end) of a running episode: replaces the resident arrivals by a
+ * fresh Poisson stream that starts at t_start (the process is memoryless) and rewinds the arrival cursors; call it
+ * between two steps, with t_start = the end of the last stepped window.  `window` keys the Philox counter so that
+ * successive windows draw different numbers (window 0, t_start 0 = mlb_gen_poisson).  Long episodes (env.py:81
+ * defaults to 10 000 steps) then need only one window of arrivals in HBM at a time. */
+int mlb_gen_poisson_window(mlb_env *h, double rate, double mean_work, double t_start, double t_end,
+                           uint64_t seed, uint32_t window, void *stream);
+
 /* Copy the arrival stream of (env, agent) back to the host (for CPU baselines).
  * Returns the flow count in *n; copies at most cap entries. Synchronous. */
 int mlb_get_arrivals(mlb_env *h, int32_t env, int32_t agent, float *time, float *work,
@@ -200,6 +208,24 @@ int mlb_reset(mlb_env *h, const uint8_t *env_mask, void *stream);
 int mlb_step(mlb_env *h, const void *action, int action_loc,
              float *out_obs, double *out_reward, uint8_t *out_done, int out_loc,
              void *stream);
+
+/*
+ * The same step for a HOST consumer that keeps its observation array across steps: instead of all E*S*11 floats,
+ * only what changed crosses PCIe -- the n_flow_on column (2 bytes per row) and one 48-byte record {row index, the 11
+ * floats} per row in which Algorithm R wrote a reservoir slot this step (untouched reservoirs keep their features:
+ * both decay-weighted statistics are invariant to `now`) -- and host threads apply them to `host_obs`.
+ *   host_obs   float [E][S][11], PINNED, persistent: must hold the observation of the previous step (after
+ *              mlb_reset: zeros; after steps taken through mlb_step: call mlb_step with out_obs = host_obs once)
+ *   action     HOST, cfg.action_kind encoding;  out_reward / out_done: HOST, nullable
+ *   threads    host threads that apply the records (<= 0: min(hardware threads, 16))
+ *   d2h_bytes  (nullable) receives the device->host bytes this call moved
+ * Chunks of envs are pipelined like in mlb_step; a chunk in which most rows changed (early in an episode) is copied
+ * as a plain block straight into place, so the call never moves more than mlb_step does.  Synchronous: returns when
+ * host_obs is up to date.  The result is bit-identical to mlb_step's out_obs.  (No reference counterpart: the
+ * reference env returns a fresh (S, 11) array per step, env.py:283-286.)
+ */
+int mlb_step_changed(mlb_env *h, const void *action, float *host_obs, double *out_reward, uint8_t *out_done,
+                     int threads, int64_t *d2h_bytes, void *stream);
 
 /* Per-flow server ids chosen so far (parallel to the arrival arrays), int32. */
 int mlb_get_assignments(mlb_env *h, int32_t *dst, int64_t n, int loc, void *stream);

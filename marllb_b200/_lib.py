@@ -35,7 +35,7 @@ EXPORTS = [
     "mlb_step", "mlb_get_assignments", "mlb_device_ptr", "mlb_get_state", "mlb_status",
     "mlb_launch_count", "mlb_profile_begin", "mlb_profile_end", "mlb_profile_pair_ms", "mlb_mt19937_fill", "mlb_reservoir_add", "mlb_reservoir_features",
     "mlb_reward_metric", "mlb_legacy_seed", "mlb_legacy_obs", "mlb_normalize_obs",
-    "mlb_stage_arrivals", "mlb_commit_arrivals", "mlb_legacy_step",
+    "mlb_stage_arrivals", "mlb_commit_arrivals", "mlb_legacy_step", "mlb_gen_poisson_window", "mlb_step_changed",
 ]
 
 
@@ -82,9 +82,11 @@ def load():
         "mlb_set_speeds": (C.c_int, [vp, vp, i64, C.c_int, vp]),
         "mlb_load_arrivals": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, vp]),
         "mlb_gen_poisson": (C.c_int, [vp, f64, f64, f64, u64, vp]),
+        "mlb_gen_poisson_window": (C.c_int, [vp, f64, f64, f64, f64, u64, C.c_uint32, vp]),
         "mlb_get_arrivals": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, i64, C.POINTER(i64)]),
         "mlb_reset": (C.c_int, [vp, vp, vp]),
         "mlb_step": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int, vp]),
+        "mlb_step_changed": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.POINTER(i64), vp]),
         "mlb_get_assignments": (C.c_int, [vp, vp, i64, C.c_int, vp]),
         "mlb_device_ptr": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "mlb_get_state": (C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_int]),

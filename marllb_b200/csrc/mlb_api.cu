@@ -6,7 +6,11 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -59,6 +63,15 @@ struct mlb_env {
     int prof_cap = 0, prof_n = 0;
     size_t state_bytes[MLB_F_COUNT_] = {0};
     void* state_ptr[MLB_F_COUNT_] = {nullptr};
+    // changed-rows host step (mlb_step_changed): device compaction buffers, pinned staging, host apply threads
+    uint32_t* cr_rec = nullptr;        // device [E*S][12] records: row index | 11 floats
+    uint16_t* cr_col = nullptr;        // device [E*S] n_flow_on column (dense, 2 bytes per row)
+    uint32_t* cr_cnt = nullptr;        // device [chunks] records written per chunk
+    uint32_t* cr_h_rec = nullptr;      // pinned mirrors
+    uint16_t* cr_h_col = nullptr;
+    uint32_t* cr_h_cnt = nullptr;
+    std::vector<cudaEvent_t> cr_ev_cnt, cr_ev_copy;
+    struct HostPool* pool = nullptr;
     // mlb_stage_arrivals may run on a second host thread next to mlb_step (see the header): the allocation list
     // and the error text are the two things both threads write
     std::mutex mu;
@@ -155,16 +168,16 @@ __global__ void gen_poisson_kernel(float* __restrict__ time, float* __restrict__
                                    int32_t* __restrict__ bucket, float* __restrict__ uu,
                                    int32_t* __restrict__ count, int n_streams, int cap, int Sa,
                                    uint32_t stream_base, double rate, double mean_work,
-                                   double horizon, uint64_t seed) {
+                                   double t_start, double horizon, uint64_t seed, uint32_t window) {
     const int lane = threadIdx.x & 31;
     const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sidx >= n_streams) return;
     const size_t base = (size_t)sidx * cap;
-    double t0 = 0.0;
+    double t0 = t_start;
     int n = 0;
     for (int chunk = 0; n < cap && t0 < horizon; chunk++) {
         uint32_t r[4];
-        philox4x32_10((uint32_t)(chunk * 32 + lane), stream_base + (uint32_t)sidx, 0x4d4c4221u, 0u,
+        philox4x32_10((uint32_t)(chunk * 32 + lane), stream_base + (uint32_t)sidx, 0x4d4c4221u, window,
                       (uint32_t)seed, (uint32_t)(seed >> 32), r);
         const double u1 = ((double)r[0] + 0.5) * (1.0 / 4294967296.0);
         const double u2 = ((double)r[1] + 0.5) * (1.0 / 4294967296.0);
@@ -190,6 +203,86 @@ __global__ void gen_poisson_kernel(float* __restrict__ time, float* __restrict__
     }
     if (lane == 0) count[sidx] = n;
 }
+
+// ------------------------------------------------------------------ changed-rows compaction
+// One thread per (env, server) row of envs [e0, e1): writes the row's n_flow_on into the dense 16-bit column and,
+// when Algorithm R wrote a slot of either reservoir of the row this step (res_chg, written by event_kernel for
+// every reservoir), appends {row index, the 11 observation floats} to this chunk's record list.
+__global__ void compact_rows_kernel(const DevState d, uint32_t* __restrict__ rec, uint16_t* __restrict__ col,
+                                    uint32_t* __restrict__ cnt) {
+    const int S = d.S;
+    const size_t row0 = (size_t)d.e0 * S, rows = (size_t)(d.e1 - d.e0) * S;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const bool in = i < rows;
+    const size_t row = row0 + (in ? i : 0);
+    const int e = (int)(row / S), sv = (int)(row - (size_t)e * S);
+    bool changed = false;
+    if (in) {
+        const uint32_t c0 = d.res_chg[((size_t)e * 2 + 0) * S + sv], c1 = d.res_chg[((size_t)e * 2 + 1) * S + sv];
+        changed = d.feature_cache != 1 || ((c0 >> 21) & 7u) != 0u || ((c1 >> 21) & 7u) != 0u;
+        col[row] = (uint16_t)d.n_on[row];
+    }
+    const unsigned bal = __ballot_sync(MLB_FULL, changed);
+    if (bal == 0u) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(cnt, (uint32_t)__popc(bal));
+    base = __shfl_sync(MLB_FULL, base, 0);
+    if (changed) {
+        const size_t k = row0 + base + __popc(bal & ((1u << lane) - 1u));   // chunk's region starts at its first row
+        const float* o = d.obs + row * MLB_OBS_COLS;
+        uint4* r = reinterpret_cast<uint4*>(rec + k * 12);
+        r[0] = make_uint4((uint32_t)row, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]));
+        r[1] = make_uint4(__float_as_uint(o[3]), __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]));
+        r[2] = make_uint4(__float_as_uint(o[7]), __float_as_uint(o[8]), __float_as_uint(o[9]), __float_as_uint(o[10]));
+    }
+}
+
+// Host threads that apply the compact records to the caller's observation array (persistent across calls).
+struct HostPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::function<void(int, int)> job;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    explicit HostPool(int n) {
+        for (int t = 0; t < n; t++)
+            th.emplace_back([this, t, n] {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::function<void(int, int)> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return stop || gen != seen; });
+                        if (stop) return;
+                        seen = gen;
+                        f = job;
+                    }
+                    f(t, n);
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (--pending == 0) cv_done.notify_all();
+                }
+            });
+    }
+    void run(std::function<void(int, int)> f) {      // f(thread index, thread count) on every thread; returns when all are done
+        std::unique_lock<std::mutex> lk(mu);
+        job = std::move(f);
+        pending = (int)th.size();
+        gen++;
+        cv.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
 
 // ------------------------------------------------------------------ helpers
 template <int POLICY, int RNG>
@@ -357,6 +450,12 @@ int mlb_destroy(mlb_env* h) {
     for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h->pool;
+    for (cudaEvent_t e : h->cr_ev_cnt) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->cr_ev_copy) cudaEventDestroy(e);
+    if (h->cr_h_rec) cudaFreeHost(h->cr_h_rec);
+    if (h->cr_h_col) cudaFreeHost(h->cr_h_col);
+    if (h->cr_h_cnt) cudaFreeHost(h->cr_h_cnt);
     if (h->stg_ready) cudaEventDestroy(h->stg_ready);
     if (h->stg_free) cudaEventDestroy(h->stg_free);
     delete h;
@@ -692,13 +791,20 @@ int mlb_commit_arrivals(mlb_env* h, void* stream) {
 }
 
 int mlb_gen_poisson(mlb_env* h, double rate, double mean_work, double horizon, uint64_t seed, void* stream) {
+    return mlb_gen_poisson_window(h, rate, mean_work, 0.0, horizon, seed, 0u, stream);
+}
+
+int mlb_gen_poisson_window(mlb_env* h, double rate, double mean_work, double t_start, double t_end, uint64_t seed,
+                           uint32_t window, void* stream) {
     if (!h) return MLB_EINVAL;
-    if (!(rate > 0) || !(mean_work > 0) || !(horizon > 0)) return fail(h, MLB_EINVAL, "rate, mean_work, horizon must be positive");
+    const double horizon = t_end;
+    if (!(rate > 0) || !(mean_work > 0) || !(t_start >= 0) || !(t_end > t_start))
+        return fail(h, MLB_EINVAL, "rate, mean_work must be positive and 0 <= t_start < t_end");
     CK(h, cudaSetDevice(h->device));
     DevState& d = h->d;
     cudaStream_t st = (cudaStream_t)stream;
     const int EA = d.E * d.A;
-    const double mu = rate * horizon;
+    const double mu = rate * (t_end - t_start);
     const int cap = (int)(mu + 8.0 * std::sqrt(mu) + 64.0);
     const bool alias = needs_bucket(h->cfg.policy);
     int rc = alloc_arrivals(h, (int64_t)EA * cap, alias);
@@ -711,7 +817,7 @@ int mlb_gen_poisson(mlb_env* h, double rate, double mean_work, double horizon, u
     gen_poisson_kernel<<<blocks, threads, 0, st>>>(h->arr_time, h->arr_work, alias ? h->arr_bucket : nullptr,
                                                    alias ? h->arr_u : nullptr, h->arr_n, EA, cap, d.Sa,
                                                    (uint32_t)h->cfg.env_id_base * (uint32_t)d.A,
-                                                   rate, mean_work, horizon, seed);
+                                                   rate, mean_work, t_start, horizon, seed, window);
     h->launches++;
     CK(h, cudaGetLastError());
     CK(h, cudaMemsetAsync(d.arr_cur, 0, (size_t)EA * 4, st));
@@ -847,6 +953,129 @@ int mlb_step(mlb_env* h, const void* action, int action_loc, float* out_obs, dou
     if (out_obs) CK(h, cudaMemcpyAsync(out_obs, d.obs, ES * MLB_OBS_COLS * 4, kind, st));
     if (out_reward) CK(h, cudaMemcpyAsync(out_reward, d.reward, (size_t)d.E * 8, kind, st));
     if (out_done) CK(h, cudaMemcpyAsync(out_done, d.done, (size_t)d.E, kind, st));
+    return MLB_OK;
+}
+
+// End-to-end step that moves only what changed (see the header).  Synchronous.
+int mlb_step_changed(mlb_env* h, const void* action, float* host_obs, double* out_reward, uint8_t* out_done,
+                     int threads, int64_t* d2h_bytes, void* stream) {
+    if (!h || !action || !host_obs) return fail(h, MLB_EINVAL, "null argument");
+    if (!h->have_arrivals) return fail(h, MLB_ESTATE, "mlb_step before mlb_load_arrivals / mlb_gen_poisson");
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevState& d = h->d;
+    const size_t S = (size_t)d.S, ES = (size_t)d.E * S;
+    const size_t asz = action_elem(d.action_kind);
+    int n_chunks = d.E >= h->host_chunks * 1024 ? h->host_chunks : 1;
+    if (n_chunks < 1) n_chunks = 1;
+    if (!h->cr_rec) {
+        CK(h, dalloc(h, &h->cr_rec, ES * 12));
+        CK(h, dalloc(h, &h->cr_col, ES));
+        CK(h, dalloc(h, &h->cr_cnt, (size_t)64));
+        CK(h, cudaMallocHost((void**)&h->cr_h_rec, ES * 48));
+        CK(h, cudaMallocHost((void**)&h->cr_h_col, ES * 2));
+        CK(h, cudaMallocHost((void**)&h->cr_h_cnt, 64 * 4));
+    }
+    if (n_chunks > 64) n_chunks = 64;
+    if (!h->copy_stream) {
+        CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(h, cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming));
+    }
+    while ((int)h->cr_ev_cnt.size() < n_chunks) {
+        cudaEvent_t a, b;
+        CK(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->cr_ev_cnt.push_back(a);
+        h->cr_ev_copy.push_back(b);
+    }
+    if (threads <= 0) {
+        threads = (int)std::thread::hardware_concurrency();
+        threads = threads > 16 ? 16 : (threads < 1 ? 1 : threads);
+    }
+    if (!h->pool || (int)h->pool->th.size() != threads) {
+        delete h->pool;
+        h->pool = new HostPool(threads);
+    }
+    const int per = ((d.E + n_chunks - 1) / n_chunks + h->epb - 1) / h->epb * h->epb;
+    // ---- phase 1: every chunk's kernels, compaction and record count, back to back on the caller's stream
+    CK(h, cudaMemsetAsync(h->cr_cnt, 0, 64 * 4, st));
+    int nc = 0;
+    for (int e0 = 0; e0 < d.E; e0 += per, nc++) {
+        const int e1 = e0 + per < d.E ? e0 + per : d.E;
+        const size_t ne = (size_t)(e1 - e0);
+        CK(h, cudaMemcpyAsync((char*)h->d_action + (size_t)e0 * S * asz, (const char*)action + (size_t)e0 * S * asz,
+                              ne * S * asz, cudaMemcpyHostToDevice, st));
+        const int rc = launch_step(h, h->d_action, e0, e1, st, nullptr);
+        if (rc != MLB_OK) return rc;
+        DevState dv = h->d;
+        dv.e0 = e0;
+        dv.e1 = e1;
+        const size_t rows = ne * S;
+        compact_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(dv, h->cr_rec, h->cr_col, h->cr_cnt + nc);
+        h->launches++;
+        CK(h, cudaMemcpyAsync(h->cr_h_cnt + nc, h->cr_cnt + nc, 4, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaEventRecord(h->cr_ev_cnt[nc], st));
+    }
+    CK(h, cudaGetLastError());
+    if (out_reward) CK(h, cudaMemcpyAsync(out_reward, d.reward, (size_t)d.E * 8, cudaMemcpyDeviceToHost, st));
+    if (out_done) CK(h, cudaMemcpyAsync(out_done, d.done, (size_t)d.E, cudaMemcpyDeviceToHost, st));
+    // ---- phase 2: per chunk, as soon as its count is known: the records + the n_flow_on column (or, when most rows
+    // changed, the chunk's observation block straight into place) on the copy stream; the host threads apply chunk
+    // c - 1 while chunk c is on the wire
+    int64_t moved = 0;
+    std::vector<uint32_t> n_rec(nc);
+    std::vector<char> sparse(nc);
+    auto apply = [&](int c) -> int {
+        CK(h, cudaEventSynchronize(h->cr_ev_copy[c]));
+        if (!sparse[c]) return MLB_OK;
+        const int e0 = c * per, e1 = e0 + per < d.E ? e0 + per : d.E;
+        const size_t row0 = (size_t)e0 * S, rows = (size_t)(e1 - e0) * S;
+        const uint32_t* rec = h->cr_h_rec + row0 * 12;
+        const uint16_t* col = h->cr_h_col + row0;
+        const uint32_t n = n_rec[c];
+        h->pool->run([=](int t, int nt) {
+            const size_t a = rows * (size_t)t / nt, b = rows * (size_t)(t + 1) / nt;
+            for (size_t i = a; i < b; i++) {                     // n_flow_on of every row; untouched lines stay clean
+                float* o = host_obs + (row0 + i) * MLB_OBS_COLS;
+                const float v = (float)col[i];
+                if (*o != v) *o = v;
+            }
+            const size_t ra = (size_t)n * t / nt, rb = (size_t)n * (t + 1) / nt;
+            for (size_t k = ra; k < rb; k++) {
+                const uint32_t* r = rec + k * 12;
+                memcpy(host_obs + (size_t)r[0] * MLB_OBS_COLS, r + 1, MLB_OBS_COLS * 4);
+            }
+        });
+        return MLB_OK;
+    };
+    for (int c = 0; c < nc; c++) {
+        const int e0 = c * per, e1 = e0 + per < d.E ? e0 + per : d.E;
+        const size_t row0 = (size_t)e0 * S, rows = (size_t)(e1 - e0) * S;
+        CK(h, cudaEventSynchronize(h->cr_ev_cnt[c]));
+        const uint32_t n = h->cr_h_cnt[c];
+        n_rec[c] = n;
+        sparse[c] = (size_t)n * 48 + rows * 2 < rows * MLB_OBS_COLS * 4 * 3 / 4;
+        if (sparse[c]) {
+            CK(h, cudaMemcpyAsync(h->cr_h_col + row0, h->cr_col + row0, rows * 2, cudaMemcpyDeviceToHost, h->copy_stream));
+            if (n) CK(h, cudaMemcpyAsync(h->cr_h_rec + row0 * 12, h->cr_rec + row0 * 12, (size_t)n * 48, cudaMemcpyDeviceToHost, h->copy_stream));
+            moved += (int64_t)rows * 2 + (int64_t)n * 48 + 4;
+        } else {
+            CK(h, cudaMemcpyAsync(host_obs + row0 * MLB_OBS_COLS, d.obs + row0 * MLB_OBS_COLS, rows * MLB_OBS_COLS * 4,
+                                  cudaMemcpyDeviceToHost, h->copy_stream));
+            moved += (int64_t)rows * MLB_OBS_COLS * 4 + 4;
+        }
+        CK(h, cudaEventRecord(h->cr_ev_copy[c], h->copy_stream));
+        if (c > 0) {
+            const int rc = apply(c - 1);
+            if (rc != MLB_OK) return rc;
+        }
+    }
+    {
+        const int rc = apply(nc - 1);
+        if (rc != MLB_OK) return rc;
+    }
+    CK(h, cudaStreamSynchronize(st));
+    if (d2h_bytes) *d2h_bytes = moved + (out_reward ? (int64_t)d.E * 8 : 0) + (out_done ? (int64_t)d.E : 0);
     return MLB_OK;
 }
 

@@ -96,22 +96,40 @@ class FlatBucket:
         return [flat[o:o + n].view(shape) for o, n, shape in self._slices]
 
 
-def allreduce_mean_(flat_g, group=None):
-    """Data-parallel gradient reduction over one flat bucket: NCCL (or gloo) all-reduce SUM, then
-    divide by the world size so the loss keeps its mean-over-the-global-batch meaning
-    (F.mse_loss / .mean(), sac_agent.py:197-198,216).  No-op without an initialised process group."""
+def _dp_world(group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return flat_g
-    world = dist.get_world_size(group)
+        return 1
+    return dist.get_world_size(group)
+
+
+def allreduce_mean_(flat_g, group=None):
+    """Data-parallel gradient reduction over one flat bucket: ONE all-reduce that averages over the ranks, so the
+    loss keeps its mean-over-the-global-batch meaning (F.mse_loss / .mean(), sac_agent.py:197-198,216).  NCCL
+    averages inside the collective (ncclAvg: no separate scaling launch); gloo (CPU tests) sums, then scales.
+    No-op without an initialised process group."""
+    import torch.distributed as dist
+    world = _dp_world(group)
     if world == 1:
         return flat_g
-    dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=group)
     if flat_g.is_cuda:
-        ops.axpby(0.0, flat_g, 1.0 / world, flat_g)
+        dist.all_reduce(flat_g, op=dist.ReduceOp.AVG, group=group)
     else:
+        dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=group)
         flat_g.mul_(1.0 / world)
     return flat_g
+
+
+_comm_streams = {}
+
+
+def comm_stream(device):
+    """One side stream per device for the gradient all-reduces ("launched on a side stream right after
+    the last backward GEMM and consumed by the fused Adam kernel")."""
+    key = (device.type, device.index)
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(device=device)
+    return _comm_streams[key]
 
 
 class Adam:
@@ -129,11 +147,31 @@ class Adam:
         self._t_dev = torch.zeros(1, dtype=torch.int32, device=bucket.flat_p.device)
         self._coef_dev = torch.zeros(2, dtype=torch.float32, device=bucket.flat_p.device)
         self.data_parallel, self.max_grad_norm = data_parallel, max_grad_norm
+        self._reduce_done = None     # event of an all-reduce in flight on the side stream (reduce_async)
+
+    def reduce_async(self):
+        """Start the data-parallel all-reduce of this bucket's gradients on the side stream, right after the
+        backward pass that produced them; step() waits for it.  Whatever the caller launches in between on the
+        compute stream overlaps the collective (the fork / join is expressed with events, so it is captured into a
+        CUDA graph like any other launch).  No-op on one rank."""
+        b = self.bucket
+        if not self.data_parallel or not b.flat_g.is_cuda or _dp_world() == 1:
+            return
+        cur = torch.cuda.current_stream(b.flat_g.device)
+        side = comm_stream(b.flat_g.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            allreduce_mean_(b.flat_g)
+            self._reduce_done = torch.cuda.Event()
+            self._reduce_done.record(side)
 
     def step(self):
         """[all-reduce] -> [clip by the GLOBAL norm] -> Adam, each over the whole bucket."""
         b = self.bucket
-        if self.data_parallel:
+        if self._reduce_done is not None:
+            torch.cuda.current_stream(b.flat_g.device).wait_event(self._reduce_done)
+            self._reduce_done = None
+        elif self.data_parallel:
             allreduce_mean_(b.flat_g)
         if self.max_grad_norm is not None:
             ops.clip_grad_norm_([b.flat_g], self.max_grad_norm)

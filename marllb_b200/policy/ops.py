@@ -343,8 +343,8 @@ def sac_alpha_loss(logp, log_alpha, target_entropy):
     return loss, d
 
 
-def exp_scalar(x):
-    y = torch.empty_like(x)
+def exp_scalar(x, out=None):
+    y = torch.empty_like(x) if out is None else out
     check(_L().mlb_exp_scalar(_p(x), _p(y), _st()))
     return y
 

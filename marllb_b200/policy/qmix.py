@@ -440,7 +440,7 @@ class QMIXAgent:
         dones = torch.as_tensor(batch['dones'], dtype=f32).to(dev).contiguous()       # [B,T]
         seq_len = torch.as_tensor(np.asarray(batch['seq_lengths'], dtype=np.int32)).to(dev)
         key = (tuple(obs.shape), tuple(actions.shape), tuple(states.shape))
-        if self.graph_updates and not self._dp_active():
+        if self.graph_updates:
             stats = self._update_graphed(key, obs, actions, rewards, states, dones, seq_len)
         else:
             stats = self._update_device(obs, actions, rewards, states, dones, seq_len)
@@ -453,8 +453,8 @@ class QMIXAgent:
 
     def _update_graphed(self, key, *inputs):
         """Replay the whole device part of update() (~900 launches at C3 sizes) as one CUDA graph; one
-        graph per batch shape, static input buffers.  Not used under data parallelism (the NCCL
-        all-reduce of the gradient bucket stays eager)."""
+        graph per batch shape, static input buffers.  Under data parallelism the NCCL all-reduce of the
+        gradient bucket is captured with it (every rank replays its graph once per update, in lock-step)."""
         g = self._graphs.get(key)
         if g is None:
             static = [t.clone() for t in inputs]

@@ -354,17 +354,27 @@ class SAC_GRU_Agent:
             q2n, _ = self.q2_target.forward(next_states, next_actions, q_hidden)
             y = ops.sac_q_target(rewards.reshape(-1).contiguous(), dones.reshape(-1).contiguous(),
                                  q1n.reshape(-1), q2n.reshape(-1), next_logp.reshape(-1), self.alpha, self.gamma)
-            # ---- critics, :193-207
+            # ---- critics, :193-207.  Same step order as the reference (Q1 step, Q2 step, actor step, temperature
+            # step); under data parallelism each bucket's all-reduce starts on the side stream as soon as its
+            # backward pass is done and the optimiser step that consumes it is issued as late as the data
+            # dependencies allow, so the collective overlaps the next network's forward / backward.
             q_losses = []
-            for qnet, opt in ((self.q1, self.q1_optimizer), (self.q2, self.q2_optimizer)):
-                q_cur, _ = qnet.forward(states, actions, q_hidden, save=True)
-                loss, dq = ops.mse_loss(q_cur.reshape(-1), y)
-                qnet.P.zero_grad()
-                qnet.backward(dq)
-                opt.step()
-                q_losses.append(loss)
+            q_cur, _ = self.q1.forward(states, actions, q_hidden, save=True)
+            loss, dq = ops.mse_loss(q_cur.reshape(-1), y)
+            self.q1.P.zero_grad()
+            self.q1.backward(dq)
+            self.q1_optimizer.reduce_async()
+            q_losses.append(loss)
+            q_cur, _ = self.q2.forward(states, actions, q_hidden, save=True)        # overlaps Q1's all-reduce
+            loss, dq = ops.mse_loss(q_cur.reshape(-1), y)
+            self.q2.P.zero_grad()
+            self.q2.backward(dq)
+            self.q2_optimizer.reduce_async()
+            q_losses.append(loss)
+            self.q1_optimizer.step()
             # ---- actor, :210-220
-            new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)
+            new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)   # overlaps Q2's
+            self.q2_optimizer.step()
             q1_new, _ = self.q1.forward(states, new_actions, q_hidden, save=True)
             q2_new, _ = self.q2.forward(states, new_actions, q_hidden, save=True)
             p_loss, d_logp, dq1, dq2 = ops.sac_policy_loss(logp.reshape(-1), q1_new.reshape(-1), q2_new.reshape(-1), self.alpha)
@@ -372,17 +382,21 @@ class SAC_GRU_Agent:
             ops.axpby(1.0, self.q2.backward(dq2, need_daction=True), 1.0, d_action)
             self.policy.P.zero_grad()
             self.policy.backward(d_action, d_logp)
-            self.policy_optimizer.step()
-            # ---- temperature, :223-231
+            self.policy_optimizer.reduce_async()
+            # ---- temperature, :223-231 (its 4-byte gradient rides along; both overlap the soft updates below)
             a_loss = None
             if self.auto_entropy_tuning:
                 a_loss, d_la = ops.sac_alpha_loss(logp.reshape(-1), self.log_alpha, float(self.target_entropy))
                 self._log_alpha_grad.copy_(d_la)
-                self.alpha_optimizer.step()
-                self.alpha = ops.exp_scalar(self.log_alpha)
+                self.alpha_optimizer.reduce_async()
             # ---- targets, :234-235
             soft_update(self.q1, self.q1_target, self.tau)
             soft_update(self.q2, self.q2_target, self.tau)
+            self.policy_optimizer.step()
+            if self.auto_entropy_tuning:
+                self.alpha_optimizer.step()
+                # in place: a CUDA graph that holds this update reads alpha from the same address on every replay
+                ops.exp_scalar(self.log_alpha, out=self.alpha)
             conv = (lambda t: float(t.item())) if sync_stats else (lambda t: t.reshape(()).detach())
             losses['q1'] = losses['q1'] + conv(q_losses[0])
             losses['q2'] = losses['q2'] + conv(q_losses[1])
@@ -436,7 +450,7 @@ class SAC_GRU_Agent:
                 warnings.warn(f"SAC checkpoint holds no {name}: Adam restarts from zero moments")
         if self.auto_entropy_tuning and 'log_alpha' in ck:
             self.log_alpha.copy_(ck['log_alpha'].detach().to(self.device))
-            self.alpha = ops.exp_scalar(self.log_alpha)
+            ops.exp_scalar(self.log_alpha, out=self.alpha)
             if isinstance(ck.get('alpha_optimizer_state_dict'), dict):
                 self.alpha_optimizer.load_state_dict(ck['alpha_optimizer_state_dict'])
         self.total_steps = ck['total_steps']

@@ -173,13 +173,12 @@ class SACRollout:
 
     # ---- CUDA graph: actor sampling + env step + replay push + one SAC update = one graph launch
     def capture(self, updates=1, warmup=2):
-        """Capture `step(); update(updates)` into a CUDA graph (single process: an NCCL all-reduce in
-        the optimiser steps is not captured here).  Needs a FULL replay ring (the sampling range is
-        fixed at capture) -- run at least capacity / num_envs eager steps first.  Gaussian and index
-        draws come from torch's default CUDA generator, which is graph-safe."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise RuntimeError("SACRollout.capture is single-process; run data-parallel training eagerly")
+        """Capture `step(); update(updates)` into a CUDA graph.  Under data parallelism the NCCL all-reduces of
+        the four gradient buckets are captured too (side-stream fork / join, policy/nn.py:Adam.reduce_async): every
+        rank replays its graph once per step, in lock-step, so the collectives match up.  Needs a FULL replay
+        ring (the sampling range is fixed at capture) -- run at least capacity / num_envs eager steps first (they
+        also create the NCCL communicator, which cannot happen during capture).  Gaussian and index draws come
+        from torch's default CUDA generator, which is graph-safe."""
         if len(self.replay) < self.replay.capacity:
             raise RuntimeError("fill the replay ring before capturing (sampling range is fixed in the graph)")
         dev = self.env.device

@@ -36,6 +36,11 @@ MAX_EPISODE_STEPS = 200   # training_pipeline.py:322
 DT = 0.25                 # env.py:80
 
 
+def epsilon_schedule(episode_num: int) -> float:
+    """training_pipeline.py:320: epsilon = max(0.01, 0.1 - episode / 5000)."""
+    return max(0.01, 0.1 - episode_num / 5000.0)
+
+
 class TrainingPipeline:
     def __init__(self, agent_type='qmix', num_servers=16, num_agents=4, trace_dir='data/trace',
                  checkpoint_dir='checkpoints', config=None, num_envs=32, device=None, verbose=True):
@@ -76,7 +81,8 @@ class TrainingPipeline:
                 out.append(tr)
         if not out:
             self._say("  Warning: No traces found, using synthetic Poisson")
-            speeds_sum = 1.5 * self.num_servers
+            speeds = self.config.get('server_speeds')
+            speeds_sum = 1.5 * self.num_servers if speeds is None else float(np.sum(speeds))
             for rate in self.config.get('rates', [100, 200, 500]):       # :143-145
                 mean_work = 0.8 * speeds_sum / rate
                 out.append(_traces.poisson_trace(rate, horizon, mean_work, rng=self._rng))
@@ -89,7 +95,11 @@ class TrainingPipeline:
                                 action_type='discrete' if self.agent_type == 'qmix' else 'continuous',
                                 action_dtype='uint8', max_steps=MAX_EPISODE_STEPS, device=self.device.index or 0,
                                 reward_metric=self.config.get('reward_metric', 'jain'))
-        env.set_speeds(np.where(np.arange(self.num_servers) % 2 == 0, 1.0, 2.0).astype(np.float32))
+        speeds = self.config.get('server_speeds')
+        if speeds is None:
+            speeds = np.where(np.arange(self.num_servers) % 2 == 0, 1.0, 2.0)
+        self.server_speeds = np.asarray(speeds, np.float32).reshape(self.num_servers)
+        env.set_speeds(self.server_speeds)
         return env
 
     def _init_agent(self):
@@ -133,7 +143,7 @@ class TrainingPipeline:
         Sa = S // A
         obs = self._load_round()
         ret = torch.zeros(E, dtype=torch.float64, device=self.device)
-        epsilon = max(0.01, 0.1 - episode_num / 5000.0) if explore else 0.0      # :320
+        epsilon = epsilon_schedule(episode_num) if explore else 0.0
         loss = None
         if self.agent_type == 'qmix':
             hid = None
@@ -166,7 +176,8 @@ class TrainingPipeline:
                         'states': [h_state[t, e] for t in range(T)],
                         'dones': [t == T - 1 for t in range(T)]})
                 if self.agent.episode_buffer.is_ready(self.agent.batch_size):
-                    out = self.agent.update()
+                    for _ in range(self.config.get('updates_per_round', 1)):
+                        out = self.agent.update()
                     loss = None if out is None else out['loss']
         else:
             hid = self.agent.policy.init_hidden(E)                                # [1, E, gru] zeros (:311)

@@ -133,6 +133,14 @@ class VecLoadBalanceEnv:
         self._steps_done = 0
         # pinned host buffers for the end-to-end path
         self._h_action = self._h_obs = self._h_reward = self._h_done = None
+        self._h_obs_valid = False
+        self.last_d2h_bytes = 0
+        import os as _os
+        try:
+            ncpu = len(_os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = _os.cpu_count() or 1
+        self.host_threads = max(1, min(16, ncpu))    # threads that apply step_host(obs="changed") records
 
     # ------------------------------------------------------------------ utils
     def _view(self, what, shape, dtype):
@@ -264,9 +272,13 @@ class VecLoadBalanceEnv:
         self._chunk_end = self._staged[0]
         self._kick_prefetch()
 
-    def gen_poisson(self, rate: float, mean_work: float, horizon: float, seed: int = 0):
-        """Synthetic Poisson arrivals generated on the device (training_pipeline.py:141-155)."""
-        check(self._L.mlb_gen_poisson(self._h, rate, mean_work, horizon, seed, self._stream()), self._h)
+    def gen_poisson(self, rate: float, mean_work: float, horizon: float, seed: int = 0, t_start: float = 0.0,
+                    window: int = 0):
+        """Synthetic Poisson arrivals generated on the device (training_pipeline.py:141-155) for simulated time
+        [t_start, horizon).  With t_start > 0 (between two steps of a running episode, t_start = steps done * dt) the
+        resident arrivals are replaced by the next window's: only one window lives in HBM at a time."""
+        check(self._L.mlb_gen_poisson_window(self._h, rate, mean_work, float(t_start), float(horizon), seed,
+                                             int(window), self._stream()), self._h)
 
     def get_arrivals(self, env: int, agent: int = 0):
         n = C.c_int64()
@@ -294,6 +306,7 @@ class VecLoadBalanceEnv:
                 raise ValueError("masked reset is not available while a trace stream is attached")
             self._restart_stream()
         check(self._L.mlb_reset(self._h, _nptr(m), self._stream()), self._h)
+        self._h_obs_valid = False                    # the host mirror of step_host(obs="changed") is stale
         if m is not None:
             torch.cuda.current_stream().synchronize()  # pageable mask must outlive the async copy
         if self.normalize_obs:
@@ -317,6 +330,7 @@ class VecLoadBalanceEnv:
         check(self._L.mlb_step(self._h, _dptr(a), _lib.DEVICE, None, None, None, _lib.DEVICE,
                                self._stream()), self._h)
         self._last_action = a  # keep alive until the kernel has consumed it
+        self._h_obs_valid = False
         if self.normalize_obs:
             return self._normalize_observation(self.obs), self.reward, self.done   # env.py:283-285
         return self.obs, self.reward, self.done
@@ -366,6 +380,7 @@ class VecLoadBalanceEnv:
         """Replay the captured step; returns (obs, reward, done) like step()."""
         self._graph.replay()
         self.graph_replays += 1
+        self._h_obs_valid = False
         return self.obs, self.reward, self.done
 
     def pinned_actions(self) -> "torch.Tensor":
@@ -373,17 +388,25 @@ class VecLoadBalanceEnv:
         skip the staging copy."""
         return torch.empty((self.num_envs, self.total_servers), dtype=self._adtype, pin_memory=True)
 
-    def step_host(self, action):
-        """End-to-end step with HOST buffers: H2D of the actions from pinned memory, the two
-        kernels, pinned D2H of obs / reward / done, then a stream synchronise.  With many envs the
-        library pipelines this in chunks of envs (copy of chunk c overlaps the kernels of chunk
-        c+1).  `action`: numpy array (staged through a pinned buffer) or a pinned torch tensor from
-        pinned_actions() (used in place).  Returns numpy views of the pinned output buffers."""
+    def step_host(self, action, obs: str = "full"):
+        """End-to-end step with HOST buffers: H2D of the actions from pinned memory, the env kernels, pinned D2H
+        of obs / reward / done, then a stream synchronise.  With many envs the library pipelines this in chunks of
+        envs (copy of chunk c overlaps the kernels of chunk c+1).  `action`: numpy array (staged through a pinned
+        buffer) or a pinned torch tensor from pinned_actions() (used in place).  Returns numpy views of the pinned
+        output buffers (the observation array is the same persistent buffer on every call).
+
+        obs="full": all E*S*11 floats cross PCIe every step.  obs="changed": only the n_flow_on column and the rows
+        in which a reservoir slot was written do (`mlb_step_changed`); host threads apply them to the persistent
+        array.  Same result bit for bit; `last_d2h_bytes` tells what moved.  Deep into an episode Algorithm R accepts
+        few samples and the difference is large; early on most rows change and the library falls back to block copies."""
+        if obs not in ("full", "changed"):
+            raise ValueError("obs must be 'full' or 'changed'")
         E, S = self.num_envs, self.total_servers
         if self._h_obs is None:
-            self._h_obs = torch.empty((E, S, 11), dtype=torch.float32, pin_memory=True)
+            self._h_obs = torch.zeros((E, S, 11), dtype=torch.float32).pin_memory()
             self._h_reward = torch.empty((E,), dtype=torch.float64, pin_memory=True)
             self._h_done = torch.empty((E,), dtype=torch.uint8, pin_memory=True)
+            self._h_obs_valid = False
         if isinstance(action, torch.Tensor) and action.is_pinned() and action.dtype == self._adtype \
                 and action.is_contiguous() and action.numel() == E * S:
             src = action
@@ -395,9 +418,18 @@ class VecLoadBalanceEnv:
         if self._trace is not None:
             self._advance_stream()
             self._steps_done += 1
-        check(self._L.mlb_step(self._h, _dptr(src), _lib.HOST, _dptr(self._h_obs),
-                               _dptr(self._h_reward), _dptr(self._h_done), _lib.HOST, self._stream()), self._h)
-        torch.cuda.current_stream().synchronize()
+        if obs == "changed" and self._h_obs_valid and not self.normalize_obs:
+            moved = C.c_int64()
+            check(self._L.mlb_step_changed(self._h, _dptr(src), _dptr(self._h_obs), _dptr(self._h_reward),
+                                           _dptr(self._h_done), self.host_threads, C.byref(moved), self._stream()), self._h)
+            self.last_d2h_bytes = int(moved.value)
+        else:
+            # also the key frame of the changed-rows mode: the host mirror is (re)built by one full copy
+            check(self._L.mlb_step(self._h, _dptr(src), _lib.HOST, _dptr(self._h_obs),
+                                   _dptr(self._h_reward), _dptr(self._h_done), _lib.HOST, self._stream()), self._h)
+            torch.cuda.current_stream(self.device).synchronize()
+            self.last_d2h_bytes = self.e2e_bytes[1]
+            self._h_obs_valid = True
         return self._h_obs.numpy(), self._h_reward.numpy(), self._h_done.numpy()
 
     @property

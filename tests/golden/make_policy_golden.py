@@ -210,6 +210,16 @@ def checkpoints():
     out["sac_upd3_eps_next"], out["sac_upd3_eps_new"] = e_next.numpy(), e_new.numpy()
     out["sac_upd3_losses"] = np.array([losses['q1'], losses['q2'], losses['policy'], losses['alpha']])
     out["sac_upd3_alpha"] = np.array([resumed.alpha.item()])
+    # Reference quirk (sac_agent.py:304-306): load() REBINDS self.log_alpha to the checkpoint tensor, so the
+    # temperature optimiser is left holding the orphaned initial parameter (which never receives a gradient again) and
+    # alpha stays frozen at its checkpoint value.  What a resume SHOULD give is what the never-reloaded agent gives on
+    # the same third update: recorded as the expected temperature.
+    out["sac_ckpt_log_alpha"] = np.array([float(torch.load(os.path.join(HERE, "ref_sac_ckpt.pt"))["log_alpha"].item())])
+    torch.manual_seed(203)
+    agent.update_parameters(1)
+    out["sac_upd3_log_alpha_cont"] = np.array([float(agent.log_alpha.item())])
+    for (k1, v1), (k2, v2) in zip(agent.policy.state_dict().items(), resumed.policy.state_dict().items()):
+        assert torch.equal(v1, v2), k1           # everything else resumes identically
     for pre, net in (("policy.", resumed.policy), ("q1.", resumed.q1), ("q2.", resumed.q2), ("q1t.", resumed.q1_target)):
         out.update(sd_np("sac_upd3." + pre, net.state_dict()))
     # ---- QMIX

@@ -73,3 +73,81 @@ def test_qmix_update_two_ranks_equals_global_batch():
         assert p.exitcode == 0
     assert np.array_equal(out[0][1], out[1][1])                     # ranks stay in lock-step, bit for bit
     np.testing.assert_allclose(out[0][1], want, rtol=2e-4, atol=2e-6)
+
+
+# ---- SAC (config C4's learner): four gradient buckets, all-reduces started on the side stream (Adam.reduce_async) and
+# ---- captured in a CUDA graph together with the update
+def _sac_setup(device, B):
+    from marllb_b200.policy import SAC_GRU_Agent
+    torch.manual_seed(11)
+    agent = SAC_GRU_Agent(state_dim=44, action_dim=4, hidden_dim=64, gru_dim=32, batch_size=B, device=device)
+    rng = np.random.RandomState(4)
+    f = lambda a: torch.as_tensor(a, dtype=torch.float32)
+    batch = (f(rng.randn(B, 44)), f(np.tanh(rng.randn(B, 4))), f(rng.rand(B, 1)), f(rng.randn(B, 44)),
+             f((rng.rand(B, 1) < 0.2).astype(np.float32)), f(rng.randn(1, B, 32) * 0.2))
+    eps = (f(rng.randn(B, 4)), f(rng.randn(B, 4)))
+    return agent, batch, eps
+
+
+def _sac_params(agent):
+    return torch.cat([agent.policy_optimizer.bucket.flat_p, agent.q1_optimizer.bucket.flat_p,
+                      agent.q2_optimizer.bucket.flat_p, agent.log_alpha.reshape(-1)]).detach().cpu().numpy()
+
+
+def _sac_worker(rank, world, port, q, graphed):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    B = 16
+    agent, batch, eps = _sac_setup(dev, B)
+    half = B // world
+    sl = slice(rank * half, (rank + 1) * half)
+    mine = tuple((t[:, sl] if t.dim() == 3 else t[sl]).contiguous().to(dev) for t in batch)
+    e_next, e_new = eps[0][sl].contiguous().to(dev), eps[1][sl].contiguous().to(dev)
+    upd = lambda: agent.update_parameters(1, batch=mine, eps_next=e_next, eps_new=e_new, sync_stats=False)
+    if graphed:
+        upd(); upd()                                           # eager (creates the NCCL communicator)
+        side = torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            upd()                                              # captured, not executed: all-reduces included
+        graph.replay(); graph.replay()
+    else:
+        for _ in range(4):
+            upd()
+    torch.cuda.synchronize(dev)
+    q.put((rank, _sac_params(agent)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("graphed", [False, True])
+def test_sac_update_two_ranks_equals_global_batch(graphed):
+    """Four SAC updates with the batch split over two ranks (averaging all-reduce of each bucket on the side stream;
+    graphed=True: two of them replayed from a CUDA graph that holds the NCCL calls) = four updates with the whole
+    batch on one rank; the two ranks end bit-identical."""
+    B = 16
+    ref, batch, eps = _sac_setup(torch.device("cuda", 0), B)
+    dev = torch.device("cuda", 0)
+    full = tuple(t.to(dev) for t in batch)
+    for _ in range(4):
+        ref.update_parameters(1, batch=full, eps_next=eps[0].to(dev), eps_new=eps[1].to(dev), sync_stats=False)
+    want = _sac_params(ref)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000) + (1 if graphed else 0)
+    procs = [ctx.Process(target=_sac_worker, args=(r, 2, port, q, graphed)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=300) for _ in procs), key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(out[0][1], out[1][1])                     # replicas in lock-step, bit for bit
+    np.testing.assert_allclose(out[0][1], want, rtol=3e-4, atol=3e-6)
