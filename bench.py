@@ -227,11 +227,11 @@ def run_reference(args):
     }))
 
 
-def workload_config(args, wl, world=None):
+def workload_config(args, wl, world=None, name=None):
     pol = {"qmix": "QMIX epsilon-greedy action selection (eps=0.05) fused with the env step",
            "sac": "SAC-GRU actor sampling + env step + one SAC update (batch 256) per step",
            None: "random policy"}[wl.get("policy")]
-    return {"workload": f"{args.workload}: {wl['envs']} envs/GPU x {wl['agents']} LB agent x {wl['servers']} servers, "
+    return {"workload": f"{name or args.workload}: {wl['envs']} envs/GPU x {wl['agents']} LB agent x {wl['servers']} servers, "
                         f"K={wl['K']}-slot reservoirs, Poisson {wl['rate']:.0f} flows/s/agent, rho={RHO}, {pol}, SED",
             "envs_per_gpu": wl["envs"], "agents": wl["agents"], "servers_per_agent": wl["servers"],
             "reservoir_k": wl["K"], "flows_per_s_per_agent": wl["rate"], "dt_s": DT,
@@ -325,6 +325,9 @@ def measure(args, name, world, rank, local, main):
             else:
                 sac.step()
                 sac.update(1, sac_gen)
+        elif rollout is None and graphed:
+            env.graph_action.copy_(pool[k % 8])
+            env.step_graph()
         elif rollout is None:
             env.step(pool[k % 8])
         elif graphed:
@@ -354,6 +357,16 @@ def measure(args, name, world, rank, local, main):
         prof_eager = env.profile_end()
         rollout.capture(0.05)
         graphed = True
+    env_graph = False
+    if not main and not has_policy and not args.no_graph and E * A < 32768:
+        # small batches are launch-gap bound (c2: 4096 warps = 0.7 of a wave): per-kernel times from a short eager
+        # pass, then the four launches of a step replayed as one CUDA graph
+        env.profile_begin(10)
+        for k in range(10):
+            do_step(k)
+        prof_eager = env.profile_end()
+        env.capture()
+        env_graph = graphed = True
     if sac is not None and not args.no_graph:
         n_fill = 0
         while len(sac.replay) < sac.replay.capacity:      # the graph samples from a full ring
@@ -406,7 +419,7 @@ def measure(args, name, world, rank, local, main):
         ev_ms, ft_ms, prof_steps = prof_eager
         pair_ms = None
     if graphed:
-        launches = (rollout if rollout is not None else sac).graph_launches * steps
+        launches = (env if env_graph else (rollout if rollout is not None else sac)).graph_launches * steps
     value = world * E * A * steps / (ms_max * 1e-3)
 
     # C4: the replicas must stay in lock-step (identical initial weights + identical averaged gradients): checksum of
@@ -670,7 +683,7 @@ def run_ours(args):
         for name in ("c2", "c3", "c4"):
             r = measure(args, name, world, rank, local, main=False)
             if rank == 0:
-                r["config"] = workload_config(args, WORKLOADS[name], world)["workload"]
+                r["config"] = workload_config(args, WORKLOADS[name], world, name)["workload"]
                 configs[name] = r
     if rank == 0:
         out = {
