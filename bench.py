@@ -451,7 +451,7 @@ def measure(args, name, world, rank, local, main):
     if param_spread is not None:
         res["param_checksum_spread_over_ranks"] = param_spread
     if not main:
-        env.close()
+        _release(env, rollout, sac)
         del env, rollout, sac, sac_agent, pool
         torch.cuda.empty_cache()
         return res if rank == 0 else None
@@ -615,10 +615,26 @@ def measure(args, name, world, rank, local, main):
                                          "reservoir slot was written, applied by host threads to the persistent host "
                                          "observation array (bit-equal result)"} if e2e_changed else None)},
         "clocks": clk})
-    env.close()
+    _release(env, rollout, sac)
     del env, pool
     torch.cuda.empty_cache()
     return res
+
+
+def _release(env, rollout, sac):
+    """CUDA graphs that hold NCCL kernels must be gone before the process group is torn down (a communicator destroyed
+    under a live graph hangs at exit): reset every captured graph, then free the env."""
+    import gc
+    import torch
+    torch.cuda.synchronize()
+    for obj in (env, rollout, sac):
+        g = getattr(obj, "_graph", None)
+        if g is not None:
+            g.reset()
+            obj._graph = None
+    env.close()
+    gc.collect()
+    torch.cuda.synchronize()
 
 
 def cpu_legs(args, wl):
@@ -706,9 +722,17 @@ def run_ours(args):
                 os.sched_setaffinity(0, prev_affinity)       # the CPU baseline uses every host core
             out["cpu_baseline"] = cpu_legs(args, wl)
         print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
+        # dead-man switch: the JSON line is out; a teardown that does not finish (seen with NCCL kernels captured in CUDA
+        # graphs) must not keep the launcher waiting
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+        t.cancel()
 
 
 def main():

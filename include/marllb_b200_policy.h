@@ -48,6 +48,23 @@ int mlb_linear_tc_supported(int32_t M, int32_t N, int32_t K, int64_t lda, int64_
 int mlb_linear_tc(const float *X, int64_t lda, const float *W, int64_t ldw, const float *bias,
                   float *C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
 
+/*
+ * The general product of the UPDATE path on the tensor cores (tcgen05, 3xTF32; csrc/mlb_gemm_tc.cu):
+ *   C[m*ldc + n] = act( beta * C + sum_k A[m*a_rs + k*a_cs] * B[k*b_rs + n*b_cs] + bias[n] )
+ * with each operand either contraction-contiguous (a_cs == 1 / b_rs == 1) or contiguous along its other index
+ * (a_rs == 1 / b_cs == 1): nn.Linear forward, its input gradient dx = dy W and its weight gradient dW = dy^T x
+ * (autograd of sac_agent.py:197-231, qmix_agent.py:275-285).  Few-tile / long-K shapes are split over K (partial tiles
+ * to a workspace, summed in split order: deterministic).  The non-unit strides and ldc must be multiples of 4, N a
+ * multiple of 4 and >= 32, K >= 32, pointers 16-byte aligned: mlb_gemm_tc_supported tells; mlb_gemm routes supported
+ * single-matrix calls above a size threshold here by itself.  Returns MLB_ESTATE / MLB_ENOMEM (nothing launched) when
+ * a tensor map or the workspace cannot be had (e.g. workspace growth during stream capture).
+ */
+int mlb_gemm_tc_supported(const float *A, int64_t a_rs, int64_t a_cs, const float *B, int64_t b_rs, int64_t b_cs,
+                          const float *C, int64_t ldc, int32_t M, int32_t N, int32_t K);
+int mlb_gemm_tc(const float *A, int64_t a_rs, int64_t a_cs, const float *B, int64_t b_rs, int64_t b_cs, float *C,
+                int64_t ldc, const float *bias, int32_t M, int32_t N, int32_t K, float beta, int32_t act,
+                void *stream);
+
 /* nn.GRU single step, gate part (torch gate order r,z,n):
  *   gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (computed by mlb_gemm), both [M][3H];
  *   r = sigmoid(gi_r+gh_r), z = sigmoid(gi_z+gh_z), n = tanh(gi_n + r*gh_n), h' = (1-z)*n + z*h.
@@ -173,6 +190,21 @@ int mlb_reward_normalize(const float *reward, float *out, float scale, int32_t B
 /* discrete SAC critic target (sac_gru_discrete.py:316-319): y = r + gamma*(min(q1n,q2n) - alpha*logp_next) */
 int mlb_dsac_q_target(const float *reward, const float *q1n, const float *q2n, const float *logp_next,
                       const float *alpha, float gamma, float *y, int32_t M, void *stream);
+
+/* Device-resident replay ring for the batched rollout (ReplayBuffer.push / sample, problem-04-sac-gru/src/
+ * replay_buffer.py:35-94, keeps one transition per Python call in a host deque).  Ring tensors: r_state /
+ * r_next_state [capacity][state_dim], r_action [capacity][action_dim], r_hidden [capacity][hidden_dim], r_reward /
+ * r_done [capacity] float.  mlb_replay_push writes the n transitions of one env step to rows (pos + e) % capacity and
+ * advances the device-held write position (so a CUDA graph replay lands in the right place); mlb_replay_gather copies
+ * the rows idx[0..batch) into contiguous batch tensors (uniform indices drawn by the caller). */
+int mlb_replay_push(const float *state, const float *action, const double *reward, const float *next_state,
+                    const uint8_t *done, const float *hidden, float *r_state, float *r_action, float *r_reward,
+                    float *r_next_state, float *r_done, float *r_hidden, int64_t *pos_dev, int32_t n,
+                    int32_t capacity, int32_t state_dim, int32_t action_dim, int32_t hidden_dim, void *stream);
+int mlb_replay_gather(const float *r_state, const float *r_action, const float *r_reward, const float *r_next_state,
+                      const float *r_done, const float *r_hidden, const int64_t *idx, float *state, float *action,
+                      float *reward, float *next_state, float *done, float *hidden, int32_t batch,
+                      int32_t state_dim, int32_t action_dim, int32_t hidden_dim, void *stream);
 
 #ifdef __cplusplus
 }

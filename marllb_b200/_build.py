@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmarllb_b200.so")
-SOURCES = ["mlb_api.cu", "mlb_ops.cu", "mlb_policy.cu", "mlb_linear_tc.cu"]
+SOURCES = ["mlb_api.cu", "mlb_ops.cu", "mlb_policy.cu", "mlb_linear_tc.cu", "mlb_gemm_tc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

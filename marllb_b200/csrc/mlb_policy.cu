@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/marllb_b200.h"
 #include "../../include/marllb_b200_policy.h"
@@ -650,6 +651,52 @@ __global__ void dsac_q_target_kernel(const float* __restrict__ r, const float* _
     if (i < M) y[i] = r[i] + gamma * (fminf(q1n[i], q2n[i]) - alpha[0] * lp[i]);
 }
 
+// ---- device-resident replay ring (rollout.DeviceReplay; reference: ReplayBuffer.push / sample,
+// problem-04-sac-gru/src/replay_buffer.py:35-94, one transition per Python call into a host deque).
+struct ReplayPtrs {
+    float* state; float* action; float* next_state; float* hidden; float* reward; float* done;
+};
+__device__ __forceinline__ void replay_copy_row(float* dst, const float* src, int n) {
+    if ((n & 3) == 0) {
+        for (int i = threadIdx.x; i < n / 4; i += blockDim.x)
+            reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+// E transitions -> ring rows (pos + e) % capacity; one block per transition
+__global__ void replay_push_kernel(const float* __restrict__ state, const float* __restrict__ action,
+                                   const double* __restrict__ reward, const float* __restrict__ next_state,
+                                   const uint8_t* __restrict__ done, const float* __restrict__ hidden, ReplayPtrs r,
+                                   const int64_t* __restrict__ pos, int capacity, int sd, int ad, int hd) {
+    const int e = blockIdx.x;
+    const int64_t row = (*pos + e) % capacity;
+    replay_copy_row(r.state + row * sd, state + (int64_t)e * sd, sd);
+    replay_copy_row(r.next_state + row * sd, next_state + (int64_t)e * sd, sd);
+    replay_copy_row(r.action + row * ad, action + (int64_t)e * ad, ad);
+    replay_copy_row(r.hidden + row * hd, hidden + (int64_t)e * hd, hd);
+    if (threadIdx.x == 0) {
+        r.reward[row] = (float)reward[e];
+        r.done[row] = done[e] ? 1.f : 0.f;
+    }
+}
+__global__ void replay_advance_kernel(int64_t* pos, int n, int capacity) { *pos = (*pos + n) % capacity; }
+// batch rows idx[b] of the ring -> contiguous batch tensors
+__global__ void replay_gather_kernel(ReplayPtrs r, const int64_t* __restrict__ idx, float* __restrict__ state,
+                                     float* __restrict__ action, float* __restrict__ reward, float* __restrict__ next_state,
+                                     float* __restrict__ done, float* __restrict__ hidden, int sd, int ad, int hd) {
+    const int b = blockIdx.x;
+    const int64_t row = idx[b];
+    replay_copy_row(state + (int64_t)b * sd, r.state + row * sd, sd);
+    replay_copy_row(next_state + (int64_t)b * sd, r.next_state + row * sd, sd);
+    replay_copy_row(action + (int64_t)b * ad, r.action + row * ad, ad);
+    replay_copy_row(hidden + (int64_t)b * hd, r.hidden + row * hd, hd);
+    if (threadIdx.x == 0) {
+        reward[b] = r.reward[row];
+        done[b] = r.done[row];
+    }
+}
+
 extern "C" {
 
 int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_bs,
@@ -658,6 +705,19 @@ int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const flo
              void* stream) {
     if (!A || !B || !C || M < 0 || N < 0 || K < 0 || batch < 1) return MLB_EINVAL;
     if (M == 0 || N == 0) return MLB_OK;
+    // single products big enough to fill tensor-core tiles go to the tcgen05 kernel (csrc/mlb_gemm_tc.cu); MLB_GEMM_TC_MIN
+    // (multiply-adds, default 2^21; 0 disables) is an A/B knob
+    {
+        static const int64_t tc_min = [] {
+            const char* e = getenv("MLB_GEMM_TC_MIN");
+            return e ? (int64_t)atoll(e) : (int64_t)1 << 21;
+        }();
+        if (batch == 1 && tc_min > 0 && (int64_t)M * N * K >= tc_min &&
+            mlb_gemm_tc_supported(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K)) {
+            const int rc = mlb_gemm_tc(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, beta, act, stream);
+            if (rc != MLB_ESTATE && rc != MLB_ENOMEM) return rc;   // those two: nothing was launched, use the FFMA kernel
+        }
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
     // few output tiles and a long reduction: split K over more thread blocks (workspace per device, grown
     // outside stream capture only)
@@ -964,6 +1024,36 @@ int mlb_dsac_q_target(const float* reward, const float* q1n, const float* q2n, c
     if (!reward || !q1n || !q2n || !logp_next || !alpha || !y) return MLB_EINVAL;
     if (M == 0) return MLB_OK;
     dsac_q_target_kernel<<<nblk(M, 256), 256, 0, (cudaStream_t)stream>>>(reward, q1n, q2n, logp_next, alpha, gamma, y, M);
+    return ok();
+}
+
+int mlb_replay_push(const float* state, const float* action, const double* reward, const float* next_state,
+                    const uint8_t* done, const float* hidden, float* r_state, float* r_action, float* r_reward,
+                    float* r_next_state, float* r_done, float* r_hidden, int64_t* pos_dev, int32_t n, int32_t capacity,
+                    int32_t state_dim, int32_t action_dim, int32_t hidden_dim, void* stream) {
+    if (!state || !action || !reward || !next_state || !done || !hidden || !r_state || !r_action || !r_reward ||
+        !r_next_state || !r_done || !r_hidden || !pos_dev || n < 0 || n > capacity)
+        return MLB_EINVAL;
+    if (n == 0) return MLB_OK;
+    ReplayPtrs r{r_state, r_action, r_next_state, r_hidden, r_reward, r_done};
+    replay_push_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(state, action, reward, next_state, done, hidden, r, pos_dev,
+                                                          capacity, state_dim, action_dim, hidden_dim);
+    replay_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(pos_dev, n, capacity);
+    return ok();
+}
+
+int mlb_replay_gather(const float* r_state, const float* r_action, const float* r_reward, const float* r_next_state,
+                      const float* r_done, const float* r_hidden, const int64_t* idx, float* state, float* action,
+                      float* reward, float* next_state, float* done, float* hidden, int32_t batch, int32_t state_dim,
+                      int32_t action_dim, int32_t hidden_dim, void* stream) {
+    if (!r_state || !r_action || !r_reward || !r_next_state || !r_done || !r_hidden || !idx || !state || !action ||
+        !reward || !next_state || !done || !hidden || batch < 0)
+        return MLB_EINVAL;
+    if (batch == 0) return MLB_OK;
+    ReplayPtrs r{const_cast<float*>(r_state), const_cast<float*>(r_action), const_cast<float*>(r_next_state),
+                 const_cast<float*>(r_hidden), const_cast<float*>(r_reward), const_cast<float*>(r_done)};
+    replay_gather_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(r, idx, state, action, reward, next_state, done, hidden,
+                                                                state_dim, action_dim, hidden_dim);
     return ok();
 }
 

@@ -23,6 +23,8 @@ def _L():
         sig = {
             "mlb_gemm": [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, vp, i64, i32, i32, i32, i32, f32, i32, vp],
             "mlb_linear_tc_supported": [i32, i32, i32, i64, i64, i64],
+            "mlb_gemm_tc_supported": [vp, i64, i64, vp, i64, i64, vp, i64, i32, i32, i32],
+            "mlb_gemm_tc": [vp, i64, i64, vp, i64, i64, vp, i64, vp, i32, i32, i32, f32, i32, vp],
             "mlb_linear_tc": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp],
             "mlb_gru_gates_forward": [vp, vp, vp, vp, vp, i32, i32, vp],
             "mlb_gru_gates_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
@@ -59,6 +61,8 @@ def _L():
             "mlb_weighted_sum_backward": [vp, vp, vp, vp, vp, i32, i32, vp],
             "mlb_reward_normalize": [vp, vp, f32, i32, i32, vp],
             "mlb_dsac_q_target": [vp, vp, vp, vp, vp, f32, vp, i32, vp],
+            "mlb_replay_push": [vp] * 13 + [i32] * 5 + [vp],
+            "mlb_replay_gather": [vp] * 13 + [i32] * 4 + [vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -67,7 +71,7 @@ def _L():
     return L
 
 
-POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_gru_gates_forward", "mlb_gru_gates_backward", "mlb_relu_backward",
+POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_gemm_tc_supported", "mlb_gemm_tc", "mlb_gru_gates_forward", "mlb_gru_gates_backward", "mlb_relu_backward",
                   "mlb_abs_backward", "mlb_colsum", "mlb_axpby", "mlb_sumsq", "mlb_scale", "mlb_adam", "mlb_adam_dev",
                   "mlb_egreedy_select", "mlb_onehot_action", "mlb_row_max", "mlb_mixer_forward", "mlb_mixer_backward",
                   "mlb_tanh_gaussian_forward", "mlb_tanh_gaussian_backward", "mlb_abs_forward",
@@ -75,7 +79,8 @@ POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_g
                   "mlb_sac_alpha_loss", "mlb_exp_scalar",
                   "mlb_softmax_forward", "mlb_softmax_backward", "mlb_concat_onehot", "mlb_categorical",
                   "mlb_logprob_backward", "mlb_scatter_class", "mlb_td_lambda_targets", "mlb_reward_normalize",
-                  "mlb_dsac_q_target", "mlb_weighted_sum_forward", "mlb_weighted_sum_backward"]
+                  "mlb_dsac_q_target", "mlb_weighted_sum_forward", "mlb_weighted_sum_backward",
+                  "mlb_replay_push", "mlb_replay_gather"]
 
 
 def _p(t):
@@ -132,6 +137,21 @@ def linear(x, W, b=None, act=ACT_NONE, out=None):
                         _p(W), N * K if (batched and W.dim() == 3) else 0, 1, K,
                         _p(out), M * N, N, _p(b), N if (b is not None and b.dim() == 2) else 0,
                         M, N, K, G, 0.0, act, _st()))
+    return out
+
+
+def gemm_tc(A, B, out=None, bias=None, beta=0.0, act=ACT_NONE, trans_a=False, trans_b=False):
+    """C = act(beta * C + op(A) op(B) + bias) on the tensor cores (mlb_gemm_tc; tests and benchmarks call it directly,
+    the layers reach it through mlb_gemm's own dispatch).  A [M,K] (or [K,M] with trans_a), B [K,N] (or [N,K] with
+    trans_b = the nn.Linear weight layout), both contiguous."""
+    _chk(A), _chk(B)
+    M, K = (A.shape[1], A.shape[0]) if trans_a else A.shape
+    N = B.shape[0] if trans_b else B.shape[1]
+    if out is None:
+        out = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    a_rs, a_cs = (1, M) if trans_a else (K, 1)
+    b_rs, b_cs = (1, K) if trans_b else (N, 1)
+    check(_L().mlb_gemm_tc(_p(A), a_rs, a_cs, _p(B), b_rs, b_cs, _p(out), out.stride(0), _p(bias), M, N, K, beta, act, _st()))
     return out
 
 
@@ -246,6 +266,31 @@ def onehot_action(action, servers_per_agent, hot=2, cold=0, out=None):
     if out is None:
         out = torch.empty((action.shape[0], action.shape[1] * servers_per_agent), dtype=torch.uint8, device=action.device)
     check(_L().mlb_onehot_action(_p(action), M, servers_per_agent, 1, hot, cold, _p(out), _st()))
+    return out
+
+
+def replay_push(ring, pos_dev, state, action, reward, next_state, done, hidden):
+    """ring = (state, action, reward, next_state, done, hidden) ring tensors; one launch (+ the position update)."""
+    r_state, r_action, r_reward, r_next, r_done, r_hidden = ring
+    n = state.shape[0]
+    assert reward.dtype == torch.float64 and done.dtype == torch.uint8 and pos_dev.dtype == torch.int64
+    for t in (state, action, next_state, hidden):
+        _chk(t)
+    check(_L().mlb_replay_push(_p(state), _p(action), _p(reward), _p(next_state), _p(done), _p(hidden), _p(r_state),
+                               _p(r_action), _p(r_reward), _p(r_next), _p(r_done), _p(r_hidden), _p(pos_dev), n,
+                               r_state.shape[0], r_state.shape[1], r_action.shape[1], r_hidden.shape[1], _st()))
+
+
+def replay_gather(ring, idx):
+    r_state, r_action, r_reward, r_next, r_done, r_hidden = ring
+    B = idx.numel()
+    f = dict(dtype=torch.float32, device=r_state.device)
+    out = (torch.empty((B, r_state.shape[1]), **f), torch.empty((B, r_action.shape[1]), **f), torch.empty((B, 1), **f),
+           torch.empty((B, r_state.shape[1]), **f), torch.empty((B, 1), **f), torch.empty((B, r_hidden.shape[1]), **f))
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    check(_L().mlb_replay_gather(_p(r_state), _p(r_action), _p(r_reward), _p(r_next), _p(r_done), _p(r_hidden), _p(idx),
+                                 _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _p(out[4]), _p(out[5]), B,
+                                 r_state.shape[1], r_action.shape[1], r_hidden.shape[1], _st()))
     return out
 
 

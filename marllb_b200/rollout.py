@@ -105,18 +105,20 @@ class DeviceReplay:
         self.hidden = torch.empty((capacity, gru_dim), **f)
 
     def push_batch(self, state, action, reward, next_state, done, hidden):
+        """state / next_state [n, state_dim], action [n, action_dim], hidden [n, gru] float32; reward [n] float64 and
+        done [n] uint8 as the env returns them.  One kernel writes the n rows at the DEVICE-held position (a captured
+        push lands in the right place on every replay), a second one advances it."""
         n = state.shape[0]
         if n > self.capacity:
             raise ValueError("batch larger than the replay capacity")
-        # the slot indices come from the device-side position so that a captured push lands in the
-        # right place on every replay
-        idx = (self._pos_dev + torch.arange(n, device=self.state.device)) % self.capacity
-        for dst, src in ((self.state, state), (self.action, action), (self.reward, reward.reshape(n, 1).float()),
-                         (self.next_state, next_state), (self.done, done.reshape(n, 1).float()), (self.hidden, hidden)):
-            dst.index_copy_(0, idx, src)
-        self._pos_dev.add_(n).remainder_(self.capacity)
+        ops.replay_push(self._ring(), self._pos_dev, state.contiguous(), action.contiguous(),
+                        reward.reshape(n).to(torch.float64), next_state.contiguous(),
+                        done.reshape(n).to(torch.uint8), hidden.contiguous())
         self.pos = (self.pos + n) % self.capacity      # host mirror (not advanced by graph replays)
         self.size = min(self.size + n, self.capacity)
+
+    def _ring(self):
+        return (self.state, self.action, self.reward, self.next_state, self.done, self.hidden)
 
     def __len__(self):
         return self.size
@@ -124,9 +126,8 @@ class DeviceReplay:
     def sample(self, batch_size, generator=None):
         """-> the tuple SAC_GRU_Agent.update_parameters(batch=...) takes (hidden as [1, B, gru])."""
         idx = torch.randint(0, self.size, (batch_size,), device=self.state.device, generator=generator)
-        g = lambda t: t.index_select(0, idx)
-        return (g(self.state), g(self.action), g(self.reward), g(self.next_state), g(self.done),
-                g(self.hidden).unsqueeze(0))
+        s, a, r, ns, d, h = ops.replay_gather(self._ring(), idx)
+        return (s, a, r, ns, d, h.unsqueeze(0))
 
 
 class SACRollout:

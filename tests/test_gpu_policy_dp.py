@@ -117,13 +117,19 @@ def _sac_worker(rank, world, port, q, graphed):
         with torch.cuda.graph(graph):
             upd()                                              # captured, not executed: all-reduces included
         graph.replay(); graph.replay()
+        torch.cuda.synchronize(dev)
+        graph.reset()                      # a graph holding NCCL kernels must be gone before the communicator is
+        del graph
     else:
         for _ in range(4):
             upd()
     torch.cuda.synchronize(dev)
     q.put((rank, _sac_params(agent)))
+    import threading
+    threading.Timer(30.0, lambda: os._exit(0)).start()      # teardown must not outlive the test
     dist.barrier()
     dist.destroy_process_group()
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
