@@ -16,14 +16,17 @@
 // Like mlb_linear_tc.cu the accumulator in tensor memory holds two k-blocks at a time (the tensor core rounds its fp32
 // accumulator toward zero on every instruction) and is drained into per-thread registers with round-to-nearest adds.
 //
-// Split-K: grid.z CTAs share one output tile's k-blocks; raw partial tiles go to a workspace ([split][M padded to
-// 128][N], written by TMA) and gemm_tc_reduce_kernel adds them in split order (deterministic) with beta / bias /
-// activation.  beta != 0 (dW accumulation) always takes that route, so the main kernel never reads C.
+// Split-K (reductions of 4 k-blocks and more on few tiles): grid.z CTAs share one output tile's k-blocks; raw partial
+// tiles go to a workspace ([split][M padded to 128][N]) and gemm_tc_reduce_kernel adds them in split order
+// (deterministic) with beta / bias / activation, spread over as many SMs as the output has 256-element blocks.  (Tried:
+// the last CTA of a tile, found by a ticket counter, adding the partial tiles itself -- one launch less, but its 256
+// threads need 16 rounds of L2 latency for a 128 x 128 tile: 1.82 ms per SAC update instead of 1.14.)  Unsplit tiles
+// apply beta * C (dW accumulation), bias and the activation in their own epilogue.
 //
 // One CTA = one 128 x NT tile (NT = 64 or 128) over a range of k-blocks, 10 warps:
 //   warp 0      TMA producer (raw ring, 2 stages)
 //   warp 1      tensor memory allocation, tcgen05.mma issue (one elected lane), tcgen05.commit
-//   warps 2..9  raw tile -> hi / lo operand tiles (2 stages), TMEM drain, epilogue (shared memory + TMA store)
+//   warps 2..9  raw tile -> hi / lo operand tiles (2 stages), TMEM drain, epilogue (shared memory -> coalesced stores)
 #include <algorithm>
 
 #include "../../include/marllb_b200.h"
@@ -41,7 +44,11 @@ constexpr int WORK_THREADS = 32 * WORKER_WARPS;    // 256
 constexpr int THREADS = 64 + WORK_THREADS;
 
 struct GtParams {
-    const float* bias;     // only read when the tile is final (splits == 1)
+    float* C;              // final output (splits == 1) ...
+    float* ws;             // ... or the workspace of raw partial tiles [split][m_pad][N] (splits > 1)
+    const float* bias;     // only read when the tile is final
+    int64_t ldc;
+    float beta;
     int M, N, K, act;
     int kb_per_split;      // k-blocks per CTA along grid.z
     int m_pad;             // rows per split in the workspace (splits > 1), else 0
@@ -92,7 +99,7 @@ __device__ __forceinline__ void split_tile(const unsigned char* raw, unsigned ch
 template <int NT, bool AT, bool BT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_c, const GtParams p) {
+               const GtParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     constexpr uint32_t a_bytes = TILE_M * TILE_K * 4;          // 16 KB
@@ -240,41 +247,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (i > 0 && i % DRAIN_KB == 0) drain(i / DRAIN_KB - 1);
         }
         drain((nkb - 1) / DRAIN_KB);
-        // ---- epilogue: stage the tile in shared memory (the operand ring is free: the last drain saw every MMA
-        // complete) as NT/32 sub-tiles of [128 rows x 128 bytes], 128-byte swizzle, and let TMA write it (coalesced,
-        // clipped at the matrix edge).  A final tile (splits == 1) gets bias + activation here; partial tiles go out raw.
+        // ---- epilogue: a thread owns an accumulator ROW, so direct stores would put one 32-byte sector per lane and
+        // instruction on the wire.  The tile is staged in shared memory instead (the operand ring is free: the last
+        // drain saw every MMA complete) as NT/32 sub-tiles of [128 rows x 128 bytes] with the 128-byte XOR swizzle
+        // (conflict-free float4 writes), then all worker threads write it out row-contiguously (8 lanes = one 128-byte
+        // line).  A final tile gets beta * C, bias and the activation on the way; partial tiles go out raw.
         const int r = q * 32 + lane;
         const int c0 = half * NC;
-        const int n_valid = min(NT, p.N - n0);
-        const bool fin = p.m_pad == 0;
 #pragma unroll
         for (int c = 0; c < NC; c += 4) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (fin && p.bias) {
-                if (c0 + c + 0 < n_valid) bv.x = __ldg(p.bias + n0 + c0 + c + 0);
-                if (c0 + c + 1 < n_valid) bv.y = __ldg(p.bias + n0 + c0 + c + 1);
-                if (c0 + c + 2 < n_valid) bv.z = __ldg(p.bias + n0 + c0 + c + 2);
-                if (c0 + c + 3 < n_valid) bv.w = __ldg(p.bias + n0 + c0 + c + 3);
-            }
-            float4 o;
-            o.x = tot[c + 0] + bv.x; o.y = tot[c + 1] + bv.y; o.z = tot[c + 2] + bv.z; o.w = tot[c + 3] + bv.w;
-            if (fin) { o.x = gt_act(o.x, p.act); o.y = gt_act(o.y, p.act); o.z = gt_act(o.z, p.act); o.w = gt_act(o.w, p.act); }
             const int col = c0 + c, sub = col >> 5, chunk = (col & 31) >> 2;
-            *reinterpret_cast<float4*>(op_base + (size_t)sub * (TILE_M * 128) + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
+            *reinterpret_cast<float4*>(op_base + (size_t)sub * (TILE_M * 128) + r * 128 + ((chunk ^ (r & 7)) << 4)) =
+                make_float4(tot[c + 0], tot[c + 1], tot[c + 2], tot[c + 3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(WORK_THREADS) : "memory");
-        if (threadIdx.x == 64) {
-            const int row0 = (fin ? 0 : (int)blockIdx.z * p.m_pad) + m0;
-#pragma unroll
-            for (int sub = 0; sub < NT / 32; sub++) {
-                if (n0 + sub * 32 < p.N)
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(&map_c), "r"(smem_u32(op_base + (size_t)sub * (TILE_M * 128))), "r"(n0 + sub * 32), "r"(row0)
-                                 : "memory");
+        const bool fin = p.m_pad == 0;
+        float* out = fin ? p.C : p.ws + (size_t)blockIdx.z * p.m_pad * p.N;
+        const int64_t ld_out = fin ? p.ldc : (int64_t)p.N;
+        auto finish = [&](float4 v, int gm, int gn) {      // beta * C + bias, activation, store to C
+            float* dst = p.C + (int64_t)gm * p.ldc + gn;
+            if (p.bias) {
+                v.x += __ldg(p.bias + gn); v.y += __ldg(p.bias + gn + 1);
+                v.z += __ldg(p.bias + gn + 2); v.w += __ldg(p.bias + gn + 3);
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
+            if (p.beta != 0.f) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y);
+                v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+            }
+            v.x = gt_act(v.x, p.act); v.y = gt_act(v.y, p.act); v.z = gt_act(v.z, p.act); v.w = gt_act(v.w, p.act);
+            *reinterpret_cast<float4*>(dst) = v;
+        };
+#pragma unroll
+        for (int sub = 0; sub < NT / 32; sub++) {
+#pragma unroll
+            for (int it = 0; it < (TILE_M * 8) / WORK_THREADS; it++) {
+                const int idx = t + it * WORK_THREADS;
+                const int row = idx >> 3, chunk = idx & 7;
+                const int gm = m0 + row, gn = n0 + sub * 32 + chunk * 4;
+                if (gm < p.M && gn < p.N) {            // N % 4 == 0: a float4 never straddles the edge
+                    const float4 v = *reinterpret_cast<const float4*>(op_base + (size_t)sub * (TILE_M * 128) + row * 128 + ((chunk ^ (row & 7)) << 4));
+                    if (fin) finish(v, gm, gn);
+                    else __stcg(reinterpret_cast<float4*>(out + (int64_t)gm * ld_out + gn), v);
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -360,28 +376,28 @@ int mlb_gemm_tc(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int6
     // split K until the grid covers the SMs about once, keeping at least two k-blocks per CTA
     int splits = 1;
     const int tiles = tiles_m * tiles_n;
+    // (measured on the SAC update at C4 sizes: a CTA spends ~1.2 us per k-block, so even 4-8 k-blocks are worth a
+    // second launch that adds the partial tiles)
     if (tiles < 120 && nkb >= 4) splits = std::max(1, std::min({148 / tiles, nkb / 2, 32}));
     int kb_per = (nkb + splits - 1) / splits;
     splits = (nkb + kb_per - 1) / kb_per;                       // no empty CTA
-    const bool partial = splits > 1 || beta != 0.f;
+    const bool partial = splits > 1;
     const int m_pad = tiles_m * TILE_M;
     float* ws = nullptr;
     if (partial) {
         ws = workspace((size_t)splits * m_pad * N * sizeof(float), st);
         if (!ws) return MLB_ENOMEM;                             // caller falls back to the FFMA kernel
     }
-    CUtensorMap ma, mb, mc;
+    CUtensorMap ma, mb;
     const bool ok_a = at ? make_map_2d(&ma, A, M, K, lda, TILE_M, TILE_K, false) : make_map_2d(&ma, A, K, M, lda, TILE_K, TILE_M, true);
     const bool ok_b = bt ? make_map_2d(&mb, B, N, K, ldb, NT, TILE_K, false) : make_map_2d(&mb, B, K, N, ldb, TILE_K, NT, true);
-    const bool ok_c = partial ? make_map_2d(&mc, ws, N, (int64_t)splits * m_pad, N, TILE_K, TILE_M, true)
-                              : make_map_2d(&mc, C, N, M, ldc, TILE_K, TILE_M, true);
-    if (!ok_a || !ok_b || !ok_c) return MLB_ESTATE;            // nothing launched: the caller may use the FFMA kernel
-    GtParams p{partial ? nullptr : bias, M, N, K, act, kb_per, partial ? m_pad : 0};
+    if (!ok_a || !ok_b) return MLB_ESTATE;            // nothing launched: the caller may use the FFMA kernel
+    GtParams p{C, ws, partial ? nullptr : bias, ldc, beta, M, N, K, act, kb_per, partial ? m_pad : 0};
     const void* fn = NT == 64 ? pick_kernel<64>(at, bt) : pick_kernel<128>(at, bt);
     const size_t smem = smem_bytes(NT);
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MLB_ECUDA;
     dim3 grid(tiles_n, tiles_m, splits);
-    void* args[] = {&ma, &mb, &mc, &p};
+    void* args[] = {&ma, &mb, &p};
     if (cudaLaunchKernel(fn, grid, dim3(THREADS), args, smem, st) != cudaSuccess) return MLB_ECUDA;
     if (partial) {
         const int64_t total = (int64_t)M * N;

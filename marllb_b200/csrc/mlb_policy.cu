@@ -96,6 +96,93 @@ gemm_kernel(const float* __restrict__ A, int64_t a_bs, int64_t a_rs, int64_t a_c
     }
 }
 
+// ---- skinny products of the MLP heads (fc3: 256 -> 1 and its two gradients), where a 64 x 64 tile is mostly padding
+// C[m][n], n < N <= 8: one warp per output row, lanes stride the contraction, shuffle reduction
+template <int NMAX>
+__global__ void gemm_skinny_n_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B,
+                                     int64_t b_rs, int64_t b_cs, float* __restrict__ C, int64_t ldc,
+                                     const float* __restrict__ bias, int M, int N, int K, float beta, int act) {
+    const int m = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) acc[n] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float a = __ldg(A + (int64_t)m * a_rs + (int64_t)k * a_cs);
+#pragma unroll
+        for (int n = 0; n < NMAX; n++)
+            if (n < N) acc[n] = fmaf(a, __ldg(B + (int64_t)k * b_rs + (int64_t)n * b_cs), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    }
+    if (lane < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int n = 0; n < NMAX; n++) v = lane == n ? acc[n] : v;
+        if (bias) v += bias[lane];
+        float* c = C + (int64_t)m * ldc + lane;
+        if (beta != 0.f) v += beta * *c;
+        if (act == MLB_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == MLB_ACT_ABS) v = fabsf(v);
+        *c = v;
+    }
+}
+// C[m][n], m < M <= 8: block = 32 columns x 32 contraction lanes (coalesced over n when b_cs == 1), shared-memory reduction
+template <int MMAX>
+__global__ void gemm_skinny_m_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B,
+                                     int64_t b_rs, int64_t b_cs, float* __restrict__ C, int64_t ldc,
+                                     const float* __restrict__ bias, int M, int N, int K, float beta, int act) {
+    __shared__ float part[32][MMAX][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    float acc[MMAX];
+#pragma unroll
+    for (int m = 0; m < MMAX; m++) acc[m] = 0.f;
+    if (n < N) {
+#pragma unroll 4
+        for (int k = threadIdx.y; k < K; k += 32) {
+            const float b = __ldg(B + (int64_t)k * b_rs + (int64_t)n * b_cs);
+#pragma unroll
+            for (int m = 0; m < MMAX; m++)
+                if (m < M) acc[m] = fmaf(__ldg(A + (int64_t)m * a_rs + (int64_t)k * a_cs), b, acc[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MMAX; m++) part[threadIdx.y][m][threadIdx.x] = acc[m];
+    __syncthreads();
+    if (n < N && threadIdx.y < M) {
+        const int m = threadIdx.y;
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) v += part[j][m][threadIdx.x];
+        if (bias) v += bias[n];
+        float* c = C + (int64_t)m * ldc + n;
+        if (beta != 0.f) v += beta * *c;
+        if (act == MLB_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == MLB_ACT_ABS) v = fabsf(v);
+        *c = v;
+    }
+}
+// K <= 8 (outer products): one thread per output element
+__global__ void gemm_thin_k_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B,
+                                   int64_t b_rs, int64_t b_cs, float* __restrict__ C, int64_t ldc,
+                                   const float* __restrict__ bias, int M, int N, int K, float beta, int act) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * N) return;
+    const int m = (int)(i / N), n = (int)(i - (int64_t)m * N);
+    float v = 0.f;
+    for (int k = 0; k < K; k++) v = fmaf(__ldg(A + (int64_t)m * a_rs + (int64_t)k * a_cs), __ldg(B + (int64_t)k * b_rs + (int64_t)n * b_cs), v);
+    if (bias) v += bias[n];
+    float* c = C + (int64_t)m * ldc + n;
+    if (beta != 0.f) v += beta * *c;
+    if (act == MLB_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == MLB_ACT_ABS) v = fabsf(v);
+    *c = v;
+}
+
 // C = act(beta*C + sum_s ws[s] + bias), partial sums added in split order (deterministic)
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int batch, float* __restrict__ C,
                                      int64_t c_bs, int64_t ldc, const float* __restrict__ bias, int64_t bias_bs,
@@ -172,19 +259,21 @@ __global__ void abs_bwd_kernel(const float* __restrict__ pre, const float* __res
     }
 }
 
-// db[n] = beta*db[n] + sum_m dy[m][n]; one block per 32 columns, 8 row-lanes
+// db[n] = beta*db[n] + sum_m dy[m][n]; one block per 32 columns, 32 row-lanes
 __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int N, int64_t ld, float beta) {
-    __shared__ float part[8][33];
+    __shared__ float part[32][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    if (n < N)
-        for (int m = threadIdx.y; m < M; m += 8) s += dy[(int64_t)m * ld + n];
+    if (n < N) {
+#pragma unroll 4
+        for (int m = threadIdx.y; m < M; m += 32) s += __ldg(dy + (int64_t)m * ld + n);
+    }
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && n < N) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) t += part[k][threadIdx.x];
+        for (int k = 0; k < 32; k++) t += part[k][threadIdx.x];
         db[n] = (beta != 0.f ? beta * db[n] : 0.f) + t;
     }
 }
@@ -718,6 +807,21 @@ int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const flo
             if (rc != MLB_ESTATE && rc != MLB_ENOMEM) return rc;   // those two: nothing was launched, use the FFMA kernel
         }
     }
+    if (batch == 1 && K >= 1) {
+        cudaStream_t st = (cudaStream_t)stream;
+        if (K <= 8) {
+            gemm_thin_k_kernel<<<nblk((int64_t)M * N, 256), 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, beta, act);
+            return ok();
+        }
+        if (N <= 8) {
+            gemm_skinny_n_kernel<8><<<nblk((int64_t)M * 32, 128), 128, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, beta, act);
+            return ok();
+        }
+        if (M <= 8) {
+            gemm_skinny_m_kernel<8><<<nblk(N, 32), dim3(32, 32), 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, beta, act);
+            return ok();
+        }
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
     // few output tiles and a long reduction: split K over more thread blocks (workspace per device, grown
     // outside stream capture only)
@@ -790,7 +894,7 @@ int mlb_abs_backward(const float* pre, const float* dy, float* dx, int64_t n, vo
 int mlb_colsum(const float* dy, float* db, int32_t M, int32_t N, int64_t ld, float beta, void* stream) {
     if (!dy || !db) return MLB_EINVAL;
     if (N == 0) return MLB_OK;
-    colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, db, M, N, ld, beta);
+    colsum_kernel<<<(N + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(dy, db, M, N, ld, beta);
     return ok();
 }
 

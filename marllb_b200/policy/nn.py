@@ -91,6 +91,7 @@ class FlatBucket:
             self._slices.append((o, t.numel(), tuple(t.shape)))
         if len(param_sets) == 1 and not extra:
             param_sets[0]._flat_g = self.flat_g
+            param_sets[0]._flat_p = self.flat_p
 
     def views(self, flat):
         return [flat[o:o + n].view(shape) for o, n, shape in self._slices]

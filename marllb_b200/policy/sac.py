@@ -178,7 +178,12 @@ class QNetwork:
 
 
 def soft_update(source, target, tau):
-    """networks.py:248-260: target = tau*source + (1-tau)*target."""
+    """networks.py:248-260: target = tau*source + (1-tau)*target.  One launch when both parameter sets live in flat
+    buffers of the same layout (the agent's networks do), else one per tensor."""
+    fs, ft = getattr(source.P, "_flat_p", None), getattr(target.P, "_flat_p", None)
+    if fs is not None and ft is not None and fs.numel() == ft.numel():
+        ops.axpby(tau, fs, 1.0 - tau, ft)
+        return
     for ps, pt in zip(source.P.tensors(), target.P.tensors()):
         ops.axpby(tau, ps, 1.0 - tau, pt)
 
@@ -295,6 +300,7 @@ class SAC_GRU_Agent:
         self.q2_target = QNetwork(state_dim, action_dim, hidden_dim, gru_dim, self.device)
         hard_update(self.q1, self.q1_target)
         hard_update(self.q2, self.q2_target)
+        self._target_buckets = [FlatBucket([self.q1_target.P]), FlatBucket([self.q2_target.P])]   # flat: one-launch soft update
         # four optimisers like the reference (sac_agent.py:93-106), each over one flat bucket that is
         # all-reduced once per step in the reference's step order
         self.policy_optimizer = Adam(FlatBucket([self.policy.P]), lr_policy)

@@ -37,7 +37,11 @@ def test_linear_tc_matches_float64(M, N, K):
     # and it is at least as accurate as the FFMA kernel on the same data
     G = torch.empty((M, N), device="cuda")
     from marllb_b200.policy.ops import _L, _p, _st, check
-    check(_L().mlb_gemm(_p(x), 0, K, 1, _p(W), 0, 1, K, _p(G), M * N, N, _p(b), 0, M, N, K, 1, 0.0, 0, _st()))
+    # (two identical batches: batched calls stay on the FFMA tile kernel, single ones may be routed to the tensor-core or
+    # the skinny kernels by mlb_gemm itself)
+    G2 = torch.empty((2, M, N), device="cuda")
+    check(_L().mlb_gemm(_p(x), 0, K, 1, _p(W), 0, 1, K, _p(G2), M * N, N, _p(b), 0, M, N, K, 2, 0.0, 0, _st()))
+    G = G2[0]
     ref = _ref(x, W, b, 0)
     e_tc = (ops.linear_tc(x, W, b).double() - ref).abs().max().item()
     e_ff = (G.double() - ref).abs().max().item()

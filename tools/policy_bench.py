@@ -37,3 +37,17 @@ print("SAC update   batch=256 state=2816 action=256: %.2f ms, %d kernel launches
 x = torch.randn(1024, S * 11, device="cuda")
 ms, l = timeit(lambda: sac.select_action_batch(x))
 print("SAC actor    1024 envs: %.3f ms, %d kernel launches" % (ms, l), flush=True)
+
+# the same SAC update replayed from a CUDA graph: device time without Python launch overhead
+upd = lambda: sac.update_parameters(1, batch=b, sync_stats=False)
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    upd(); upd()
+torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+l0 = ops.LAUNCHES
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    upd()
+nl = ops.LAUNCHES - l0
+ms, _ = timeit(g.replay, n=30)
+print("SAC update   (CUDA graph)          : %.3f ms, %d launches through ops in the graph" % (ms, nl), flush=True)
