@@ -191,6 +191,17 @@ int mlb_reward_normalize(const float *reward, float *out, float scale, int32_t B
 int mlb_dsac_q_target(const float *reward, const float *q1n, const float *q2n, const float *logp_next,
                       const float *alpha, float gamma, float *y, int32_t M, void *stream);
 
+/* nn.GRU over a whole sequence in one launch (the unrolled time loops of QMIXAgent.update, qmix_agent.py:217-224,
+ * 246-253): gi_all [T][B][3H] = x_t W_ih^T + b_ih for every step (one GEMM), h0 [B][H] -> hs [T][B][H]; hprev, ghs,
+ * gates (nullable) receive what the backward pass needs.  mlb_gru_seq_backward: dhs [T][B][H] gradient w.r.t. every
+ * output -> dgi_all, dgh_all [T][B][3H] (the weight gradients are then two GEMMs over T*B rows) and dh0 (nullable).
+ * 3H <= 1024 threads and W_hh resident in shared memory: H <= 128.  Same arithmetic as the per-step kernels. */
+int mlb_gru_seq_forward(const float *gi_all, const float *W_hh, const float *b_hh, const float *h0, float *hs,
+                        float *hprev, float *ghs, float *gates, int32_t T, int32_t B, int32_t H, void *stream);
+int mlb_gru_seq_backward(const float *dhs, const float *gates, const float *hprev, const float *ghs,
+                         const float *W_hh, float *dgi_all, float *dgh_all, float *dh0, int32_t T, int32_t B,
+                         int32_t H, void *stream);
+
 /* Device-resident replay ring for the batched rollout (ReplayBuffer.push / sample, problem-04-sac-gru/src/
  * replay_buffer.py:35-94, keeps one transition per Python call in a host deque).  Ring tensors: r_state /
  * r_next_state [capacity][state_dim], r_action [capacity][action_dim], r_hidden [capacity][hidden_dim], r_reward /

@@ -246,6 +246,138 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ dh_new, const flo
     dh_direct[i] = g * z;
 }
 
+// ---- the GRU time loop of an update in ONE launch (forward) and one more (backward through time).
+// QMIXAgent.update unrolls T = 50 steps per agent (qmix_agent.py:217-224, 246-253): launched step by step that is ~10
+// kernels per step and agent, each microseconds of work.  Batch rows are independent, so a block takes RB rows through
+// all T steps with the recurrent weights resident in shared memory (3H x H floats: 48 KB at H = 64) and the hidden
+// state never leaving the SM.  Same arithmetic as the per-step kernels (gemm accumulation order k = 0..H-1 with fmaf,
+// bias added last; gru_gates_fwd/bwd formulas), so the two forms agree to fp32 rounding.
+constexpr int GRU_SEQ_RB = 4;   // batch rows per block
+
+// hs[t] = GRU(gi_all[t], hs[t-1]);  saves what backward needs (nullable): hprev[t], ghs[t] = h W_hh^T + b_hh, gates[t]
+__global__ void gru_seq_fwd_kernel(const float* __restrict__ gi_all, const float* __restrict__ W_hh,
+                                   const float* __restrict__ b_hh, const float* __restrict__ h0, float* __restrict__ hs,
+                                   float* __restrict__ hprev, float* __restrict__ ghs, float* __restrict__ gates, int T, int B,
+                                   int H) {
+    extern __shared__ float gsm[];
+    const int H3 = 3 * H;
+    float* WT = gsm;                       // [H][3H]: WT[k][j] = W_hh[j][k] (threads j consecutive: conflict-free)
+    float* h_s = WT + (size_t)H * H3;      // [RB][H]
+    float* gh_s = h_s + GRU_SEQ_RB * H;    // [RB][3H]
+    const int tid = threadIdx.x, nt = blockDim.x;     // nt = 3H
+    const int b0 = blockIdx.x * GRU_SEQ_RB;
+    const int nr = min(GRU_SEQ_RB, B - b0);
+    for (int i = tid; i < H3 * H; i += nt) {
+        const int j = i / H, k = i - j * H;
+        WT[(size_t)k * H3 + j] = __ldg(W_hh + i);
+    }
+    for (int i = tid; i < GRU_SEQ_RB * H; i += nt) {
+        const int r = i / H, c = i - r * H;
+        h_s[i] = r < nr ? __ldg(h0 + (size_t)(b0 + r) * H + c) : 0.f;
+    }
+    const float bj = __ldg(b_hh + tid);
+    __syncthreads();
+    for (int t = 0; t < T; t++) {
+        // gh[r][j] = sum_k h[r][k] W_hh[j][k] + b_hh[j], thread = j
+        float acc[GRU_SEQ_RB];
+#pragma unroll
+        for (int r = 0; r < GRU_SEQ_RB; r++) acc[r] = 0.f;
+        for (int k = 0; k < H; k++) {
+            const float w = WT[(size_t)k * H3 + tid];
+#pragma unroll
+            for (int r = 0; r < GRU_SEQ_RB; r++) acc[r] = fmaf(h_s[r * H + k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < GRU_SEQ_RB; r++) {
+            const float v = acc[r] + bj;
+            gh_s[r * H3 + tid] = v;
+            if (ghs && r < nr) ghs[((size_t)t * B + b0 + r) * H3 + tid] = v;
+        }
+        __syncthreads();
+        // gates (gate order r, z, n) and the new hidden state, thread = (row, column)
+        for (int i = tid; i < nr * H; i += nt) {
+            const int r = i / H, c = i - r * H;
+            const size_t row = (size_t)t * B + b0 + r;
+            const float* gim = gi_all + row * H3;
+            const float* ghm = gh_s + r * H3;
+            const float rg = sigmoidf_(__ldg(gim + c) + ghm[c]);
+            const float z = sigmoidf_(__ldg(gim + H + c) + ghm[H + c]);
+            const float n = tanhf(__ldg(gim + 2 * H + c) + rg * ghm[2 * H + c]);
+            const float hold = h_s[i];
+            const float hn = (1.f - z) * n + z * hold;
+            if (hprev) hprev[row * H + c] = hold;
+            hs[row * H + c] = hn;
+            if (gates) {
+                float* gm = gates + row * H3;
+                gm[c] = rg; gm[H + c] = z; gm[2 * H + c] = n;
+            }
+            h_s[i] = hn;
+        }
+        __syncthreads();
+    }
+}
+
+// backward through time: dgi_all[t], dgh_all[t] for every step and the gradient w.r.t. h0
+__global__ void gru_seq_bwd_kernel(const float* __restrict__ dhs, const float* __restrict__ gates,
+                                   const float* __restrict__ hprev, const float* __restrict__ ghs,
+                                   const float* __restrict__ W_hh, float* __restrict__ dgi_all, float* __restrict__ dgh_all,
+                                   float* __restrict__ dh0, int T, int B, int H) {
+    extern __shared__ float gsm[];
+    const int H3 = 3 * H;
+    float* W = gsm;                            // [3H][H] as stored (threads k consecutive: conflict-free)
+    float* dh_s = W + (size_t)H3 * H;          // [RB][H] gradient flowing into step t from step t+1
+    float* dgh_s = dh_s + GRU_SEQ_RB * H;      // [RB][3H]
+    float* part = dgh_s + GRU_SEQ_RB * H3;     // [3][RB][H] partial products per gate block
+    const int tid = threadIdx.x, nt = blockDim.x;     // nt = 3H
+    const int b0 = blockIdx.x * GRU_SEQ_RB;
+    const int nr = min(GRU_SEQ_RB, B - b0);
+    for (int i = tid; i < H3 * H; i += nt) W[i] = __ldg(W_hh + i);
+    for (int i = tid; i < GRU_SEQ_RB * H; i += nt) dh_s[i] = 0.f;
+    for (int i = tid; i < GRU_SEQ_RB * H3; i += nt) dgh_s[i] = 0.f;
+    __syncthreads();
+    const int g = tid / H, k = tid - g * H;    // gate block and hidden column of this thread in the product below
+    for (int t = T - 1; t >= 0; t--) {
+        for (int i = tid; i < nr * H; i += nt) {
+            const int r = i / H, c = i - r * H;
+            const size_t row = (size_t)t * B + b0 + r;
+            const float* gm = gates + row * H3;
+            const float rg = __ldg(gm + c), z = __ldg(gm + H + c), n = __ldg(gm + 2 * H + c);
+            const float gr = __ldg(dhs + row * H + c) + dh_s[i];
+            const float dn = gr * (1.f - z);
+            const float dz = gr * (__ldg(hprev + row * H + c) - n);
+            const float dan = dn * (1.f - n * n);
+            const float ghn = __ldg(ghs + row * H3 + 2 * H + c);
+            const float dar = dan * ghn * rg * (1.f - rg);
+            const float daz = dz * z * (1.f - z);
+            float* dgim = dgi_all + row * H3;
+            float* dghm = dgh_all + row * H3;
+            dgim[c] = dar; dgim[H + c] = daz; dgim[2 * H + c] = dan;
+            const float dghn = dan * rg;
+            dghm[c] = dar; dghm[H + c] = daz; dghm[2 * H + c] = dghn;
+            dgh_s[r * H3 + c] = dar; dgh_s[r * H3 + H + c] = daz; dgh_s[r * H3 + 2 * H + c] = dghn;
+            dh_s[i] = gr * z;                  // direct path h_{t-1} -> h_t
+        }
+        __syncthreads();
+        // dh_prev[r][k] = dh_direct + sum_j dgh[r][j] W_hh[j][k]: thread (g, k) sums gate block g
+        float acc[GRU_SEQ_RB];
+#pragma unroll
+        for (int r = 0; r < GRU_SEQ_RB; r++) acc[r] = 0.f;
+        for (int jj = 0; jj < H; jj++) {
+            const float w = W[(size_t)(g * H + jj) * H + k];
+#pragma unroll
+            for (int r = 0; r < GRU_SEQ_RB; r++) acc[r] = fmaf(dgh_s[r * H3 + g * H + jj], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < GRU_SEQ_RB; r++) part[(g * GRU_SEQ_RB + r) * H + k] = acc[r];
+        __syncthreads();
+        for (int i = tid; i < GRU_SEQ_RB * H; i += nt)
+            dh_s[i] += (part[i] + part[GRU_SEQ_RB * H + i]) + part[2 * GRU_SEQ_RB * H + i];
+        __syncthreads();
+    }
+    if (dh0)
+        for (int i = tid; i < nr * H; i += nt) dh0[(size_t)(b0 + i / H) * H + (i % H)] = dh_s[i];
+}
+
 __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
@@ -1158,6 +1290,30 @@ int mlb_replay_gather(const float* r_state, const float* r_action, const float* 
                  const_cast<float*>(r_hidden), const_cast<float*>(r_reward), const_cast<float*>(r_done)};
     replay_gather_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(r, idx, state, action, reward, next_state, done, hidden,
                                                                 state_dim, action_dim, hidden_dim);
+    return ok();
+}
+
+int mlb_gru_seq_forward(const float* gi_all, const float* W_hh, const float* b_hh, const float* h0, float* hs,
+                        float* hprev, float* ghs, float* gates, int32_t T, int32_t B, int32_t H, void* stream) {
+    if (!gi_all || !W_hh || !b_hh || !h0 || !hs || T < 0 || B < 0 || H < 1) return MLB_EINVAL;
+    if (T == 0 || B == 0) return MLB_OK;
+    const size_t smem = ((size_t)3 * H * H + (size_t)GRU_SEQ_RB * H + (size_t)GRU_SEQ_RB * 3 * H) * sizeof(float);
+    if (3 * H > 1024 || smem > 227 * 1024) return MLB_EINVAL;
+    if (cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MLB_ECUDA;
+    gru_seq_fwd_kernel<<<(B + GRU_SEQ_RB - 1) / GRU_SEQ_RB, 3 * H, smem, (cudaStream_t)stream>>>(gi_all, W_hh, b_hh, h0, hs, hprev, ghs,
+                                                                                          gates, T, B, H);
+    return ok();
+}
+
+int mlb_gru_seq_backward(const float* dhs, const float* gates, const float* hprev, const float* ghs, const float* W_hh,
+                         float* dgi_all, float* dgh_all, float* dh0, int32_t T, int32_t B, int32_t H, void* stream) {
+    if (!dhs || !gates || !hprev || !ghs || !W_hh || !dgi_all || !dgh_all || T < 0 || B < 0 || H < 1) return MLB_EINVAL;
+    if (T == 0 || B == 0) return MLB_OK;
+    const size_t smem = ((size_t)3 * H * H + (size_t)GRU_SEQ_RB * H + (size_t)GRU_SEQ_RB * 3 * H + (size_t)3 * GRU_SEQ_RB * H) * sizeof(float);
+    if (3 * H > 1024 || smem > 227 * 1024) return MLB_EINVAL;
+    if (cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MLB_ECUDA;
+    gru_seq_bwd_kernel<<<(B + GRU_SEQ_RB - 1) / GRU_SEQ_RB, 3 * H, smem, (cudaStream_t)stream>>>(dhs, gates, hprev, ghs, W_hh, dgi_all,
+                                                                                          dgh_all, dh0, T, B, H);
     return ok();
 }
 

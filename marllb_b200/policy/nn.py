@@ -241,6 +241,10 @@ def linear_backward(P, wname, bname, x, dy, need_dx=True):
     return ops.matmul_nn(dy, P.p[wname]) if need_dx else None
 
 
+import os as _os
+FUSED_GRU_SEQ = _os.environ.get("MLB_FUSED_GRU_SEQ", "1") != "0"   # A/B knob: 0 = the step-by-step launches
+
+
 class GRUCellSeq:
     """nn.GRU(in, H, batch_first=True) run step by step (agent_network.py:41,76-78; networks.py:60,97)."""
 
@@ -261,6 +265,11 @@ class GRUCellSeq:
         T, B, In = xs.shape
         H = h0.shape[-1]
         gi_all = ops.linear(xs.reshape(T * B, In), P[k + "weight_ih_l0"], P[k + "bias_ih_l0"]).reshape(T, B, 3 * H)
+        if FUSED_GRU_SEQ and ops.gru_seq_supported(H):
+            # the whole time loop in one launch (csrc/mlb_policy.cu gru_seq_fwd_kernel)
+            hs, hprev, ghs, gates = ops.gru_seq_forward(gi_all.contiguous(), P[k + "weight_hh_l0"], P[k + "bias_hh_l0"],
+                                                        h0.contiguous())
+            return hs, (xs, hprev, ghs, gates)
         hs = torch.empty((T, B, H), dtype=torch.float32, device=xs.device)
         hprev = torch.empty((T, B, H), dtype=torch.float32, device=xs.device)
         ghs = torch.empty((T, B, 3 * H), dtype=torch.float32, device=xs.device)
@@ -280,6 +289,9 @@ class GRUCellSeq:
         P, k = self.P, self.k
         xs, hprev, ghs, gates = tape
         T, B, H = dhs.shape
+        if FUSED_GRU_SEQ and ops.gru_seq_supported(H):
+            dgi_all, dgh_all, dh_next = ops.gru_seq_backward(dhs.contiguous(), gates, hprev, ghs, P.p[k + "weight_hh_l0"])
+            return self._seq_param_grads(dgi_all, dgh_all, xs, hprev, need_dx, dh_next)
         dgi_all = torch.empty_like(gates)
         dgh_all = torch.empty_like(gates)
         dh_next = torch.zeros((B, H), dtype=torch.float32, device=dhs.device)
@@ -291,6 +303,11 @@ class GRUCellSeq:
             dgh_all[t].copy_(dgh)
             dh_next = ops.matmul_nn(dgh, P.p[k + "weight_hh_l0"])
             ops.axpby(1.0, dh_direct, 1.0, dh_next)
+        return self._seq_param_grads(dgi_all, dgh_all, xs, hprev, need_dx, dh_next)
+
+    def _seq_param_grads(self, dgi_all, dgh_all, xs, hprev, need_dx, dh_next):
+        P, k = self.P, self.k
+        T, B, H = hprev.shape
         In = xs.shape[-1]
         dgi2, dgh2 = dgi_all.reshape(T * B, 3 * H), dgh_all.reshape(T * B, 3 * H)
         ops.matmul_tn(dgi2, xs.reshape(T * B, In), out=P.g[k + "weight_ih_l0"], beta=1.0)

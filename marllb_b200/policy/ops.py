@@ -61,6 +61,8 @@ def _L():
             "mlb_weighted_sum_backward": [vp, vp, vp, vp, vp, i32, i32, vp],
             "mlb_reward_normalize": [vp, vp, f32, i32, i32, vp],
             "mlb_dsac_q_target": [vp, vp, vp, vp, vp, f32, vp, i32, vp],
+            "mlb_gru_seq_forward": [vp] * 8 + [i32] * 3 + [vp],
+            "mlb_gru_seq_backward": [vp] * 8 + [i32] * 3 + [vp],
             "mlb_replay_push": [vp] * 13 + [i32] * 5 + [vp],
             "mlb_replay_gather": [vp] * 13 + [i32] * 4 + [vp],
         }
@@ -80,7 +82,7 @@ POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_g
                   "mlb_softmax_forward", "mlb_softmax_backward", "mlb_concat_onehot", "mlb_categorical",
                   "mlb_logprob_backward", "mlb_scatter_class", "mlb_td_lambda_targets", "mlb_reward_normalize",
                   "mlb_dsac_q_target", "mlb_weighted_sum_forward", "mlb_weighted_sum_backward",
-                  "mlb_replay_push", "mlb_replay_gather"]
+                  "mlb_replay_push", "mlb_replay_gather", "mlb_gru_seq_forward", "mlb_gru_seq_backward"]
 
 
 def _p(t):
@@ -210,6 +212,34 @@ def gru_gates_backward(dh_new, gates, h, gh):
     dgi, dgh, dh = torch.empty_like(gates), torch.empty_like(gates), torch.empty_like(h)
     check(_L().mlb_gru_gates_backward(_p(_chk(dh_new)), _p(gates), _p(h), _p(gh), _p(dgi), _p(dgh), _p(dh), M, H, _st()))
     return dgi, dgh, dh
+
+
+def gru_seq_supported(H):
+    return 3 * H <= 1024 and (3 * H * H + 4 * H + 12 * H + 12 * H) * 4 <= 227 * 1024
+
+
+def gru_seq_forward(gi_all, W_hh, b_hh, h0, save=True):
+    """gi_all [T,B,3H] -> hs [T,B,H] (+ hprev, ghs, gates for the backward pass) in one launch."""
+    T, B, H3 = gi_all.shape
+    H = H3 // 3
+    f = dict(dtype=torch.float32, device=gi_all.device)
+    hs = torch.empty((T, B, H), **f)
+    hprev = torch.empty((T, B, H), **f) if save else None
+    ghs = torch.empty((T, B, H3), **f) if save else None
+    gates = torch.empty((T, B, H3), **f) if save else None
+    check(_L().mlb_gru_seq_forward(_p(_chk(gi_all)), _p(_chk(W_hh)), _p(_chk(b_hh)), _p(_chk(h0)), _p(hs), _p(hprev), _p(ghs),
+                                   _p(gates), T, B, H, _st()))
+    return hs, hprev, ghs, gates
+
+
+def gru_seq_backward(dhs, gates, hprev, ghs, W_hh):
+    T, B, H = dhs.shape
+    dgi = torch.empty_like(gates)
+    dgh = torch.empty_like(gates)
+    dh0 = torch.empty((B, H), dtype=torch.float32, device=dhs.device)
+    check(_L().mlb_gru_seq_backward(_p(_chk(dhs)), _p(_chk(gates)), _p(_chk(hprev)), _p(_chk(ghs)), _p(_chk(W_hh)), _p(dgi), _p(dgh),
+                                    _p(dh0), T, B, H, _st()))
+    return dgi, dgh, dh0
 
 
 def relu_backward(y, dy):
