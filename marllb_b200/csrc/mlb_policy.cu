@@ -259,17 +259,29 @@ __global__ void gru_seq_fwd_kernel(const float* __restrict__ gi_all, const float
                                    const float* __restrict__ b_hh, const float* __restrict__ h0, float* __restrict__ hs,
                                    float* __restrict__ hprev, float* __restrict__ ghs, float* __restrict__ gates, int T, int B,
                                    int H) {
-    extern __shared__ float gsm[];
+    extern __shared__ __align__(16) float gsm[];
     const int H3 = 3 * H;
-    float* WT = gsm;                       // [H][3H]: WT[k][j] = W_hh[j][k] (threads j consecutive: conflict-free)
-    float* h_s = WT + (size_t)H * H3;      // [RB][H]
+    const int H3P = H3 + 1;                // padded row: the transposing stores below (k consecutive) hit distinct banks
+    float* WT = gsm;                       // [H][3H+1]: WT[k][j] = W_hh[j][k] (threads j consecutive: conflict-free)
+    float* h_s = WT + (size_t)H * H3P;     // [RB][H]
     float* gh_s = h_s + GRU_SEQ_RB * H;    // [RB][3H]
     const int tid = threadIdx.x, nt = blockDim.x;     // nt = 3H
     const int b0 = blockIdx.x * GRU_SEQ_RB;
     const int nr = min(GRU_SEQ_RB, B - b0);
-    for (int i = tid; i < H3 * H; i += nt) {
-        const int j = i / H, k = i - j * H;
-        WT[(size_t)k * H3 + j] = __ldg(W_hh + i);
+    if ((H & 3) == 0) {                    // 128-bit loads, several in flight (T = 1 calls are all prologue)
+        const float4* W4 = reinterpret_cast<const float4*>(W_hh);
+#pragma unroll 4
+        for (int i = tid; i < H3 * H / 4; i += nt) {
+            const float4 w = __ldg(W4 + i);
+            const int j = (i * 4) / H, k = i * 4 - j * H;
+            float* dst = WT + (size_t)k * H3P + j;
+            dst[0] = w.x; dst[H3P] = w.y; dst[2 * H3P] = w.z; dst[3 * H3P] = w.w;
+        }
+    } else {
+        for (int i = tid; i < H3 * H; i += nt) {
+            const int j = i / H, k = i - j * H;
+            WT[(size_t)k * H3P + j] = __ldg(W_hh + i);
+        }
     }
     for (int i = tid; i < GRU_SEQ_RB * H; i += nt) {
         const int r = i / H, c = i - r * H;
@@ -283,7 +295,7 @@ __global__ void gru_seq_fwd_kernel(const float* __restrict__ gi_all, const float
 #pragma unroll
         for (int r = 0; r < GRU_SEQ_RB; r++) acc[r] = 0.f;
         for (int k = 0; k < H; k++) {
-            const float w = WT[(size_t)k * H3 + tid];
+            const float w = WT[(size_t)k * H3P + tid];
 #pragma unroll
             for (int r = 0; r < GRU_SEQ_RB; r++) acc[r] = fmaf(h_s[r * H + k], w, acc[r]);
         }
@@ -322,7 +334,7 @@ __global__ void gru_seq_bwd_kernel(const float* __restrict__ dhs, const float* _
                                    const float* __restrict__ hprev, const float* __restrict__ ghs,
                                    const float* __restrict__ W_hh, float* __restrict__ dgi_all, float* __restrict__ dgh_all,
                                    float* __restrict__ dh0, int T, int B, int H) {
-    extern __shared__ float gsm[];
+    extern __shared__ __align__(16) float gsm[];
     const int H3 = 3 * H;
     float* W = gsm;                            // [3H][H] as stored (threads k consecutive: conflict-free)
     float* dh_s = W + (size_t)H3 * H;          // [RB][H] gradient flowing into step t from step t+1
@@ -331,7 +343,12 @@ __global__ void gru_seq_bwd_kernel(const float* __restrict__ dhs, const float* _
     const int tid = threadIdx.x, nt = blockDim.x;     // nt = 3H
     const int b0 = blockIdx.x * GRU_SEQ_RB;
     const int nr = min(GRU_SEQ_RB, B - b0);
-    for (int i = tid; i < H3 * H; i += nt) W[i] = __ldg(W_hh + i);
+    if ((H & 3) == 0) {
+#pragma unroll 4
+        for (int i = tid; i < H3 * H / 4; i += nt) reinterpret_cast<float4*>(W)[i] = __ldg(reinterpret_cast<const float4*>(W_hh) + i);
+    } else {
+        for (int i = tid; i < H3 * H; i += nt) W[i] = __ldg(W_hh + i);
+    }
     for (int i = tid; i < GRU_SEQ_RB * H; i += nt) dh_s[i] = 0.f;
     for (int i = tid; i < GRU_SEQ_RB * H3; i += nt) dgh_s[i] = 0.f;
     __syncthreads();
@@ -1297,7 +1314,7 @@ int mlb_gru_seq_forward(const float* gi_all, const float* W_hh, const float* b_h
                         float* hprev, float* ghs, float* gates, int32_t T, int32_t B, int32_t H, void* stream) {
     if (!gi_all || !W_hh || !b_hh || !h0 || !hs || T < 0 || B < 0 || H < 1) return MLB_EINVAL;
     if (T == 0 || B == 0) return MLB_OK;
-    const size_t smem = ((size_t)3 * H * H + (size_t)GRU_SEQ_RB * H + (size_t)GRU_SEQ_RB * 3 * H) * sizeof(float);
+    const size_t smem = ((size_t)(3 * H + 1) * H + (size_t)GRU_SEQ_RB * H + (size_t)GRU_SEQ_RB * 3 * H) * sizeof(float);
     if (3 * H > 1024 || smem > 227 * 1024) return MLB_EINVAL;
     if (cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MLB_ECUDA;
     gru_seq_fwd_kernel<<<(B + GRU_SEQ_RB - 1) / GRU_SEQ_RB, 3 * H, smem, (cudaStream_t)stream>>>(gi_all, W_hh, b_hh, h0, hs, hprev, ghs,
