@@ -107,6 +107,11 @@ static cudaError_t dalloc(mlb_env* h, T** p, size_t n) {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
     if (e == cudaSuccess) {
+        // debug aid (tools/determinism_probe.py): MLB_POISON=<byte> fills every fresh allocation, so that a read of
+        // memory nothing wrote shows up as a difference between two runs with different fill bytes
+        if (const char* pz = getenv("MLB_POISON")) e = cudaMemset(q, (int)strtol(pz, nullptr, 0) & 255, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+    }
+    if (e == cudaSuccess) {
         std::lock_guard<std::mutex> lk(h->mu);
         h->allocs.push_back(q);
         *p = reinterpret_cast<T*>(q);

@@ -212,8 +212,14 @@ __device__ __forceinline__ void ranks_full_sort(const float (&v)[EPL], int n, in
 // ---------------------------------------------------------------------------
 // Incremental rank maintenance for a FULL reservoir (all 32*EPL slots valid) in which
 // Algorithm R replaced a few slots.  v[] already holds the new values, rk[] the ranks of
-// the previous contents.  Order is the strict total order on (value, slot), so equal
-// values rank by slot index (any order of equal values is a valid sorted order).
+// the previous contents.  Any order of equal values is a valid sorted order, and the stored
+// ranks may hold tied values in ANY order (the bitonic sort does not order ties), so the
+// update must not assume one: a new value is inserted AFTER every present element that
+// equals it -- "before" = (v_i <= x), "after" = (v_i > x), which is consistent with whatever
+// order the ties already have.  (Ranking ties by slot index instead, as this code first did,
+// produced duplicate ranks when a third equal value met a tied pair that a re-sort had left in
+// non-slot order; float32 durations taken as differences of timestamps are quantised, so such
+// triple ties do occur at scale: tools/determinism_probe.py, tests/test_gpu_ties.py.)
 //
 // One replaced slot c (the common case): remove its old rank, count the elements below
 // the new value, shift the ones above.  ~45 instructions.
@@ -226,7 +232,7 @@ __device__ __forceinline__ void rank_replace_one(const float (&v)[EPL], int (&rk
     int cnt = 0;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        before[r] = v[r] < x || (v[r] == x && s0 + r < c);  // (v_i, i) < (x, c); false for i == c
+        before[r] = v[r] < x || (v[r] == x && s0 + r != c);  // v_i <= x for every other slot; false for i == c
         cnt += before[r] ? 1 : 0;
     }
     const int r_new = __reduce_add_sync(MLB_FULL, cnt);
@@ -244,14 +250,14 @@ __device__ __forceinline__ uint32_t rank_replace_one_packed(const float (&v)[4],
     const float xs = slot_fetch<4>(v, c);
     const float x = xs + 0.0f;  // -0 -> +0, so that the integer successor below is the next float up
     const uint32_t r_old = (__shfl_sync(MLB_FULL, rkp, lc) >> (8 * sub)) & 255u;
-    // (v_i, i) < (x, c)  <=>  v_i < x or (v_i == x and i < c)  <=>  v_i < (i < c ? nextup(x) : x)
+    // v_i <= x  <=>  v_i < nextup(x) for every slot but c itself (which holds x and must not count)
     const uint32_t xb = __float_as_uint(x);
     const float xup = __uint_as_float((xb >> 31) ? xb - 1u : xb + 1u);
-    const int dl = c - lane * 4;  // slots r < dl of this lane lie before c
+    const int dl = c - lane * 4;  // slot r == dl of this lane is c
     uint32_t bef = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        const float xr = r < dl ? xup : x;
+        const float xr = r == dl ? x : xup;
         bef |= v[r] < xr ? (1u << (8 * r)) : 0u;
     }
     const uint32_t r_new = (uint32_t)__reduce_add_sync(MLB_FULL, __popc(bef));
@@ -293,7 +299,7 @@ __device__ __forceinline__ void rank_replace_few(const float (&v)[EPL], int (&rk
 #pragma unroll
         for (int r = 0; r < EPL; r++) {
             const bool present = rk[r] >= 0;
-            const bool before = v[r] < x || (v[r] == x && s0 + r < c);
+            const bool before = v[r] <= x;            // slot c itself is not present yet
             after[r] = present && !before;
             cnt += (present && before) ? 1 : 0;
         }
@@ -578,12 +584,12 @@ __device__ __forceinline__ void rank_replace_one_h16(const float (&v)[8], uint32
     const uint32_t r_old = (__shfl_sync(MLB_FULL, wsel, lc, 16) >> (8 * (sub & 3))) & 255u;
     const uint32_t xb = __float_as_uint(x);
     const float xup = __uint_as_float((xb >> 31) ? xb - 1u : xb + 1u);
-    const int dl = c - hl * 8;  // slots r < dl of this lane lie before c
+    const int dl = c - hl * 8;  // slot r == dl of this lane is c (it holds x itself and must not count)
     uint32_t bef0 = 0, bef1 = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        bef0 |= v[r] < (r < dl ? xup : x) ? (1u << (8 * r)) : 0u;
-        bef1 |= v[r + 4] < (r + 4 < dl ? xup : x) ? (1u << (8 * r)) : 0u;
+        bef0 |= v[r] < (r == dl ? x : xup) ? (1u << (8 * r)) : 0u;
+        bef1 |= v[r + 4] < (r + 4 == dl ? x : xup) ? (1u << (8 * r)) : 0u;
     }
     const uint32_t r_new = half_reduce_add_u16((uint32_t)(__popc(bef0) + __popc(bef1)), half);
     const uint32_t rep = (r_old + 1u) * 0x01010101u;
@@ -708,12 +714,11 @@ __device__ __forceinline__ void rank_update_h16(const float (&v)[8], uint32_t (&
         const float x = __shfl_sync(MLB_FULL, pick8(v, sub), lc, 16) + 0.0f;
         const uint32_t xb = __float_as_uint(x);
         const float xup = __uint_as_float((xb >> 31) ? xb - 1u : xb + 1u);
-        const int dl = c - s0;
-        uint32_t bef0 = 0, bef1 = 0;
+        uint32_t bef0 = 0, bef1 = 0;      // v_i <= x; slot c itself is not present yet (masked by pm below)
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            bef0 |= v[r] < (r < dl ? xup : x) ? (1u << (8 * r)) : 0u;
-            bef1 |= v[r + 4] < (r + 4 < dl ? xup : x) ? (1u << (8 * r)) : 0u;
+            bef0 |= v[r] < xup ? (1u << (8 * r)) : 0u;
+            bef1 |= v[r + 4] < xup ? (1u << (8 * r)) : 0u;
         }
         const uint32_t r_new = half_reduce_add_u16((uint32_t)(__popc(bef0 & pm0) + __popc(bef1 & pm1)), half);
         if (ins) {
