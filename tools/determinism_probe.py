@@ -13,10 +13,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from marllb_b200 import VecLoadBalanceEnv  # noqa: E402
 
 
-def run(a, keep_step=None, keep_env=None):
+def run(a, keep_step=None, keep_env=None, feature_cache=True):
     E, S = a.envs, a.servers
     total = a.steps + 16
-    env = VecLoadBalanceEnv(E, num_servers=S, max_steps=total + 1)
+    env = VecLoadBalanceEnv(E, num_servers=S, max_steps=total + 1, feature_cache=feature_cache)
     env.set_speeds(np.where(np.arange(S) % 2 == 0, 1.0, 2.0).astype(np.float32))
     rate = 128.0 * S / 64
     env.gen_poisson(rate, 0.8 * 1.5 * S / rate, total * 0.25 + 1.0, seed=1234)
@@ -44,8 +44,21 @@ def main():
     ap.add_argument("--servers", type=int, default=64)
     ap.add_argument("--steps", type=int, default=2148)
     ap.add_argument("--runs", type=int, default=3)
+    ap.add_argument("--vs-resort", action="store_true",
+                    help="compare the incremental statistics (feature_cache=True) with a full re-sort of every reservoir every "
+                         "step (feature_cache=False): per-(step, env) observation sums within 2e-6 relative")
     a = ap.parse_args()
     ref, _ = run(a)
+    if a.vs_resort:
+        cur, _ = run(a, feature_cache=False)
+        rel = ((cur - ref).abs() / ref.abs().clamp_min(1e-6))
+        bad = rel > 2e-6
+        print(f"incremental vs re-sort over {a.steps} steps x {a.envs} envs: max relative difference of an env's observation sum "
+              f"{float(rel.max()):.3e}; {int(bad.sum())} (step, env) pairs above 2e-6", flush=True)
+        if int(bad.sum()):
+            st = bad.any(1).nonzero().flatten()
+            print("  first steps:", st[:8].tolist(), "envs at the first:", bad[int(st[0])].nonzero().flatten()[:8].tolist())
+        return
     for r in range(1, a.runs):
         cur, _ = run(a)
         diff = (cur != ref)
