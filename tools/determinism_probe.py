@@ -16,13 +16,15 @@ from marllb_b200 import VecLoadBalanceEnv  # noqa: E402
 def run(a, keep_step=None, keep_env=None, feature_cache=True):
     E, S = a.envs, a.servers
     total = a.steps + 16
-    env = VecLoadBalanceEnv(E, num_servers=S, max_steps=total + 1, feature_cache=feature_cache)
-    env.set_speeds(np.where(np.arange(S) % 2 == 0, 1.0, 2.0).astype(np.float32))
-    rate = 128.0 * S / 64
+    A = a.agents
+    env = VecLoadBalanceEnv(E, num_servers=S, num_agents=A, max_steps=total + 1, feature_cache=feature_cache,
+                            rng_mode=a.rng_mode)
+    env.set_speeds(np.where(np.arange(S * A) % 2 == 0, 1.0, 2.0).astype(np.float32))
+    rate = a.rate or 128.0 * S / 64
     env.gen_poisson(rate, 0.8 * 1.5 * S / rate, total * 0.25 + 1.0, seed=1234)
     env.reset()
     g = torch.Generator(device="cuda").manual_seed(0)
-    acts = [torch.randint(0, 3, (E, S), device="cuda", dtype=torch.uint8, generator=g) for _ in range(8)]
+    acts = [torch.randint(0, 3, (E, S * A), device="cuda", dtype=torch.uint8, generator=g) for _ in range(8)]
     sums = torch.empty((a.steps, E), dtype=torch.float32, device="cuda")
     kept = None
     for k in range(a.steps):
@@ -41,7 +43,10 @@ def run(a, keep_step=None, keep_env=None, feature_cache=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=131072)
-    ap.add_argument("--servers", type=int, default=64)
+    ap.add_argument("--servers", type=int, default=64, help="servers per agent")
+    ap.add_argument("--agents", type=int, default=1)
+    ap.add_argument("--rate", type=float, default=0.0, help="flows/s/agent (default 2 per server)")
+    ap.add_argument("--rng-mode", default="replay", choices=["replay", "philox"])
     ap.add_argument("--steps", type=int, default=2148)
     ap.add_argument("--runs", type=int, default=3)
     ap.add_argument("--vs-resort", action="store_true",
