@@ -52,6 +52,7 @@ struct mlb_env {
     uint8_t* d_mask = nullptr;
     size_t ev_smem = 0, ft_smem = 0, pr_smem = 0;   // dynamic shared memory of the event / feature / pair kernel
     bool use_pair = false;             // pair_kernel applies (128-slot reservoirs, feature cache on)
+    int pair_wpe_small = 4;            // warps per (env, agent) in pair_kernel for launches of <= 8192 (env, agent) pairs
     int ev_threads = 128;              // event kernel: independent warps
     int epb = 1, ft_threads = 32;      // feature kernel: epb envs x A agent warps per block
     cudaStream_t copy_stream = nullptr;   // device->host copies of the chunked host-buffer step
@@ -363,6 +364,8 @@ static int launch_cfg(mlb_env* h) {
     if (e == cudaSuccess) e = set_smem(feature_fn(c.servers_per_agent, h->ft_threads <= 128 && !getenv("MLB_FT_BIG")), h->ft_smem, h->ft_threads, h->ft_threads <= 128 ? 48 : 32);
     h->use_pair = h->d.KP == 128 && h->d.K == 128 && c.feature_cache == 1 && !getenv("MLB_NO_PAIR");
     h->d.use_pair = h->use_pair ? 1 : 0;
+    h->d.pair_wpe = 1;
+    h->pair_wpe_small = getenv("MLB_PAIR_WPE1") ? 1 : 4;    // A/B knob: 1 = never deal a list out to a block
     h->pr_smem = (size_t)4 * pair_warp_smem_bytes(SP);
     if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent, 0), h->pr_smem, 128, 32);
     if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent, 1), h->pr_smem, 128, 32);
@@ -882,7 +885,9 @@ static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_
     if (pe) CK(h, cudaEventRecord(pe[1], st));
     void* ft_args[] = {&dv};
     if (h->use_pair) {
-        const int pr_blocks = (int)(((int64_t)(e1 - e0) * dv.A + 3) / 4);
+        const int64_t pairs = (int64_t)(e1 - e0) * dv.A;
+        dv.pair_wpe = pairs <= 8192 ? h->pair_wpe_small : 1;
+        const int pr_blocks = (int)(dv.pair_wpe == 4 ? pairs : (pairs + 3) / 4);
         CK(h, cudaLaunchKernel(pair_fn(dv.Sa, 0), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
         CK(h, cudaLaunchKernel(pair_fn(dv.Sa, 1), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
         h->launches += 2;

@@ -17,6 +17,7 @@ struct DevState {
     int L;                 // words per MT19937 replay row
     int feature_cache, record_assign;
     int use_pair;          // pair_kernel evaluates the "fast" reservoirs before feature_kernel
+    int pair_wpe;          // warps per (env, agent) in pair_kernel: 1, or 4 (small launches: the list is dealt out to a block)
     int rng_mode;          // MLB_RNG_REPLAY (table rows of RandomState(seed_base + j)) or MLB_RNG_PHILOX (per env)
     uint32_t rng_key;      // philox mode: key word 0 (= rng_seed_base)
     int env_id_base;       // global id of env 0 (philox streams are keyed by the GLOBAL env id)

@@ -575,7 +575,11 @@ pair_kernel(const __grid_constant__ DevState d) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int A = d.A, Sa = d.Sa, S = d.S;
-    const int ea = d.e0 * A + blockIdx.x * (blockDim.x >> 5) + warp;
+    // Large launches: one warp per (env, agent).  Small ones (a few thousand envs: a fraction of a wave, where the time
+    // is one warp's walk through its list) deal the list of one (env, agent) out to the four warps of a block.
+    const int wpe = d.pair_wpe;
+    const int ea = d.e0 * A + (wpe == 1 ? blockIdx.x * (blockDim.x >> 5) + warp : (int)blockIdx.x);
+    const int sub = wpe == 1 ? 0 : warp;
     if (ea >= d.e1 * A) return;
     const int e = ea / A;
     const int agent = ea - e * A;
@@ -627,11 +631,13 @@ pair_kernel(const __grid_constant__ DevState d) {
         cp_async16(dst + 512, ts4 + off);
         cp_async4(dst + 1024 - lane * 12, rank4 + off);
     };
-    stage_in(dlist[0].y & 511u, 0);
-    if (nfast > 1) stage_in(dlist[1].y & 511u, 1);
+    const int i0 = 2 * sub, di = 2 * wpe;     // this warp takes the pairs i0, i0 + di, ...
+    if (i0 >= nfast) return;
+    stage_in(dlist[i0].y & 511u, 0);
+    if (i0 + 1 < nfast) stage_in(dlist[i0 + 1].y & 511u, 1);
     cp_async_commit();
 #pragma unroll 1
-    for (int i = 0; i < nfast; i += 2) {
+    for (int i = i0; i < nfast; i += di) {
         const bool valid = i + half < nfast;              // an odd list ends with half 1 idle
         const uint2 ent = dlist[valid ? i + half : i];
         const uint32_t id = ent.y & 511u;
@@ -642,9 +648,9 @@ pair_kernel(const __grid_constant__ DevState d) {
         const float4 t0 = reinterpret_cast<const float4*>(rec + 512)[hl * 2], t1q = reinterpret_cast<const float4*>(rec + 512)[hl * 2 + 1];
         const uint2 rq = reinterpret_cast<const uint2*>(rec + 1024)[hl];
         __syncwarp();
-        if (i + 2 < nfast) {
-            stage_in(dlist[i + 2].y & 511u, 0);
-            if (i + 3 < nfast) stage_in(dlist[i + 3].y & 511u, 1);
+        if (i + di < nfast) {
+            stage_in(dlist[i + di].y & 511u, 0);
+            if (i + di + 1 < nfast) stage_in(dlist[i + di + 1].y & 511u, 1);
             cp_async_commit();
         }
         const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
