@@ -65,6 +65,14 @@ int mlb_gemm_tc(const float *A, int64_t a_rs, int64_t a_cs, const float *B, int6
                 int64_t ldc, const float *bias, int32_t M, int32_t N, int32_t K, float beta, int32_t act,
                 void *stream);
 
+/* Split-K products (mlb_gemm, mlb_gemm_tc) keep their partial tiles in a per-device workspace.  Work issued on
+ * CONCURRENT streams must not share it: the calling host thread selects one of MLB_WS_SLOTS workspaces (default 0)
+ * for the products it issues from then on -- SAC_GRU_Agent.update_parameters runs the twin critics Q1 / Q2
+ * (sac_agent.py:193-207, 213-215: independent until the loss) on two streams with slots 0 / 1. */
+#define MLB_WS_SLOTS 4
+int mlb_set_workspace_slot(int32_t slot);
+int mlb_get_workspace_slot(void);
+
 /* nn.GRU single step, gate part (torch gate order r,z,n):
  *   gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (computed by mlb_gemm), both [M][3H];
  *   r = sigmoid(gi_r+gh_r), z = sigmoid(gi_z+gh_z), n = tanh(gi_n + r*gh_n), h' = (1-z)*n + z*h.

@@ -935,6 +935,15 @@ __global__ void replay_gather_kernel(ReplayPtrs r, const int64_t* __restrict__ i
     }
 }
 
+// Workspace slot of the calling host thread (split-K partial tiles): see mlb_set_workspace_slot in the header.
+static thread_local int g_ws_slot = 0;
+extern "C" int mlb_set_workspace_slot(int32_t slot) {
+    if (slot < 0 || slot >= MLB_WS_SLOTS) return MLB_EINVAL;
+    g_ws_slot = slot;
+    return MLB_OK;
+}
+extern "C" int mlb_get_workspace_slot(void) { return g_ws_slot; }
+
 extern "C" {
 
 int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_bs,
@@ -982,24 +991,25 @@ int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const flo
     }
     float* ws = nullptr;
     if (splits > 1) {
-        static float* ws_ptr[64] = {nullptr};
-        static size_t ws_cap[64] = {0};
+        static float* ws_ptr[64][MLB_WS_SLOTS] = {{nullptr}};
+        static size_t ws_cap[64][MLB_WS_SLOTS] = {{0}};
         int dev = 0;
         cudaGetDevice(&dev);
+        const int slot = mlb_get_workspace_slot();     // concurrent streams use different slots (mlb_set_workspace_slot)
         const size_t need = (size_t)splits * batch * M * N * sizeof(float);
-        if (dev < 64 && need > ws_cap[dev]) {
+        if (dev < 64 && need > ws_cap[dev][slot]) {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             cudaStreamIsCapturing((cudaStream_t)stream, &cs);
             if (cs == cudaStreamCaptureStatusNone) {
                 const size_t cap = std::max<size_t>(need, (size_t)32 << 20);
                 float* q = nullptr;
                 if (cudaMalloc(&q, cap) == cudaSuccess) {   // the old buffer may still be in use by queued work: keep it
-                    ws_ptr[dev] = q;
-                    ws_cap[dev] = cap;
+                    ws_ptr[dev][slot] = q;
+                    ws_cap[dev][slot] = cap;
                 }
             }
         }
-        if (dev < 64 && need <= ws_cap[dev]) ws = ws_ptr[dev]; else splits = 1;
+        if (dev < 64 && need <= ws_cap[dev][slot]) ws = ws_ptr[dev][slot]; else splits = 1;
     }
     grid.z = batch * splits;
     gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, a_bs, a_rs, a_cs, B, b_bs, b_rs, b_cs, C, c_bs, ldc,

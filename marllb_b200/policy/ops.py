@@ -65,6 +65,8 @@ def _L():
             "mlb_gru_seq_backward": [vp] * 8 + [i32] * 3 + [vp],
             "mlb_replay_push": [vp] * 13 + [i32] * 5 + [vp],
             "mlb_replay_gather": [vp] * 13 + [i32] * 4 + [vp],
+            "mlb_set_workspace_slot": [i32],
+            "mlb_get_workspace_slot": [],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -82,7 +84,8 @@ POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_g
                   "mlb_softmax_forward", "mlb_softmax_backward", "mlb_concat_onehot", "mlb_categorical",
                   "mlb_logprob_backward", "mlb_scatter_class", "mlb_td_lambda_targets", "mlb_reward_normalize",
                   "mlb_dsac_q_target", "mlb_weighted_sum_forward", "mlb_weighted_sum_backward",
-                  "mlb_replay_push", "mlb_replay_gather", "mlb_gru_seq_forward", "mlb_gru_seq_backward"]
+                  "mlb_replay_push", "mlb_replay_gather", "mlb_gru_seq_forward", "mlb_gru_seq_backward",
+                  "mlb_set_workspace_slot", "mlb_get_workspace_slot"]
 
 
 def _p(t):
@@ -90,6 +93,29 @@ def _p(t):
 
 
 LAUNCHES = 0   # kernels launched through this module (every op fetches the stream once per launch)
+
+
+class side_branch:
+    """`with side_branch(stream):` -- issue the enclosed ops on `stream`, concurrently with what the caller goes on to
+    issue on its own stream, with their own split-K workspace (mlb_set_workspace_slot).  The caller forks before
+    (stream.wait_stream(current)) and joins after (current.wait_stream(stream)); under stream capture both become
+    graph edges, so the two chains are parallel branches of the CUDA graph."""
+
+    def __init__(self, stream, slot=1):
+        self.stream, self.slot = stream, slot
+
+    def __enter__(self):
+        L = _L()
+        self._prev = L.mlb_get_workspace_slot()
+        check(L.mlb_set_workspace_slot(self.slot))
+        self._ctx = torch.cuda.stream(self.stream)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._ctx.__exit__(*exc)
+        _L().mlb_set_workspace_slot(self._prev)
+        return False
 
 
 def _st():

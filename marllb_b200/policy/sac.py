@@ -12,6 +12,8 @@ passed (parity tests pass the reference's draws).
 """
 from __future__ import annotations
 
+import contextlib
+import os
 import random
 from collections import deque
 from pathlib import Path
@@ -318,8 +320,16 @@ class SAC_GRU_Agent:
             self.alpha = torch.tensor([alpha], dtype=torch.float32, device=self.device)
             self.target_entropy = None
         self.replay_buffer = ReplayBuffer(capacity=buffer_size)
+        # Q2's passes of an update on a second stream, concurrently with Q1's (update_parameters); MLB_SAC_TWIN=0: one stream
+        self.twin_streams = os.environ.get("MLB_SAC_TWIN", "1") != "0"
+        self._twin = None
         self.total_steps = 0
         self.training_stats = {'q1_loss': [], 'q2_loss': [], 'policy_loss': [], 'alpha_loss': [], 'alpha': []}
+
+    def _twin_stream(self):
+        if self._twin is None:
+            self._twin = torch.cuda.Stream(device=self.device)
+        return self._twin
 
     def select_action(self, state, hidden, evaluate=False, eps=None):
         """sac_agent.py:124-149 -> (action numpy [action_dim], hidden_new [1,1,gru])."""
@@ -354,38 +364,65 @@ class SAC_GRU_Agent:
                 q_hidden = self.q1.init_hidden(B)
             else:
                 policy_hidden = q_hidden = hiddens                                    # sac_agent.py:171-172
+            # The twin critics are independent until their outputs meet (min(Q1', Q2') in the target, min(Q1, Q2) in the
+            # actor loss): every Q2 pass is issued on a second stream (`fork` .. `join`), concurrently with the Q1 pass
+            # on the caller's stream.  At batch 256 each network is a dependent chain of small kernels that leave most
+            # of the 148 SMs idle, so the two chains overlap almost entirely; inside a CUDA graph they become parallel
+            # branches.  Arithmetic and step order are unchanged (sac_agent.py:201-231: Q1 step, Q2 step, actor, alpha).
+            cur = torch.cuda.current_stream(self.device)
+            twin = self._twin_stream() if self.twin_streams else None
+
+            def fork():
+                if twin is not None:
+                    twin.wait_stream(cur)
+
+            def join():
+                if twin is not None:
+                    cur.wait_stream(twin)
+
+            branch = (lambda: ops.side_branch(twin)) if twin is not None else contextlib.nullcontext
             # ---- critic targets (no gradient), :175-190
             next_actions, next_logp, _, _ = self.policy.sample(next_states, policy_hidden, eps=eps_next)
+            fork()
+            with branch():
+                q2n, _ = self.q2_target.forward(next_states, next_actions, q_hidden)
             q1n, _ = self.q1_target.forward(next_states, next_actions, q_hidden)
-            q2n, _ = self.q2_target.forward(next_states, next_actions, q_hidden)
+            join()
             y = ops.sac_q_target(rewards.reshape(-1).contiguous(), dones.reshape(-1).contiguous(),
                                  q1n.reshape(-1), q2n.reshape(-1), next_logp.reshape(-1), self.alpha, self.gamma)
-            # ---- critics, :193-207.  Same step order as the reference (Q1 step, Q2 step, actor step, temperature
-            # step); under data parallelism each bucket's all-reduce starts on the side stream as soon as its
-            # backward pass is done and the optimiser step that consumes it is issued as late as the data
+            # ---- critics, :193-207.  Under data parallelism each bucket's all-reduce starts on the communication stream
+            # as soon as its backward pass is done and the optimiser step that consumes it is issued as late as the data
             # dependencies allow, so the collective overlaps the next network's forward / backward.
-            q_losses = []
-            q_cur, _ = self.q1.forward(states, actions, q_hidden, save=True)
-            loss, dq = ops.mse_loss(q_cur.reshape(-1), y)
+            fork()
+            with branch():
+                q_cur2, _ = self.q2.forward(states, actions, q_hidden, save=True)
+                loss2, dq = ops.mse_loss(q_cur2.reshape(-1), y)
+                self.q2.P.zero_grad()
+                self.q2.backward(dq)
+                self.q2_optimizer.reduce_async()
+            q_cur1, _ = self.q1.forward(states, actions, q_hidden, save=True)
+            loss1, dq = ops.mse_loss(q_cur1.reshape(-1), y)
             self.q1.P.zero_grad()
             self.q1.backward(dq)
             self.q1_optimizer.reduce_async()
-            q_losses.append(loss)
-            q_cur, _ = self.q2.forward(states, actions, q_hidden, save=True)        # overlaps Q1's all-reduce
-            loss, dq = ops.mse_loss(q_cur.reshape(-1), y)
-            self.q2.P.zero_grad()
-            self.q2.backward(dq)
-            self.q2_optimizer.reduce_async()
-            q_losses.append(loss)
+            join()
+            q_losses = [loss1, loss2]
             self.q1_optimizer.step()
             # ---- actor, :210-220
-            new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)   # overlaps Q2's
+            new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)   # overlaps Q2's all-reduce
             self.q2_optimizer.step()
+            fork()
+            with branch():
+                q2_new, _ = self.q2.forward(states, new_actions, q_hidden, save=True)
             q1_new, _ = self.q1.forward(states, new_actions, q_hidden, save=True)
-            q2_new, _ = self.q2.forward(states, new_actions, q_hidden, save=True)
+            join()
             p_loss, d_logp, dq1, dq2 = ops.sac_policy_loss(logp.reshape(-1), q1_new.reshape(-1), q2_new.reshape(-1), self.alpha)
+            fork()
+            with branch():
+                d_action2 = self.q2.backward(dq2, need_daction=True)
             d_action = self.q1.backward(dq1, need_daction=True)
-            ops.axpby(1.0, self.q2.backward(dq2, need_daction=True), 1.0, d_action)
+            join()
+            ops.axpby(1.0, d_action2, 1.0, d_action)
             self.policy.P.zero_grad()
             self.policy.backward(d_action, d_logp)
             self.policy_optimizer.reduce_async()
