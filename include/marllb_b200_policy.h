@@ -69,9 +69,12 @@ int mlb_gemm_tc(const float *A, int64_t a_rs, int64_t a_cs, const float *B, int6
  * CONCURRENT streams must not share it: the calling host thread selects one of MLB_WS_SLOTS workspaces (default 0)
  * for the products it issues from then on -- SAC_GRU_Agent.update_parameters runs the twin critics Q1 / Q2
  * (sac_agent.py:193-207, 213-215: independent until the loss) on two streams with slots 0 / 1. */
-#define MLB_WS_SLOTS 4
+#define MLB_WS_SLOTS 8
 int mlb_set_workspace_slot(int32_t slot);
 int mlb_get_workspace_slot(void);
+/* Give slots 1 .. n_slots-1 the capacity slot 0 has reached on the current device (nothing can be allocated inside a
+ * stream capture): call after an eager warm-up of the same code on one stream. */
+int mlb_reserve_workspace_slots(int32_t n_slots);
 
 /* nn.GRU single step, gate part (torch gate order r,z,n):
  *   gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (computed by mlb_gemm), both [M][3H];

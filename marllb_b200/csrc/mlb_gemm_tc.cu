@@ -33,6 +33,8 @@
 #include "../../include/marllb_b200_policy.h"
 #include "mlb_tc_common.cuh"
 
+extern "C" float* mlb_workspace_get(int kind, size_t need, void* stream);   // mlb_policy.cu
+
 namespace {
 using namespace mlb_tc;
 
@@ -325,28 +327,8 @@ size_t smem_bytes(int NT) {
     return RAW_STAGES * (a + b) + OP_STAGES * 2 * (a + b) + 8 * (2 * RAW_STAGES + 2 * OP_STAGES + 6) + 1024;
 }
 
-// per-device, per-slot workspace for partial tiles, grown outside stream capture only (like mlb_gemm's).  The slot
-// (mlb_set_workspace_slot) keeps products issued on concurrent streams apart: the twin critics of the SAC update run on
-// two streams, each with its own slot.
-float* workspace(size_t need, cudaStream_t stream) {
-    static float* ws_ptr[64][MLB_WS_SLOTS] = {{nullptr}};
-    static size_t ws_cap[64][MLB_WS_SLOTS] = {{0}};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int slot = mlb_get_workspace_slot();
-    if (dev >= 64) return nullptr;
-    if (need > ws_cap[dev][slot]) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(stream, &cs);
-        if (cs != cudaStreamCaptureStatusNone) return nullptr;
-        const size_t cap = std::max<size_t>(need, (size_t)64 << 20);
-        float* q = nullptr;
-        if (cudaMalloc(&q, cap) != cudaSuccess) return nullptr;   // the old buffer may still be in use by queued work: keep it
-        ws_ptr[dev][slot] = q;
-        ws_cap[dev][slot] = cap;
-    }
-    return ws_ptr[dev][slot];
-}
+// per-device, per-slot workspace for partial tiles (mlb_policy.cu: mlb_workspace_get), grown outside stream capture only
+float* workspace(size_t need, cudaStream_t stream) { return mlb_workspace_get(1, need, stream); }
 
 }  // namespace
 

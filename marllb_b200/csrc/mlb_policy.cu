@@ -3,6 +3,7 @@
 // Reference modules: problem-05-qmix/src/{agent_network,mixing_network,qmix_agent}.py and
 // problem-04-sac-gru/src/{networks,sac_agent}.py (paths under simulation-mode/).
 #include <algorithm>
+#include <mutex>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -944,6 +945,46 @@ extern "C" int mlb_set_workspace_slot(int32_t slot) {
 }
 extern "C" int mlb_get_workspace_slot(void) { return g_ws_slot; }
 
+// Split-K workspaces: [kind: 0 = FFMA gemm_kernel, 1 = gemm_tc_kernel][device][slot], grown outside stream capture only
+// (cudaMalloc is not capturable); an outgrown buffer is left alone, queued work may still use it.
+static float* g_ws_ptr[2][64][MLB_WS_SLOTS];
+static size_t g_ws_cap[2][64][MLB_WS_SLOTS];
+static std::mutex g_ws_mu;
+static float* ws_grow(int kind, int dev, int slot, size_t need, void* stream) {
+    if (need <= g_ws_cap[kind][dev][slot]) return g_ws_ptr[kind][dev][slot];
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return nullptr;
+    const size_t cap = std::max<size_t>(need, (size_t)(kind ? 64 : 32) << 20);
+    float* q = nullptr;
+    if (cudaMalloc(&q, cap) != cudaSuccess) return nullptr;
+    g_ws_ptr[kind][dev][slot] = q;
+    g_ws_cap[kind][dev][slot] = cap;
+    return q;
+}
+extern "C" float* mlb_workspace_get(int kind, size_t need, void* stream) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || kind < 0 || kind > 1) return nullptr;
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    return ws_grow(kind, dev, g_ws_slot, need, stream);
+}
+// Give slots 1 .. n_slots-1 of the current device the capacity slot 0 has reached, so that work that moves to side
+// streams INSIDE a stream capture (where nothing can be allocated) finds its workspace: call after an eager warm-up
+// of the same code on one stream.
+extern "C" int mlb_reserve_workspace_slots(int32_t n_slots) {
+    if (n_slots < 1 || n_slots > MLB_WS_SLOTS) return MLB_EINVAL;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64) return MLB_EINVAL;
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (int kind = 0; kind < 2; kind++)
+        for (int s = 1; s < n_slots; s++)
+            if (g_ws_cap[kind][dev][0] > g_ws_cap[kind][dev][s] && !ws_grow(kind, dev, s, g_ws_cap[kind][dev][0], nullptr))
+                return MLB_ENOMEM;
+    return MLB_OK;
+}
+
 extern "C" {
 
 int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_bs,
@@ -991,25 +1032,8 @@ int mlb_gemm(const float* A, int64_t a_bs, int64_t a_rs, int64_t a_cs, const flo
     }
     float* ws = nullptr;
     if (splits > 1) {
-        static float* ws_ptr[64][MLB_WS_SLOTS] = {{nullptr}};
-        static size_t ws_cap[64][MLB_WS_SLOTS] = {{0}};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const int slot = mlb_get_workspace_slot();     // concurrent streams use different slots (mlb_set_workspace_slot)
-        const size_t need = (size_t)splits * batch * M * N * sizeof(float);
-        if (dev < 64 && need > ws_cap[dev][slot]) {
-            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-            cudaStreamIsCapturing((cudaStream_t)stream, &cs);
-            if (cs == cudaStreamCaptureStatusNone) {
-                const size_t cap = std::max<size_t>(need, (size_t)32 << 20);
-                float* q = nullptr;
-                if (cudaMalloc(&q, cap) == cudaSuccess) {   // the old buffer may still be in use by queued work: keep it
-                    ws_ptr[dev][slot] = q;
-                    ws_cap[dev][slot] = cap;
-                }
-            }
-        }
-        if (dev < 64 && need <= ws_cap[dev][slot]) ws = ws_ptr[dev][slot]; else splits = 1;
+        ws = mlb_workspace_get(0, (size_t)splits * batch * M * N * sizeof(float), stream);
+        if (!ws) splits = 1;
     }
     grid.z = batch * splits;
     gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, a_bs, a_rs, a_cs, B, b_bs, b_rs, b_cs, C, c_bs, ldc,

@@ -234,10 +234,48 @@ class Adam:
         self._t_dev.fill_(self.t)
 
 
+class wgrad_on:
+    """`with wgrad_on(stream, slot):` -- backward passes issued inside put their PARAMETER-gradient kernels (dW = dy^T x,
+    db = colsum(dy)) on `stream`, off the chain that carries the input gradient from layer to layer: nothing downstream
+    in the pass reads them, and at update batch sizes each is a small launch that would otherwise sit on the critical
+    path.  The operands are kept alive until the join at scope exit (their blocks belong to the issuing stream's
+    allocator pool and must not be recycled while the side stream still reads them)."""
+    active = None
+
+    def __init__(self, stream, slot):
+        self.stream, self.slot, self.keep = stream, slot, []
+
+    def __enter__(self):
+        self._outer, wgrad_on.active = wgrad_on.active, self
+        return self
+
+    def __exit__(self, *exc):
+        wgrad_on.active = self._outer
+        torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+        self.keep.clear()
+        return False
+
+    def run(self, fn, *operands):
+        self.stream.wait_stream(torch.cuda.current_stream(self.stream.device))
+        with ops.side_branch(self.stream, self.slot):
+            fn()
+        self.keep.append(operands)
+
+
+def _param_grads(fn, *operands):
+    w = wgrad_on.active
+    if w is None:
+        fn()
+    else:
+        w.run(fn, *operands)
+
+
 def linear_backward(P, wname, bname, x, dy, need_dx=True):
     """Accumulate dW += dy^T x, db += colsum(dy); return dx = dy W (x, dy 2-D)."""
-    ops.matmul_tn(dy, x, out=P.g[wname], beta=1.0)
-    ops.colsum(dy, out=P.g[bname], beta=1.0)
+    def grads():
+        ops.matmul_tn(dy, x, out=P.g[wname], beta=1.0)
+        ops.colsum(dy, out=P.g[bname], beta=1.0)
+    _param_grads(grads, dy, x)
     return ops.matmul_nn(dy, P.p[wname]) if need_dx else None
 
 
@@ -310,9 +348,12 @@ class GRUCellSeq:
         T, B, H = hprev.shape
         In = xs.shape[-1]
         dgi2, dgh2 = dgi_all.reshape(T * B, 3 * H), dgh_all.reshape(T * B, 3 * H)
-        ops.matmul_tn(dgi2, xs.reshape(T * B, In), out=P.g[k + "weight_ih_l0"], beta=1.0)
-        ops.colsum(dgi2, out=P.g[k + "bias_ih_l0"], beta=1.0)
-        ops.matmul_tn(dgh2, hprev.reshape(T * B, H), out=P.g[k + "weight_hh_l0"], beta=1.0)
-        ops.colsum(dgh2, out=P.g[k + "bias_hh_l0"], beta=1.0)
+
+        def grads():
+            ops.matmul_tn(dgi2, xs.reshape(T * B, In), out=P.g[k + "weight_ih_l0"], beta=1.0)
+            ops.colsum(dgi2, out=P.g[k + "bias_ih_l0"], beta=1.0)
+            ops.matmul_tn(dgh2, hprev.reshape(T * B, H), out=P.g[k + "weight_hh_l0"], beta=1.0)
+            ops.colsum(dgh2, out=P.g[k + "bias_hh_l0"], beta=1.0)
+        _param_grads(grads, dgi_all, dgh_all, xs, hprev)
         dxs = ops.matmul_nn(dgi2, P.p[k + "weight_ih_l0"]).reshape(T, B, In) if need_dx else None
         return dxs, dh_next

@@ -67,6 +67,7 @@ def _L():
             "mlb_replay_gather": [vp] * 13 + [i32] * 4 + [vp],
             "mlb_set_workspace_slot": [i32],
             "mlb_get_workspace_slot": [],
+            "mlb_reserve_workspace_slots": [i32],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -85,7 +86,7 @@ POLICY_EXPORTS = ["mlb_gemm", "mlb_linear_tc_supported", "mlb_linear_tc", "mlb_g
                   "mlb_logprob_backward", "mlb_scatter_class", "mlb_td_lambda_targets", "mlb_reward_normalize",
                   "mlb_dsac_q_target", "mlb_weighted_sum_forward", "mlb_weighted_sum_backward",
                   "mlb_replay_push", "mlb_replay_gather", "mlb_gru_seq_forward", "mlb_gru_seq_backward",
-                  "mlb_set_workspace_slot", "mlb_get_workspace_slot"]
+                  "mlb_set_workspace_slot", "mlb_get_workspace_slot", "mlb_reserve_workspace_slots"]
 
 
 def _p(t):
@@ -116,6 +117,12 @@ class side_branch:
         self._ctx.__exit__(*exc)
         _L().mlb_set_workspace_slot(self._prev)
         return False
+
+
+def reserve_workspace_slots(n):
+    """Slots 1 .. n-1 get the capacity slot 0 has reached (call after an eager single-stream warm-up; nothing can be
+    allocated once a stream capture is running)."""
+    check(_L().mlb_reserve_workspace_slots(n))
 
 
 def _st():

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .nn import Adam, FlatBucket, GRUCellSeq, Params, linear_backward
+from .nn import Adam, FlatBucket, GRUCellSeq, Params, linear_backward, wgrad_on
 from .qmix import _device
 
 
@@ -320,16 +320,24 @@ class SAC_GRU_Agent:
             self.alpha = torch.tensor([alpha], dtype=torch.float32, device=self.device)
             self.target_entropy = None
         self.replay_buffer = ReplayBuffer(capacity=buffer_size)
-        # Q2's passes of an update on a second stream, concurrently with Q1's (update_parameters); MLB_SAC_TWIN=0: one stream
-        self.twin_streams = os.environ.get("MLB_SAC_TWIN", "1") != "0"
+        # update_parameters on several streams (Q2's passes beside Q1's, parameter gradients beside the input-gradient
+        # chain, the actor's forward beside the critic steps).  "graph" (default): only while the update is being
+        # captured into a CUDA graph, where the streams become parallel branches -- launched eagerly the update is bound
+        # by Python launch overhead and the stream switches only add to it; "always"; "off".  MLB_SAC_TWIN = 0 / 1 / 2.
+        self.twin_streams = {"0": "off", "1": "graph", "2": "always"}.get(os.environ.get("MLB_SAC_TWIN", "1"), "graph")
         self._twin = None
         self.total_steps = 0
         self.training_stats = {'q1_loss': [], 'q2_loss': [], 'policy_loss': [], 'alpha_loss': [], 'alpha': []}
 
     def _twin_stream(self):
+        return self._aux_stream(0)
+
+    def _aux_stream(self, k):
+        """Side streams of update_parameters: 0 = Q2's passes, 1 / 2 = parameter gradients of the pass on the caller's
+        stream / on stream 0, 3 = the actor's forward for the new actions."""
         if self._twin is None:
-            self._twin = torch.cuda.Stream(device=self.device)
-        return self._twin
+            self._twin = [torch.cuda.Stream(device=self.device) for _ in range(4)]
+        return self._twin[k]
 
     def select_action(self, state, hidden, evaluate=False, eps=None):
         """sac_agent.py:124-149 -> (action numpy [action_dim], hidden_new [1,1,gru])."""
@@ -370,7 +378,8 @@ class SAC_GRU_Agent:
             # of the 148 SMs idle, so the two chains overlap almost entirely; inside a CUDA graph they become parallel
             # branches.  Arithmetic and step order are unchanged (sac_agent.py:201-231: Q1 step, Q2 step, actor, alpha).
             cur = torch.cuda.current_stream(self.device)
-            twin = self._twin_stream() if self.twin_streams else None
+            multi = self.twin_streams == "always" or (self.twin_streams == "graph" and torch.cuda.is_current_stream_capturing())
+            twin = self._twin_stream() if multi else None
 
             def fork():
                 if twin is not None:
@@ -381,8 +390,17 @@ class SAC_GRU_Agent:
                     cur.wait_stream(twin)
 
             branch = (lambda: ops.side_branch(twin)) if twin is not None else contextlib.nullcontext
+            wg1 = (lambda: wgrad_on(self._aux_stream(1), 2)) if twin is not None else contextlib.nullcontext
+            wg2 = (lambda: wgrad_on(self._aux_stream(2), 3)) if twin is not None else contextlib.nullcontext
             # ---- critic targets (no gradient), :175-190
             next_actions, next_logp, _, _ = self.policy.sample(next_states, policy_hidden, eps=eps_next)
+            # the actor's forward for the new actions (:211) depends on nothing the critic steps change: it runs on its
+            # own stream from here (same draw order: next-state noise first) and is joined before the actor's critic passes
+            pol = self._aux_stream(3) if twin is not None else None
+            if pol is not None:
+                pol.wait_stream(cur)
+                with ops.side_branch(pol, 4):
+                    new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)
             fork()
             with branch():
                 q2n, _ = self.q2_target.forward(next_states, next_actions, q_hidden)
@@ -398,18 +416,23 @@ class SAC_GRU_Agent:
                 q_cur2, _ = self.q2.forward(states, actions, q_hidden, save=True)
                 loss2, dq = ops.mse_loss(q_cur2.reshape(-1), y)
                 self.q2.P.zero_grad()
-                self.q2.backward(dq)
+                with wg2():
+                    self.q2.backward(dq)
                 self.q2_optimizer.reduce_async()
             q_cur1, _ = self.q1.forward(states, actions, q_hidden, save=True)
             loss1, dq = ops.mse_loss(q_cur1.reshape(-1), y)
             self.q1.P.zero_grad()
-            self.q1.backward(dq)
+            with wg1():
+                self.q1.backward(dq)
             self.q1_optimizer.reduce_async()
             join()
             q_losses = [loss1, loss2]
             self.q1_optimizer.step()
             # ---- actor, :210-220
-            new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)   # overlaps Q2's all-reduce
+            if pol is None:
+                new_actions, logp, _, _ = self.policy.sample(states, policy_hidden, eps=eps_new, save=True)   # overlaps Q2's all-reduce
+            else:
+                cur.wait_stream(pol)
             self.q2_optimizer.step()
             fork()
             with branch():
@@ -419,12 +442,15 @@ class SAC_GRU_Agent:
             p_loss, d_logp, dq1, dq2 = ops.sac_policy_loss(logp.reshape(-1), q1_new.reshape(-1), q2_new.reshape(-1), self.alpha)
             fork()
             with branch():
-                d_action2 = self.q2.backward(dq2, need_daction=True)
-            d_action = self.q1.backward(dq1, need_daction=True)
+                with wg2():
+                    d_action2 = self.q2.backward(dq2, need_daction=True)
+            with wg1():
+                d_action = self.q1.backward(dq1, need_daction=True)
             join()
             ops.axpby(1.0, d_action2, 1.0, d_action)
             self.policy.P.zero_grad()
-            self.policy.backward(d_action, d_logp)
+            with wg1():
+                self.policy.backward(d_action, d_logp)
             self.policy_optimizer.reduce_async()
             # ---- temperature, :223-231 (its 4-byte gradient rides along; both overlap the soft updates below)
             a_loss = None
@@ -447,6 +473,8 @@ class SAC_GRU_Agent:
             if a_loss is not None:
                 losses['alpha'] = losses['alpha'] + conv(a_loss)
             self.total_steps += 1
+            if twin is None and self.twin_streams == "graph":
+                ops.reserve_workspace_slots(5)      # a later capture of this update finds its side streams' split-K workspaces
         for k in losses:
             losses[k] = losses[k] / updates
         if not sync_stats:
