@@ -695,13 +695,9 @@ def run_ours(args):
     wl = dict(WORKLOADS[args.workload])
     res = measure(args, args.workload, world, rank, local, main=True)
     configs = {}
-    if not args.no_configs and args.workload == "c5":
-        for name in ("c2", "c3", "c4"):
-            r = measure(args, name, world, rank, local, main=False)
-            if rank == 0:
-                r["config"] = workload_config(args, WORKLOADS[name], world, name)["workload"]
-                configs[name] = r
-    if rank == 0:
+
+    def emit():
+        """The ONE JSON line (rank 0), from whatever has been measured so far."""
         out = {
             "metric": "agent-steps/sec", "value": res["value"], "unit": "agent-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -712,11 +708,36 @@ def run_ours(args):
         if configs:
             # the other BASELINE.json configurations at the same N (short runs; c4 is the one with a collective:
             # SAC update sharded over the GPUs, NCCL all-reduce of the gradient buckets inside the CUDA graph)
-            out["configs"] = configs
-        nccl_log = os.environ.get("NCCL_DEBUG_FILE")
+            out["configs"] = dict(configs)
         if world > 1:
             out["nccl"] = {"nranks": world, "version": ".".join(map(str, torch.cuda.nccl.version())),
-                           "debug": os.environ.get("NCCL_DEBUG"), "log": nccl_log}
+                           "debug": os.environ.get("NCCL_DEBUG"), "log": os.environ.get("NCCL_DEBUG_FILE")}
+        return out
+
+    if not args.no_configs and args.workload == "c5":
+        # dead-man switch for the side configurations: they must never cost the headline line.  If one of them does
+        # not come back (a collective that hangs on a sick link, say) the line goes out without it and every rank exits.
+        current = {"name": None}
+
+        def give_up():
+            if rank == 0:
+                configs[current["name"]] = {"error": f"did not finish within {args.config_deadline:.0f} s; skipped"}
+                print(json.dumps(emit()))
+                sys.stdout.flush()
+            os._exit(0)
+
+        for name in ("c2", "c3", "c4"):
+            current["name"] = name
+            dog = threading.Timer(args.config_deadline, give_up)
+            dog.daemon = True
+            dog.start()
+            r = measure(args, name, world, rank, local, main=False)
+            dog.cancel()
+            if rank == 0:
+                r["config"] = workload_config(args, WORKLOADS[name], world, name)["workload"]
+                configs[name] = r
+    if rank == 0:
+        out = emit()
         if world == 1 and not args.no_cpu and wl.get("policy") is None:
             if prev_affinity is not None:
                 os.sched_setaffinity(0, prev_affinity)       # the CPU baseline uses every host core
@@ -750,6 +771,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the short c2 / c3 / c4 runs of the `configs` sub-dict")
     ap.add_argument("--config-steps", type=int, default=30)
     ap.add_argument("--config-burnin", type=int, default=160)
+    ap.add_argument("--config-deadline", type=float, default=150.0,
+                    help="seconds after which a side configuration (c2 / c3 / c4) is abandoned and the line printed without it")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-feature-cache", action="store_true")
