@@ -13,6 +13,8 @@ block.  `strict_reference=False` gathers each agent's own Q.
 """
 from __future__ import annotations
 
+import contextlib
+import os
 import random
 from collections import deque
 from pathlib import Path
@@ -376,6 +378,10 @@ class QMIXAgent:
         self.episode_buffer = EpisodeBuffer(capacity=buffer_capacity, num_agents=num_agents)
         self.graph_updates = False      # True: replay the device part of update() as a CUDA graph
         self._graphs = {}
+        # inside a stream capture the per-agent chains of update() (online and target forwards, backwards) are issued on
+        # several streams = parallel branches of the graph (MLB_QMIX_BRANCHES=0: one stream); eager updates use one stream
+        self.parallel_branches = os.environ.get("MLB_QMIX_BRANCHES", "1") != "0"
+        self._aux = None
         self.total_updates = 0
         self.training_stats = {'loss': [], 'q_tot': [], 'target_q_tot': []}
 
@@ -466,6 +472,8 @@ class QMIXAgent:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             self._restore(snap)
+            if self.parallel_branches:
+                ops.reserve_workspace_slots(4)      # split-K workspaces of the side lanes (nothing can be allocated in a capture)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._update_device(*static)
@@ -494,8 +502,39 @@ class QMIXAgent:
         B, T, A, _ = obs.shape
         K = self.action_dim
         obs_tb = obs.permute(2, 1, 0, 3).contiguous()                                 # [A,T,B,obs] time-major per agent
+        # The 2A forward chains (online and target network of every agent) and the A backward chains are independent of
+        # each other and each keeps only a handful of SMs busy (the GRU time loop of B = 32 episodes is 8 thread blocks):
+        # while the update is being captured they go to separate streams ("lanes"), i.e. parallel branches of the graph.
+        cur = torch.cuda.current_stream(dev)
+        multi = self.parallel_branches and torch.cuda.is_current_stream_capturing()
+        if multi and self._aux is None:
+            self._aux = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        lanes = [None] + self._aux if multi else [None]
+        L = len(lanes)
+        on = lambda i: ops.side_branch(lanes[i % L], i % L) if lanes[i % L] is not None else contextlib.nullcontext()
+
+        def fork():
+            for st in lanes[1:]:
+                st.wait_stream(cur)
+
+        def join():
+            for st in lanes[1:]:
+                cur.wait_stream(st)
+
+        fork()
         # online Q for every agent and timestep (:215-229)
-        qs = [self.agent_networks[a].forward_seq(obs_tb[a]) for a in range(A)]        # each [T,B,K]
+        qs = [None] * A
+        for a in range(A):
+            with on(a):
+                qs[a] = self.agent_networks[a].forward_seq(obs_tb[a])                 # each [T,B,K]
+        # target networks (:244-253), no gradient
+        tmax = [None] * A
+        for a in range(A):
+            with on(A + a):
+                tq = self.agent_networks_target[a].forward_seq(obs_tb[a], save=False)     # [T,B,K]
+                m, _ = ops.row_max(tq.reshape(T * B, K))
+                tmax[a] = m.reshape(T, B)
+        join()
         q_all = torch.stack(qs, 0).permute(2, 1, 0, 3).contiguous()                   # [B,T,A,K]
         idx = actions[:, :, :, 0]                                                     # [B,T,A]
         if self.strict_reference:
@@ -506,12 +545,7 @@ class QMIXAgent:
         chosen = chosen.contiguous()
         states2 = states.reshape(B * T, -1).contiguous()
         q_tot = self.mixer.forward(chosen.reshape(B * T, A), states2, save=True).reshape(B, T).contiguous()
-        # targets (:244-268), no gradient
-        tmax = []
-        for a in range(A):
-            tq = self.agent_networks_target[a].forward_seq(obs_tb[a], save=False)     # [T,B,K]
-            m, _ = ops.row_max(tq.reshape(T * B, K))
-            tmax.append(m.reshape(T, B))
+        # targets (:254-268)
         target_agent_qs = torch.stack(tmax, 0).permute(2, 1, 0).contiguous()          # [B,T,A]
         target_q_tot = self.mixer_target.forward(target_agent_qs.reshape(B * T, A), states2).reshape(B, T).contiguous()
         # reward sum over agents: a [B*T, A] x ones GEMM (rewards.sum(dim=2), :267)
@@ -528,8 +562,11 @@ class QMIXAgent:
         else:
             dq_all.scatter_add_(3, idx.unsqueeze(-1), dchosen.unsqueeze(-1))
         dq_tb = dq_all.permute(2, 1, 0, 3).contiguous()                               # [A,T,B,K]
+        fork()
         for a in range(A):
-            self.agent_networks[a].backward_seq(dq_tb[a])
+            with on(a):                        # the lane that holds this agent's tape
+                self.agent_networks[a].backward_seq(dq_tb[a])
+        join()
         self.optimizer.step()                                                         # all-reduce, clip 10 (:284), Adam
         return stats
 
