@@ -45,6 +45,9 @@ WORKLOADS = {
     # config C4 (per-GPU slice): one SAC-GRU learner over 1024 envs x 256 servers, actor inference + env step +
     # one SAC update (batch 256, device replay) per step; with N > 1 the gradient buckets are all-reduced over NCCL
     "c4": dict(envs=1024, agents=1, servers=256, rate=512.0, K=128, policy="sac"),
+    # the same work per step with the SAC update as a graph branch BESIDE the env step (SACRollout.capture(overlap=True):
+    # the update's batch is drawn from the replay ring as it stood before this step's push)
+    "c4p": dict(envs=1024, agents=1, servers=256, rate=512.0, K=128, policy="sac", overlap=True),
 }
 RHO = 0.8
 DT = 0.25
@@ -229,7 +232,8 @@ def run_reference(args):
 
 def workload_config(args, wl, world=None, name=None):
     pol = {"qmix": "QMIX epsilon-greedy action selection (eps=0.05) fused with the env step",
-           "sac": "SAC-GRU actor sampling + env step + one SAC update (batch 256) per step",
+           "sac": "SAC-GRU actor sampling + env step + one SAC update (batch 256) per step"
+                  + (" (update pipelined beside the env step)" if wl.get("overlap") else ""),
            None: "random policy"}[wl.get("policy")]
     return {"workload": f"{name or args.workload}: {wl['envs']} envs/GPU x {wl['agents']} LB agent x {wl['servers']} servers, "
                         f"K={wl['K']}-slot reservoirs, Poisson {wl['rate']:.0f} flows/s/agent, rho={RHO}, {pol}, SED",
@@ -379,7 +383,7 @@ def measure(args, name, world, rank, local, main):
         for k in range(10):
             do_step(k)
         prof_eager = env.profile_end()
-        sac.capture(1)          # under data parallelism the NCCL all-reduces are captured with it
+        sac.capture(1, overlap=bool(wl.get("overlap")))   # under data parallelism the NCCL all-reduces are captured with it
         graphed = True
 
     def timed_window(n_steps):
@@ -726,7 +730,7 @@ def run_ours(args):
                 sys.stdout.flush()
             os._exit(0)
 
-        for name in ("c2", "c3", "c4"):
+        for name in ("c2", "c3", "c4", "c4p"):
             current["name"] = name
             dog = threading.Timer(args.config_deadline, give_up)
             dog.daemon = True

@@ -173,8 +173,41 @@ class SACRollout:
         return out
 
     # ---- CUDA graph: actor sampling + env step + replay push + one SAC update = one graph launch
-    def capture(self, updates=1, warmup=2):
-        """Capture `step(); update(updates)` into a CUDA graph.  Under data parallelism the NCCL all-reduces of
+    def _step_overlapped(self, updates):
+        """One step with the update beside the env step (capture(overlap=True)).  What depends on what:
+        the actor reads the policy parameters the update will overwrite -> the update starts after the actor forward;
+        the update's batch is gathered from the ring BEFORE this step's transitions are pushed (the push waits for
+        the gather), i.e. it samples the transitions of steps < t where the sequential order samples steps <= t;
+        the next step's actor uses the parameters this update leaves behind, exactly as in the sequential order."""
+        dev = self.env.device
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, "_upd_stream", None) is None:
+            self._upd_stream = torch.cuda.Stream(device=dev)
+        upd = self._upd_stream
+        self._state.copy_(self.env.obs.view(self.E, self.S * 11))      # obs is overwritten by the env step
+        action, h_new = self.agent.select_action_batch(self._state, self.hidden)
+        action = action.contiguous()
+        upd.wait_stream(cur)
+        with torch.cuda.stream(upd):
+            batch = self.replay.sample(self.agent.batch_size)
+            gathered = torch.cuda.Event()
+            gathered.record(upd)
+            losses = None
+            for _ in range(updates):
+                losses = self.agent.update_parameters(1, batch=batch, sync_stats=False)
+                if updates > 1:
+                    batch = self.replay.sample(self.agent.batch_size)
+        obs, rew, done = self.env.step(action)
+        cur.wait_event(gathered)
+        self.replay.push_batch(self._state, action, rew, obs.view(self.E, self.S * 11), done, self.hidden[0])
+        self.hidden = h_new
+        cur.wait_stream(upd)
+        return (obs, rew, done, action), losses
+
+    def capture(self, updates=1, warmup=2, overlap=False):
+        """Capture `step(); update(updates)` into a CUDA graph.  overlap=True: the update runs BESIDE the env step as a
+        parallel branch of the graph (see _step_overlapped: same work per step, the batch is drawn from the ring as it
+        stood before this step's push).  Under data parallelism the NCCL all-reduces of
         the four gradient buckets are captured too (side-stream fork / join, policy/nn.py:Adam.reduce_async): every
         rank replays its graph once per step, in lock-step, so the collectives match up.  Needs a FULL replay
         ring (the sampling range is fixed at capture) -- run at least capacity / num_envs eager steps first (they
@@ -187,6 +220,11 @@ class SACRollout:
 
         def body():
             self.hidden = self._h_static
+            if overlap:
+                out, losses = self._step_overlapped(updates)
+                self._h_static.copy_(self.hidden)
+                self.hidden = self._h_static
+                return out, losses
             out = self.step()
             self._h_static.copy_(self.hidden)
             self.hidden = self._h_static

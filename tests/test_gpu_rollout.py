@@ -105,3 +105,46 @@ def test_sac_rollout_device_replay_and_update():
     out = ro.update(2, g)
     assert set(out) == {"q1", "q2", "policy", "alpha"} and all(np.isfinite(list(out.values())))
     assert not torch.equal(p0, agent.policy.state_dict()["fc1.weight"])
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_sac_rollout_graph_sequential_and_pipelined(overlap):
+    """SACRollout.capture(): actor + env step + replay push + SAC update replayed from one CUDA graph.  overlap=True puts
+    the update beside the env step (its batch is gathered before this step's push).  Either way: the ring keeps
+    receiving the newest transitions, the learner moves, losses stay finite, the env stays healthy, and two identical
+    runs end bit-identical (the branches of the graph do not race)."""
+    from marllb_b200 import VecLoadBalanceEnv
+    from marllb_b200.policy import SAC_GRU_Agent
+    from marllb_b200.rollout import SACRollout
+    E, S, CAP = 64, 16, 256
+
+    def run():
+        env = VecLoadBalanceEnv(E, num_servers=S, action_type="continuous", max_steps=10 ** 6)
+        env.set_speeds(np.where(np.arange(S) % 2 == 0, 1.0, 2.0).astype(np.float32))
+        env.gen_poisson(64.0, 0.8 * 1.5 * S / 64.0, 20.0, seed=5)
+        env.reset()
+        torch.manual_seed(3)
+        agent = SAC_GRU_Agent(state_dim=S * 11, action_dim=S, hidden_dim=64, gru_dim=32, batch_size=64)
+        ro = SACRollout(env, agent, replay_capacity=CAP)
+        for _ in range(CAP // E):                       # fill the ring eagerly (capture needs a full ring)
+            ro.step()
+        ro.capture(1, overlap=overlap)
+        p0 = agent.policy.state_dict()["fc1.weight"].clone()
+        for k in range(12):
+            state_before = env.obs.clone().view(E, S * 11)
+            (o, r, d, a), losses = ro.step_graph()
+            assert bool((a.abs() <= 1).all()) and all(bool(torch.isfinite(v)) for v in losses.values())
+            # the transitions of this step are in the ring (the device-held write position advanced by E)
+            assert bool((ro.replay.state.view(CAP // E, E, -1) == state_before).all(-1).all(-1).any()), k
+            assert bool((ro.replay.next_state.view(CAP // E, E, -1) == o.view(E, S * 11)).all(-1).all(-1).any()), k
+        torch.cuda.synchronize()
+        env.check_status()
+        assert int(env.get_state("step")[0]) == CAP // E + 2 + 12          # fill + capture warm-up + replays
+        assert not torch.equal(p0, agent.policy.state_dict()["fc1.weight"])
+        out = (agent.policy.state_dict()["fc1.weight"].clone(), agent.q1.state_dict()["fc2.weight"].clone(), o.clone())
+        del ro._graph
+        env.close()
+        return out
+    a_, b_ = run(), run()
+    for x, y in zip(a_, b_):
+        assert torch.equal(x, y)
