@@ -774,7 +774,7 @@ def main():
                     help="second timed window after this many steps of the episode (0: skip)")
     ap.add_argument("--no-configs", action="store_true", help="skip the short c2 / c3 / c4 runs of the `configs` sub-dict")
     ap.add_argument("--config-steps", type=int, default=30)
-    ap.add_argument("--config-burnin", type=int, default=160)
+    ap.add_argument("--config-burnin", type=int, default=256)
     ap.add_argument("--config-deadline", type=float, default=150.0,
                     help="seconds after which a side configuration (c2 / c3 / c4) is abandoned and the line printed without it")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
