@@ -53,6 +53,10 @@ struct mlb_env {
     size_t ev_smem = 0, ft_smem = 0, pr_smem = 0;   // dynamic shared memory of the event / feature / pair kernel
     bool use_pair = false;             // pair_kernel applies (128-slot reservoirs, feature cache on)
     int pair_wpe_small = 4;            // warps per (env, agent) in pair_kernel for launches of <= 8192 (env, agent) pairs
+    // small launches: pair_kernel<.,1> runs BESIDE pair_kernel<.,0> (disjoint reservoirs) on this stream -- under a
+    // stream capture a parallel branch of the graph; at those sizes each launch is one warp's latency chain
+    cudaStream_t pair_stream = nullptr;
+    cudaEvent_t pair_fork = nullptr, pair_join = nullptr;
     int ev_threads = 128;              // event kernel: independent warps
     int epb = 1, ft_threads = 32;      // feature kernel: epb envs x A agent warps per block
     cudaStream_t copy_stream = nullptr;   // device->host copies of the chunked host-buffer step
@@ -366,6 +370,11 @@ static int launch_cfg(mlb_env* h) {
     h->d.use_pair = h->use_pair ? 1 : 0;
     h->d.pair_wpe = 1;
     h->pair_wpe_small = getenv("MLB_PAIR_WPE1") ? 1 : 4;    // A/B knob: 1 = never deal a list out to a block
+    if (h->use_pair && !h->pair_stream && !getenv("MLB_PAIR_SERIAL")) {
+        e = cudaStreamCreateWithFlags(&h->pair_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->pair_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->pair_join, cudaEventDisableTiming);
+    }
     h->pr_smem = (size_t)4 * pair_warp_smem_bytes(SP);
     if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent, 0), h->pr_smem, 128, 32);
     if (e == cudaSuccess && h->use_pair) e = set_smem(pair_fn(c.servers_per_agent, 1), h->pr_smem, 128, 32);
@@ -458,6 +467,9 @@ int mlb_destroy(mlb_env* h) {
     for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->pair_fork) cudaEventDestroy(h->pair_fork);
+    if (h->pair_join) cudaEventDestroy(h->pair_join);
+    if (h->pair_stream) cudaStreamDestroy(h->pair_stream);
     delete h->pool;
     for (cudaEvent_t e : h->cr_ev_cnt) cudaEventDestroy(e);
     for (cudaEvent_t e : h->cr_ev_copy) cudaEventDestroy(e);
@@ -888,8 +900,19 @@ static int launch_step(mlb_env* h, const void* dact, int e0, int e1, cudaStream_
         const int64_t pairs = (int64_t)(e1 - e0) * dv.A;
         dv.pair_wpe = pairs <= 8192 ? h->pair_wpe_small : 1;
         const int pr_blocks = (int)(dv.pair_wpe == 4 ? pairs : (pairs + 3) / 4);
+        const bool beside = dv.pair_wpe == 4 && h->pair_stream != nullptr;
+        cudaStream_t st1 = st;
+        if (beside) {
+            CK(h, cudaEventRecord(h->pair_fork, st));
+            CK(h, cudaStreamWaitEvent(h->pair_stream, h->pair_fork, 0));
+            st1 = h->pair_stream;
+        }
         CK(h, cudaLaunchKernel(pair_fn(dv.Sa, 0), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
-        CK(h, cudaLaunchKernel(pair_fn(dv.Sa, 1), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st));
+        CK(h, cudaLaunchKernel(pair_fn(dv.Sa, 1), dim3(pr_blocks), dim3(128), ft_args, h->pr_smem, st1));
+        if (beside) {
+            CK(h, cudaEventRecord(h->pair_join, h->pair_stream));
+            CK(h, cudaStreamWaitEvent(st, h->pair_join, 0));
+        }
         h->launches += 2;
     }
     if (pe) CK(h, cudaEventRecord(pe[2], st));

@@ -605,7 +605,11 @@ pair_kernel(const __grid_constant__ DevState d) {
             const uint32_t nchg = chg_count(chg);
             const uint32_t n = cnt < 128u ? cnt : 128u;
             const bool one = nchg == 1 && chg_nold(chg) == 128 && n == 128;
-            const bool inc = chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
+            // n_old == 255: pair_kernel<.,0> could not settle this one and handed it to feature_kernel.  On small launches
+            // the two pair kernels run side by side, so <.,1> may or may not see that mark yet -- either way the entry is
+            // not its own ("one" before the mark, "redo" after it).
+            const bool redo = chg_nold(chg) == 255u;
+            const bool inc = !redo && chg_nold(chg) > 0 && nchg >= 1 && nchg <= 3;
             const bool fast = j < Sa && (CLS == 0 ? one : (inc && !one));
             const unsigned bal = __ballot_sync(MLB_FULL, fast);
             if (fast) dlist[nfast + __popc(bal & ((1u << lane) - 1u))] = make_uint2(chg, (uint32_t)(j * 2 + m) | (n << 9));
